@@ -1,0 +1,195 @@
+"""CPU oracle package -- TEST INFRASTRUCTURE ONLY.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference``
+leg may import this package.  The product (``uapic.jl_b200``) never does.
+
+``corc``  : ctypes binding of ``uapic_oracle.c`` (Fortran-following restatement)
+``nporc`` : the numpy twin (Julia-following restatement)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from . import uapic_oracle_np as nporc  # noqa: F401
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "liboracle.so")
+
+WRAP_FORTRAN = 0
+WRAP_JULIA = 1
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "uapic_oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "liboracle.so"])
+    return _SO
+
+
+class OrcMesh(C.Structure):
+    _fields_ = [("xmin", C.c_double), ("xmax", C.c_double), ("ymin", C.c_double), ("ymax", C.c_double),
+                ("nx", C.c_int32), ("ny", C.c_int32)]
+
+    @property
+    def dx(self):
+        return (self.xmax - self.xmin) / self.nx
+
+    @property
+    def dy(self):
+        return (self.ymax - self.ymin) / self.ny
+
+
+def mesh(xmin, xmax, nx, ymin, ymax, ny) -> OrcMesh:
+    return OrcMesh(float(xmin), float(xmax), float(ymin), float(ymax), int(nx), int(ny))
+
+
+_dp = C.POINTER(C.c_double)
+
+
+def _p(a):
+    if a is None:
+        return None
+    assert isinstance(a, np.ndarray) and a.flags.f_contiguous or a.flags.c_contiguous
+    return a.ctypes.data_as(_dp)
+
+
+class _COracle:
+    """thin ctypes front-end; arrays are Fortran-ordered numpy arrays in the reference's shapes"""
+
+    def __init__(self):
+        self.lib = C.CDLL(build())
+        L = self.lib
+        L.orc_f_m6.restype = C.c_double
+        L.orc_f_m6.argtypes = [C.c_double]
+        L.orc_compute_rho_m6.restype = C.c_double
+        L.orc_compute_rho_m6_tau.restype = C.c_double
+        L.orc_poisson.restype = C.c_double
+        L.orc_run_bupdate.restype = C.c_int
+        L.orc_plasma_from_uniforms.restype = C.c_int64
+        L.orc_get_max_threads.restype = C.c_int
+
+    # -- helpers -------------------------------------------------------------------------------
+    def set_threads(self, n):
+        self.lib.orc_set_threads(C.c_int(int(n)))
+
+    def max_threads(self):
+        return int(self.lib.orc_get_max_threads())
+
+    def f_m6(self, q):
+        return float(self.lib.orc_f_m6(float(q)))
+
+    def ua_tables(self, ntau):
+        tau = np.zeros(ntau)
+        ltau = np.zeros(ntau)
+        self.lib.orc_ua_tables(C.c_int(ntau), _p(tau), _p(ltau))
+        return tau, ltau
+
+    def fft_tau(self, a, sign=-1, normalise=False):
+        a = np.asfortranarray(a, dtype=np.complex128)
+        out = np.empty_like(a, order="F")
+        ntau = a.shape[0]
+        nvec = a.size // ntau
+        self.lib.orc_fft_tau(C.c_int(ntau), C.c_int64(nvec), a.ctypes.data_as(_dp), out.ctypes.data_as(_dp),
+                             C.c_int(sign), C.c_int(int(normalise)))
+        return out
+
+    # -- mesh <-> particles --------------------------------------------------------------------
+    def compute_rho_m6(self, m, x, w, rho, wrap=WRAP_FORTRAN):
+        return self.lib.orc_compute_rho_m6(C.byref(m), C.c_int64(x.shape[1]), _p(x), C.c_double(w), _p(rho), C.c_int(wrap))
+
+    def interpol_eb_m6(self, m, e, x, ep, wrap=WRAP_FORTRAN):
+        self.lib.orc_interpol_eb_m6(C.byref(m), _p(e), C.c_int64(x.shape[1]), _p(x), _p(ep), C.c_int(wrap))
+
+    def interpol_eb_m6_tau(self, m, e, xt, et, wrap=WRAP_FORTRAN):
+        ntau, _, npart = xt.shape
+        self.lib.orc_interpol_eb_m6_tau(C.byref(m), _p(e), C.c_int(ntau), C.c_int64(npart), xt.ctypes.data_as(_dp), _p(et), C.c_int(wrap))
+
+    def compute_rho_m6_tau(self, m, eps, xt, t, w, rho, x, wrap=WRAP_FORTRAN):
+        ntau, _, npart = xt.shape
+        return self.lib.orc_compute_rho_m6_tau(C.byref(m), C.c_int(ntau), C.c_double(eps), C.c_int64(npart),
+                                               xt.ctypes.data_as(_dp), _p(t), C.c_double(w), _p(rho), _p(x), C.c_int(wrap))
+
+    def poisson(self, m, rho, e):
+        return self.lib.orc_poisson(C.byref(m), _p(rho), _p(e))
+
+    # -- UA stages -----------------------------------------------------------------------------
+    def preparation(self, ntau, eps, dt, x, v, ep):
+        npart = x.shape[1]
+        b = np.zeros(npart)
+        t = np.zeros(npart)
+        pl = np.zeros((ntau, npart), dtype=np.complex128, order="F")
+        ql = np.zeros((ntau, npart), dtype=np.complex128, order="F")
+        xt = np.zeros((ntau, 2, npart), dtype=np.complex128, order="F")
+        yt = np.zeros((ntau, 2, npart), dtype=np.complex128, order="F")
+        self.lib.orc_preparation(C.c_int(ntau), C.c_double(eps), C.c_double(dt), C.c_int64(npart), _p(x), _p(v), _p(ep),
+                                 _p(b), _p(t), pl.ctypes.data_as(_dp), ql.ctypes.data_as(_dp),
+                                 xt.ctypes.data_as(_dp), yt.ctypes.data_as(_dp))
+        return b, t, pl, ql, xt, yt
+
+    def compute_f(self, eps, b, xt, yt, et, normalise=True):
+        ntau, _, npart = xt.shape
+        fx = np.zeros_like(xt, order="F")
+        fy = np.zeros_like(xt, order="F")
+        self.lib.orc_compute_f(C.c_int(ntau), C.c_double(eps), C.c_int64(npart), _p(b), xt.ctypes.data_as(_dp),
+                               yt.ctypes.data_as(_dp), _p(et), fx.ctypes.data_as(_dp), fy.ctypes.data_as(_dp),
+                               C.c_int(int(normalise)))
+        return fx, fy
+
+    def ua_step1(self, eps, t, pl, xt, fx):
+        """in place on xt; returns xf"""
+        ntau, _, npart = xt.shape
+        xf = np.zeros_like(xt, order="F")
+        self.lib.orc_ua_step1(C.c_int(ntau), C.c_double(eps), C.c_int64(npart), _p(t), pl.ctypes.data_as(_dp),
+                              xt.ctypes.data_as(_dp), xf.ctypes.data_as(_dp), fx.ctypes.data_as(_dp))
+        return xf
+
+    def ua_step2(self, eps, t, pl, ql, xt, xf, fx, gx):
+        ntau, _, npart = xt.shape
+        self.lib.orc_ua_step2(C.c_int(ntau), C.c_double(eps), C.c_int64(npart), _p(t), pl.ctypes.data_as(_dp),
+                              ql.ctypes.data_as(_dp), xt.ctypes.data_as(_dp), xf.ctypes.data_as(_dp),
+                              fx.ctypes.data_as(_dp), gx.ctypes.data_as(_dp))
+
+    def compute_v(self, eps, t, yt, v):
+        ntau, _, npart = yt.shape
+        yf = np.zeros_like(yt, order="F")
+        self.lib.orc_compute_v(C.c_int(ntau), C.c_double(eps), C.c_int64(npart), _p(t), yt.ctypes.data_as(_dp),
+                               yf.ctypes.data_as(_dp), _p(v))
+        return yf
+
+    # -- driver --------------------------------------------------------------------------------
+    def run_bupdate(self, m, ntau, eps, dt, nstep, x, v, w, wrap=WRAP_FORTRAN, faithful=False):
+        """x, v: (2,np) Fortran-ordered float64, updated in place.  returns (energy, sumv, e_part, e_mesh)"""
+        npart = x.shape[1]
+        energy = np.zeros(1 + 2 * nstep)
+        sumv = np.zeros((nstep, 2))
+        ep = np.zeros((2, npart), order="F")
+        emesh = np.zeros((2, m.nx + 1, m.ny + 1), order="F")
+        rc = self.lib.orc_run_bupdate(C.byref(m), C.c_int(ntau), C.c_double(eps), C.c_double(dt), C.c_int(nstep),
+                                      C.c_int64(npart), C.c_double(w), _p(x), _p(v), _p(ep), _p(emesh), _p(energy),
+                                      _p(sumv), C.c_int(wrap), C.c_int(int(faithful)))
+        if rc != 0:
+            raise RuntimeError(f"orc_run_bupdate failed rc={rc}")
+        return energy, sumv, ep, emesh
+
+    def plasma_from_uniforms(self, m, npart, alpha, kx, u):
+        x = np.zeros((2, npart), order="F")
+        v = np.zeros((2, npart), order="F")
+        used = self.lib.orc_plasma_from_uniforms(C.byref(m), C.c_int64(npart), C.c_double(alpha), C.c_double(kx),
+                                                 _p(u), C.c_int64(u.size), _p(x), _p(v))
+        if used < 0:
+            raise RuntimeError("not enough uniform deviates")
+        return x, v, int(used)
+
+
+_corc = None
+
+
+def corc() -> _COracle:
+    global _corc
+    if _corc is None:
+        _corc = _COracle()
+    return _corc

@@ -1,0 +1,840 @@
+/*
+ * uapic_oracle.c  --  CPU ORACLE (test infrastructure, NOT the product).
+ *
+ * A plain-C restatement of the UA-PIC hot path of JuliaVlasov/UAPIC.jl, following the
+ * Fortran `bupdate` program statement by statement (operation order included).  Only
+ * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may
+ * load this file's shared object; the CUDA product path never does.
+ *
+ * PARITY STATUS: the reference holds no golden vector for the end-to-end run and neither
+ * a Fortran compiler, Julia nor FFTW exist in this image, so positions / velocities /
+ * energy history are "parity unpinned" by the reference itself.  What *is* pinned:
+ *   - test/test_poisson.jl:28,47       (Poisson vs analytic, atol 1e-14)
+ *   - test/test_particles.jl:45        (integral of rho ~ 0)
+ *   - test/test_particles.jl:73-74     (M6 interpolation reproduces a linear field)
+ * and an independently written numpy twin (oracle/uapic_oracle_np.py, following the Julia
+ * sources) must agree with this file to <= 1e-12 (tests/test_oracle.py).
+ *
+ * Every function cites the reference lines it follows.  FFTs: FFTW is a third-party
+ * dependency absent from /root/reference (Project.toml:8 `FFTW`, fortran/Makefile:7
+ * `-lfftw3`, version unpinned); a DFT is mathematically unique, so an own radix-2 /
+ * direct DFT is used, and FFTW's c2r treatment of non-Hermitian input is reproduced
+ * explicitly (see orc_poisson).
+ *
+ * Arrays use the reference's column-major layouts:
+ *   xt, yt, fx, ... : complex(8) (ntau, 2, nbpart)  -> interleaved re,im, tau fastest
+ *   et              : real(8)    (ntau, 2, nbpart)
+ *   x, v, e         : real(8)    (2, nbpart)
+ *   mesh e          : real(8)    (2, nx+1, ny+1)
+ *   mesh rho        : real(8)    (nx+1, ny+1)
+ *
+ * Build: see oracle/Makefile  (gcc -O2 -ffp-contract=off -fopenmp; no fast-math, no FMA
+ * contraction: gfortran -O3 on baseline x86-64 does not fuse either).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdio.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+typedef struct { double re, im; } cplx;
+
+static inline cplx c_make(double re, double im) { cplx z = { re, im }; return z; }
+static inline cplx c_add(cplx a, cplx b) { return c_make(a.re + b.re, a.im + b.im); }
+static inline cplx c_sub(cplx a, cplx b) { return c_make(a.re - b.re, a.im - b.im); }
+/* complex * complex as gfortran emits it (no NaN recovery needed for finite data) */
+static inline cplx c_mul(cplx a, cplx b) { return c_make(a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re); }
+static inline cplx c_rmul(double r, cplx a) { return c_make(r * a.re, r * a.im); }
+static inline cplx c_rdiv(cplx a, double r) { return c_make(a.re / r, a.im / r); }
+/* exp((0,phi)) -> cexp: exp(0)*(cos, sin) */
+static inline cplx c_expi(double phi) { return c_make(cos(phi), sin(phi)); }
+
+#define ORC_WRAP_FORTRAN 0   /* px = x/dx ; px = modulo(px, nx)          (compute_rho_m6.F90:89-93)  */
+#define ORC_WRAP_JULIA   1   /* x  = mod(x-xmin, dimx) ; px = x/dx        (src/compute_rho.jl:63-67)  */
+
+typedef struct {
+    double xmin, xmax, ymin, ymax;
+    int32_t nx, ny;
+} orc_mesh;
+
+static int g_threads = 1;
+
+void orc_set_threads(int n)
+{
+    if (n < 1) n = 1;
+    g_threads = n;
+#ifdef _OPENMP
+    omp_set_num_threads(n);
+#endif
+}
+
+int orc_get_max_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_num_procs();
+#else
+    return 1;
+#endif
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* FFT (stand-in for FFTW's unnormalised complex DFT, sign -1 forward / +1 backward)     */
+/* ------------------------------------------------------------------------------------ */
+
+typedef struct {
+    int n;
+    int pow2;
+    cplx *w;       /* w[k] = exp(-2 pi i k / n), k = 0..n-1 */
+    int *brev;
+} orc_fft_plan;
+
+static orc_fft_plan *orc_fft_new(int n)
+{
+    orc_fft_plan *p = (orc_fft_plan *)malloc(sizeof(*p));
+    p->n = n;
+    p->pow2 = (n > 0) && ((n & (n - 1)) == 0);
+    p->w = (cplx *)malloc(sizeof(cplx) * (size_t)n);
+    p->brev = (int *)malloc(sizeof(int) * (size_t)n);
+    const double pi = 4.0 * atan(1.0);
+    for (int k = 0; k < n; k++) {
+        double a = -2.0 * pi * (double)k / (double)n;
+        p->w[k] = c_make(cos(a), sin(a));
+    }
+    /* exact values on the axes / diagonals keep the transform of smooth data clean */
+    if (n % 4 == 0) { p->w[n / 4] = c_make(0.0, -1.0); p->w[3 * n / 4] = c_make(0.0, 1.0); }
+    if (n % 2 == 0) { p->w[n / 2] = c_make(-1.0, 0.0); }
+    int bits = 0;
+    while ((1 << bits) < n) bits++;
+    for (int i = 0; i < n; i++) {
+        int r = 0;
+        for (int b = 0; b < bits; b++) if (i & (1 << b)) r |= 1 << (bits - 1 - b);
+        p->brev[i] = r;
+    }
+    return p;
+}
+
+static void orc_fft_free(orc_fft_plan *p) { if (p) { free(p->w); free(p->brev); free(p); } }
+
+/* out-of-place capable (in may equal out); stride in elements; sign = -1 fwd, +1 bwd */
+static void orc_fft_exec(const orc_fft_plan *p, const cplx *in, int istride, cplx *out, int ostride, int sign)
+{
+    const int n = p->n;
+    cplx stackbuf[512];
+    cplx *buf = (n <= 512) ? stackbuf : (cplx *)malloc(sizeof(cplx) * (size_t)n);
+    if (p->pow2) {
+        for (int i = 0; i < n; i++) buf[p->brev[i]] = in[(size_t)i * istride];
+        for (int len = 2; len <= n; len <<= 1) {
+            int half = len >> 1, step = n / len;
+            for (int s = 0; s < n; s += len) {
+                for (int k = 0; k < half; k++) {
+                    cplx w = p->w[k * step];
+                    if (sign > 0) w.im = -w.im;
+                    cplx a = buf[s + k];
+                    cplx b = c_mul(w, buf[s + k + half]);
+                    buf[s + k] = c_add(a, b);
+                    buf[s + k + half] = c_sub(a, b);
+                }
+            }
+        }
+        for (int i = 0; i < n; i++) out[(size_t)i * ostride] = buf[i];
+    } else {
+        cplx tmp2[512];
+        cplx *src = (n <= 512) ? tmp2 : (cplx *)malloc(sizeof(cplx) * (size_t)n);
+        for (int i = 0; i < n; i++) src[i] = in[(size_t)i * istride];
+        for (int k = 0; k < n; k++) {
+            cplx acc = c_make(0.0, 0.0);
+            for (int j = 0; j < n; j++) {
+                cplx w = p->w[(int)(((int64_t)k * j) % n)];
+                if (sign > 0) w.im = -w.im;
+                acc = c_add(acc, c_mul(w, src[j]));
+            }
+            buf[k] = acc;
+        }
+        for (int i = 0; i < n; i++) out[(size_t)i * ostride] = buf[i];
+        if (n > 512) free(src);
+    }
+    if (n > 512) free(buf);
+}
+
+/* exported for tests of the tau FFT (mul!(x̃t, ftau, xt) / ifft!(xt,1) in test/bupdate.jl:79,85) */
+void orc_fft_tau(int ntau, int64_t nvec, const double *in, double *out, int sign, int normalise)
+{
+    orc_fft_plan *p = orc_fft_new(ntau);
+    for (int64_t k = 0; k < nvec; k++) {
+        orc_fft_exec(p, (const cplx *)in + k * ntau, 1, (cplx *)out + k * ntau, 1, sign);
+        if (normalise) {
+            cplx *o = (cplx *)out + k * ntau;
+            for (int n = 0; n < ntau; n++) o[n] = c_rdiv(o[n], (double)ntau);
+        }
+    }
+    orc_fft_free(p);
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* ua_t : tau grid and wavenumbers      fortran/ua_type.F90:32-76, src/ua_type.jl:17-41  */
+/* ------------------------------------------------------------------------------------ */
+
+void orc_ua_tables(int ntau, double *tau, double *ltau)
+{
+    const double pi = 4.0 * atan(1.0);
+    double dtau = 2.0 * pi / (double)ntau;                      /* ua_type.F90:47 */
+    for (int n = 1; n <= ntau / 2; n++) ltau[n - 1] = (double)(n - 1);          /* :51-53 */
+    for (int n = ntau / 2 + 1; n <= ntau; n++) ltau[n - 1] = (double)(n - 1 - ntau); /* :54-56 */
+    for (int n = 1; n <= ntau; n++) tau[n - 1] = (double)(n - 1) * dtau;         /* :60-62 */
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* M6 kernel                       fortran/compute_rho_m6.F90:28-45, src/compute_rho.jl:10-25 */
+/* ------------------------------------------------------------------------------------ */
+
+static inline double pow5(double x) { double x2 = x * x; double x4 = x2 * x2; return x4 * x; }
+
+static inline double f_m6(double q)
+{
+    double f;
+    if (q < 1.0)                      f = pow5(3.0 - q) - 6.0 * pow5(2.0 - q) + 15.0 * pow5(1.0 - q);
+    else if (q >= 1.0 && q < 2.0)     f = pow5(3.0 - q) - 6.0 * pow5(2.0 - q);
+    else if (q >= 2.0 && q < 3.0)     f = pow5(3.0 - q);
+    else                              f = 0.0;
+    return f / 120.0;
+}
+
+double orc_f_m6(double q) { return f_m6(q); }
+
+/* Fortran MODULO / Julia mod for reals: result has the sign of p */
+static inline double f_modulo(double a, double p)
+{
+    double r = fmod(a, p);
+    if (r != 0.0 && ((r < 0.0) != (p < 0.0))) r += p;
+    return r;
+}
+static inline int i_modulo(int a, int p) { int r = a % p; if (r != 0 && ((r < 0) != (p < 0))) r += p; return r; }
+
+typedef struct {
+    int ix[7], jy[7];   /* 0-based wrapped node indices for offsets -3..3 (centre = i, which may be nx: edge case) */
+    double cx[7], cy[7];
+} m6_stencil;
+
+/* cell + weights: compute_rho_m6.F90:89-131 / interpolation_m6.F90:87-127 (Fortran wrap);
+   src/compute_rho.jl:63-73 / src/interpolation.jl:19-29 (Julia wrap).  xw/yw return the position
+   the Julia variant stores back into particles.x */
+static inline void m6_setup(const orc_mesh *m, double dx, double dy, double x, double y, int wrap,
+                            m6_stencil *s, double *xw, double *yw)
+{
+    const int nx = m->nx, ny = m->ny;
+    double px, py;
+    if (wrap == ORC_WRAP_JULIA) {
+        double dimx = m->xmax - m->xmin, dimy = m->ymax - m->ymin;
+        double xn = f_modulo(x - m->xmin, dimx);
+        double yn = f_modulo(y - m->ymin, dimy);
+        px = xn / dx; py = yn / dy;
+        if (xw) { *xw = xn + m->xmin; *yw = yn + m->ymin; }
+    } else {
+        px = x / dx; py = y / dy;
+        px = f_modulo(px, (double)nx);
+        py = f_modulo(py, (double)ny);
+        if (xw) { *xw = x; *yw = y; }
+    }
+    int i = (int)floor(px); double dpx = px - (double)i;
+    int j = (int)floor(py); double dpy = py - (double)j;
+    for (int a = -3; a <= 3; a++) {
+        s->ix[a + 3] = (a == 0) ? i : i_modulo(i + a, nx);   /* centre index is i+1 (1-based), NOT wrapped */
+        s->jy[a + 3] = (a == 0) ? j : i_modulo(j + a, ny);
+    }
+    s->cx[0] = f_m6(3.0 + dpx); s->cx[6] = f_m6(3.0 - dpx);
+    s->cx[1] = f_m6(2.0 + dpx); s->cx[5] = f_m6(2.0 - dpx);
+    s->cx[2] = f_m6(1.0 + dpx); s->cx[4] = f_m6(1.0 - dpx);
+    s->cx[3] = f_m6(dpx);
+    s->cy[0] = f_m6(3.0 + dpy); s->cy[6] = f_m6(3.0 - dpy);
+    s->cy[1] = f_m6(2.0 + dpy); s->cy[5] = f_m6(2.0 - dpy);
+    s->cy[2] = f_m6(1.0 + dpy); s->cy[4] = f_m6(1.0 - dpy);
+    s->cy[3] = f_m6(dpy);
+}
+
+/* 49-term sequential sum, x offset outer, y offset inner: interpolation_m6.F90:130-183 */
+static inline void m6_gather(const orc_mesh *m, const double *emesh, const m6_stencil *s, double *e1, double *e2)
+{
+    const size_t ld = (size_t)(m->nx + 1);
+    for (int l = 0; l < 2; l++) {
+        double acc = 0.0;
+        for (int a = 0; a < 7; a++)
+            for (int b = 0; b < 7; b++)
+                acc = acc + s->cx[a] * s->cy[b] * emesh[l + 2 * ((size_t)s->ix[a] + ld * (size_t)s->jy[b])];
+        if (l == 0) *e1 = acc; else *e2 = acc;
+    }
+}
+
+/* 49 read-modify-writes: compute_rho_m6.F90:133-187 */
+static inline void m6_scatter(const orc_mesh *m, double *rho, const m6_stencil *s, double weight)
+{
+    const size_t ld = (size_t)(m->nx + 1);
+    for (int a = 0; a < 7; a++)
+        for (int b = 0; b < 7; b++)
+            rho[(size_t)s->ix[a] + ld * (size_t)s->jy[b]] += s->cx[a] * s->cy[b] * weight;
+}
+
+/* epilogue: ghost copy -> /(dx dy) -> subtract mean   compute_rho_m6.F90:191-200 */
+static double rho_epilogue(const orc_mesh *m, double *rho)
+{
+    const int nx = m->nx, ny = m->ny;
+    const size_t ld = (size_t)(nx + 1);
+    const double dx = (m->xmax - m->xmin) / (double)nx, dy = (m->ymax - m->ymin) / (double)ny;
+    const double dimx = m->xmax - m->xmin, dimy = m->ymax - m->ymin;
+    for (int i = 0; i < nx; i++) rho[i + ld * ny] = rho[i];
+    for (int j = 0; j < ny; j++) rho[nx + ld * j] = rho[ld * j];
+    rho[nx + ld * ny] = rho[0];
+    const double dxdy = dx * dy;
+    for (size_t k = 0; k < ld * (size_t)(ny + 1); k++) rho[k] = rho[k] / dxdy;
+    double tot = 0.0;
+    for (int j = 0; j < ny; j++) for (int i = 0; i < nx; i++) tot += rho[i + ld * j];  /* column-major sum */
+    double rho_total = tot * dx * dy;
+    double sub = rho_total / dimx / dimy;
+    for (size_t k = 0; k < ld * (size_t)(ny + 1); k++) rho[k] = rho[k] - sub;
+    return rho_total;
+}
+
+static inline double mesh_dx(const orc_mesh *m) { return (m->xmax - m->xmin) / (double)m->nx; }  /* meshfields.F90:71 */
+static inline double mesh_dy(const orc_mesh *m) { return (m->ymax - m->ymin) / (double)m->ny; }  /* meshfields.F90:72 */
+
+/* private-rho helper for the threaded deposit: thread-ordered reduction keeps results deterministic
+   for a fixed thread count; with 1 thread the summation order is exactly the reference's */
+typedef void (*deposit_body)(int64_t k, double *rho, void *ctx);
+
+static void deposit_driver(const orc_mesh *m, int64_t np, double *rho, deposit_body body, void *ctx)
+{
+    const size_t nrho = (size_t)(m->nx + 1) * (size_t)(m->ny + 1);
+    memset(rho, 0, sizeof(double) * nrho);
+    if (g_threads <= 1) {
+        for (int64_t k = 0; k < np; k++) body(k, rho, ctx);
+        return;
+    }
+#ifdef _OPENMP
+    int nt = g_threads;
+    double *priv = (double *)calloc(nrho * (size_t)nt, sizeof(double));
+    #pragma omp parallel num_threads(nt)
+    {
+        int tid = omp_get_thread_num();
+        int64_t lo = np * tid / nt, hi = np * (tid + 1) / nt;
+        double *r = priv + nrho * (size_t)tid;
+        for (int64_t k = lo; k < hi; k++) body(k, r, ctx);
+    }
+    for (int t = 0; t < nt; t++) for (size_t q = 0; q < nrho; q++) rho[q] += priv[nrho * (size_t)t + q];
+    free(priv);
+#else
+    for (int64_t k = 0; k < np; k++) body(k, rho, ctx);
+#endif
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* compute_rho_m6_real        fortran/compute_rho_m6.F90:205-335, src/compute_rho.jl:181-316 */
+/* ------------------------------------------------------------------------------------ */
+
+typedef struct { const orc_mesh *m; double *x; double w; int wrap; double dx, dy; } dep_real_ctx;
+
+static void dep_real_body(int64_t k, double *rho, void *vctx)
+{
+    dep_real_ctx *c = (dep_real_ctx *)vctx;
+    m6_stencil s; double xw, yw;
+    m6_setup(c->m, c->dx, c->dy, c->x[2 * k], c->x[2 * k + 1], c->wrap, &s, &xw, &yw);
+    if (c->wrap == ORC_WRAP_JULIA) { c->x[2 * k] = xw; c->x[2 * k + 1] = yw; }
+    m6_scatter(c->m, rho, &s, c->w);
+}
+
+/* returns rho_total (the value both languages print).  NOTE the Julia method swaps xmin/xmax
+   (src/compute_rho.jl:190-191) which only shifts the stored x by one period; the oracle's Julia
+   variant stores the in-box position instead (documented deviation, periodic-equivalent). */
+double orc_compute_rho_m6(const orc_mesh *m, int64_t np, double *x, double w, double *rho, int wrap)
+{
+    dep_real_ctx c = { m, x, w, wrap, mesh_dx(m), mesh_dy(m) };
+    deposit_driver(m, np, rho, dep_real_body, &c);
+    return rho_epilogue(m, rho);
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* interpolate_eb_m6_real     fortran/interpolation_m6.F90:193-327, src/interpolation.jl:125-247 */
+/* ------------------------------------------------------------------------------------ */
+
+void orc_interpol_eb_m6(const orc_mesh *m, const double *emesh, int64_t np, double *x, double *ep, int wrap)
+{
+    const double dx = mesh_dx(m), dy = mesh_dy(m);
+    #pragma omp parallel for schedule(static) if (g_threads > 1)
+    for (int64_t k = 0; k < np; k++) {
+        m6_stencil s; double xw, yw;
+        m6_setup(m, dx, dy, x[2 * k], x[2 * k + 1], wrap, &s, &xw, &yw);
+        if (wrap == ORC_WRAP_JULIA) { x[2 * k] = xw; x[2 * k + 1] = yw; }   /* src/interpolation.jl:152-153 */
+        m6_gather(m, emesh, &s, &ep[2 * k], &ep[2 * k + 1]);
+    }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* interpolate_eb_m6_complex  fortran/interpolation_m6.F90:40-191, src/interpolation.jl:3-123 */
+/* ------------------------------------------------------------------------------------ */
+
+void orc_interpol_eb_m6_tau(const orc_mesh *m, const double *emesh, int ntau, int64_t np,
+                            const double *xt, double *et, int wrap)
+{
+    const double dx = mesh_dx(m), dy = mesh_dy(m);
+    const cplx *X = (const cplx *)xt;
+    #pragma omp parallel for schedule(static) if (g_threads > 1)
+    for (int64_t k = 0; k < np; k++) {
+        for (int n = 0; n < ntau; n++) {
+            m6_stencil s;
+            double xr = X[n + (size_t)ntau * (0 + 2 * k)].re;          /* real(x(n,1,k)) :87 */
+            double yr = X[n + (size_t)ntau * (1 + 2 * k)].re;          /* real(x(n,2,k)) :88 */
+            m6_setup(m, dx, dy, xr, yr, wrap, &s, NULL, NULL);
+            m6_gather(m, emesh, &s, &et[n + (size_t)ntau * (0 + 2 * k)], &et[n + (size_t)ntau * (1 + 2 * k)]);
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* compute_rho_m6_complex     fortran/compute_rho_m6.F90:47-203, src/compute_rho.jl:29-179   */
+/* ------------------------------------------------------------------------------------ */
+
+typedef struct {
+    const orc_mesh *m; int ntau; double eps; const cplx *xt; const double *t; double *x; double w; int wrap;
+    const double *ltau; orc_fft_plan *plan; double dx, dy;
+} dep_tau_ctx;
+
+static void dep_tau_body(int64_t k, double *rho, void *vctx)
+{
+    dep_tau_ctx *c = (dep_tau_ctx *)vctx;
+    const int N = c->ntau;
+    cplx ft[64];
+    double pos[2];
+    const double t = c->t[k];
+    for (int comp = 0; comp < 2; comp++) {
+        orc_fft_exec(c->plan, c->xt + (size_t)N * (comp + 2 * k), 1, ft, 1, -1);        /* :74, :80 */
+        cplx sum = c_make(0.0, 0.0);
+        for (int n = 0; n < N; n++) {
+            /* exp(cmplx(0,1)*ltau*t/eps)/cmplx(ntau,0)    :76, :82 */
+            cplx el = c_expi(c->ltau[n] * t / c->eps);
+            ft[n] = c_rdiv(c_mul(ft[n], el), (double)N);     /* (ft*exp)/ntau, left to right */
+        }
+        for (int n = 0; n < N; n++) sum = c_add(sum, ft[n]);                             /* sum(ua%ft) :78 */
+        pos[comp] = sum.re;
+    }
+    m6_stencil s; double xw, yw;
+    m6_setup(c->m, c->dx, c->dy, pos[0], pos[1], c->wrap, &s, &xw, &yw);
+    c->x[2 * k] = xw; c->x[2 * k + 1] = yw;       /* Fortran: unwrapped (:86-87); Julia: wrapped (src/compute_rho.jl:69-70) */
+    m6_scatter(c->m, rho, &s, c->w);
+}
+
+double orc_compute_rho_m6_tau(const orc_mesh *m, int ntau, double eps, int64_t np, const double *xt,
+                              const double *t, double w, double *rho, double *x, int wrap)
+{
+    double tau[64], ltau[64];
+    if (ntau > 64) return NAN;
+    orc_ua_tables(ntau, tau, ltau);
+    orc_fft_plan *plan = orc_fft_new(ntau);
+    dep_tau_ctx c = { m, ntau, eps, (const cplx *)xt, t, x, w, wrap, ltau, plan, mesh_dx(m), mesh_dy(m) };
+    deposit_driver(m, np, rho, dep_tau_body, &c);
+    orc_fft_free(plan);
+    return rho_epilogue(m, rho);
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* Poisson                         fortran/poisson_2d.f90:30-111, src/poisson.jl:14-83        */
+/* ------------------------------------------------------------------------------------ */
+/* FFTW semantics reproduced: r2c with x (first Fortran dim) halved; c2r = complex inverse DFT
+   along y for every kx column, then a 1-D c2r along x that ignores Im of the kx=0 and kx=nx/2
+   bins (what FFTW's rdft2 and pocketfft's irfftn do on non-Hermitian input).                 */
+
+double orc_poisson(const orc_mesh *m, const double *rho, double *e)
+{
+    const int nx = m->nx, ny = m->ny, nh = nx / 2 + 1;
+    const size_t ld = (size_t)(nx + 1);
+    const double pi = 4.0 * atan(1.0);
+    const double dx = mesh_dx(m), dy = mesh_dy(m);
+    const double kx0 = 2.0 * pi / (m->xmax - m->xmin);     /* poisson_2d.f90:48 */
+    const double ky0 = 2.0 * pi / (m->ymax - m->ymin);     /* :49 */
+
+    orc_fft_plan *px = orc_fft_new(nx), *py = orc_fft_new(ny);
+    cplx *rk = (cplx *)malloc(sizeof(cplx) * (size_t)nh * ny);
+    cplx *ek = (cplx *)malloc(sizeof(cplx) * (size_t)nh * ny);
+    cplx *row = (cplx *)malloc(sizeof(cplx) * (size_t)(nx > ny ? nx : ny));
+    cplx *rowo = (cplx *)malloc(sizeof(cplx) * (size_t)(nx > ny ? nx : ny));
+
+    /* forward r2c: x first, then y   (:96) */
+    for (int j = 0; j < ny; j++) {
+        for (int i = 0; i < nx; i++) row[i] = c_make(rho[i + ld * j], 0.0);
+        orc_fft_exec(px, row, 1, rowo, 1, -1);
+        for (int i = 0; i < nh; i++) rk[i + (size_t)nh * j] = rowo[i];
+    }
+    for (int i = 0; i < nh; i++) orc_fft_exec(py, rk + i, nh, rk + i, nh, -1);
+
+    for (int comp = 0; comp < 2; comp++) {
+        for (int jk = 0; jk < ny; jk++) {
+            for (int ik = 0; ik < nh; ik++) {
+                double kx = (double)ik * kx0;                                        /* :59 */
+                double ky = (jk < ny / 2) ? (double)jk * ky0 : (double)(jk - ny) * ky0; /* :62, :66 */
+                if (ik == 0 && jk == 0) kx = 1.0;                                    /* :70 */
+                double k2 = kx * kx + ky * ky;                                       /* :71 */
+                double kk = (comp == 0 ? kx : ky) / k2;                              /* :72-73 */
+                /* (0,-1) * kk * rho_hat    :98-99 */
+                cplx r = rk[ik + (size_t)nh * jk];
+                cplx mk = c_make(0.0 * kk, -1.0 * kk);          /* cmplx(0,-1)*k  (k complex with zero imag) */
+                ek[ik + (size_t)nh * jk] = c_mul(mk, r);
+            }
+        }
+        /* c2r: inverse along y per kx column, then c2r along x   (:101-102) */
+        for (int i = 0; i < nh; i++) orc_fft_exec(py, ek + i, nh, ek + i, nh, +1);
+        for (int j = 0; j < ny; j++) {
+            for (int i = 0; i < nh; i++) row[i] = ek[i + (size_t)nh * j];
+            row[0].im = 0.0;
+            if ((nx & 1) == 0) row[nh - 1].im = 0.0;
+            for (int i = nh; i < nx; i++) row[i] = c_make(row[nx - i].re, -row[nx - i].im);
+            orc_fft_exec(px, row, 1, rowo, 1, +1);
+            for (int i = 0; i < nx; i++) e[comp + 2 * ((size_t)i + ld * j)] = rowo[i].re;
+        }
+    }
+    /* ghosts (:104-107) in the reference's statement order, then /(nx*ny) (:109) */
+    for (int comp = 0; comp < 2; comp++) {
+        for (int j = 0; j <= ny; j++) e[comp + 2 * ((size_t)nx + ld * j)] = e[comp + 2 * (0 + ld * j)];
+        for (int i = 0; i <= nx; i++) e[comp + 2 * ((size_t)i + ld * ny)] = e[comp + 2 * ((size_t)i + ld * 0)];
+    }
+    const double nn = (double)(nx * ny);
+    /* interior was produced unnormalised; ghosts were copied from unnormalised interior */
+    for (size_t k = 0; k < 2 * ld * (size_t)(ny + 1); k++) e[k] = e[k] / nn;
+
+    /* energy  src/poisson.jl:80-81 : sum over the full ghosted array of e1^2+e2^2, times dx*dy */
+    double nrj = 0.0;
+    for (size_t k = 0; k < ld * (size_t)(ny + 1); k++) nrj += e[2 * k] * e[2 * k] + e[2 * k + 1] * e[2 * k + 1];
+    nrj = nrj * dx * dy;
+
+    free(rk); free(ek); free(row); free(rowo); orc_fft_free(px); orc_fft_free(py);
+    return nrj;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* preparation                      fortran/ua_steps.F90:15-115, src/ua_steps.jl:3-78       */
+/* ------------------------------------------------------------------------------------ */
+
+void orc_preparation(int ntau, double eps, double dt, int64_t np, const double *x, const double *v, const double *e,
+                     double *b_out, double *t_out, double *pl_, double *ql_, double *xt_, double *yt_)
+{
+    const int N = ntau;
+    double tau[64], ltau[64];
+    orc_ua_tables(N, tau, ltau);
+    cplx *PL = (cplx *)pl_, *QL = (cplx *)ql_, *XT = (cplx *)xt_, *YT = (cplx *)yt_;
+
+    #pragma omp parallel if (g_threads > 1)
+    {
+    orc_fft_plan *plan = orc_fft_new(N);
+    cplx rt[2][64], rf[2][64];
+    #pragma omp for schedule(static)
+    for (int64_t m = 0; m < np; m++) {
+        double x1 = x[2 * m], x2 = x[2 * m + 1];                                  /* :51-52 */
+        double b = 1.0 + 0.5 * sin(x1) * sin(x2);                                 /* :54 */
+        double t = dt * b;                                                        /* :55 */
+        b_out[m] = b; t_out[m] = t;                                               /* :57-58 */
+
+        PL[(size_t)N * m] = c_make(t, 0.0);                                       /* :60 */
+        QL[(size_t)N * m] = c_make(t * t / 2.0, 0.0);                             /* :61 */
+        for (int n = 1; n < N; n++) {
+            double l = ltau[n];
+            /* elt = exp((0,-1)*ltau(n)*t/eps)    :64 */
+            cplx elt = c_expi(((-1.0 * l) * t) / eps);
+            /* pl = eps*(0,1)*(elt-1)/ltau(n)     :65 */
+            cplx em1 = c_make(elt.re - 1.0, elt.im);
+            cplx ie = c_make(eps * 0.0, eps * 1.0);                              /* eps * cmplx(0,1) */
+            PL[n + (size_t)N * m] = c_rdiv(c_mul(ie, em1), l);
+            /* ql = eps*(eps*(1-elt) - (0,1)*ltau(n)*t)/ltau(n)**2     :66 */
+            cplx ome = c_make(1.0 - elt.re, -elt.im);
+            cplx a = c_rmul(eps, ome);
+            cplx ilt = c_make(0.0 * l * t, (1.0 * l) * t);
+            cplx d = c_sub(a, ilt);
+            QL[n + (size_t)N * m] = c_rdiv(c_rmul(eps, d), l * l);
+        }
+
+        double ex = e[2 * m], ey = e[2 * m + 1];                                  /* :69-70 */
+        double vx = v[2 * m], vy = v[2 * m + 1];                                  /* :71-72 */
+        double vxb = vx / b, vyb = vy / b;                                        /* :73-74 */
+
+        for (int n = 0; n < N; n++) {
+            double st = sin(tau[n]), ct = cos(tau[n]);
+            double h1 = eps * (st * vxb - ct * vyb);                              /* :78 */
+            double h2 = eps * (st * vyb + ct * vxb);                              /* :79 */
+            double xt1 = x1 + h1 + eps * vyb;                                     /* :81 */
+            double xt2 = x2 + h2 - eps * vxb;                                     /* :82 */
+            XT[n + (size_t)N * (0 + 2 * m)] = c_make(xt1, 0.0);                   /* :84 */
+            XT[n + (size_t)N * (1 + 2 * m)] = c_make(xt2, 0.0);                   /* :85 */
+            double interv = (1.0 + 0.5 * sin(xt1) * sin(xt2) - b) / eps;          /* :87 */
+            double exb = ((ct * vy - st * vx) * interv + ex) / b;                 /* :89 */
+            double eyb = ((-ct * vx - st * vy) * interv + ey) / b;                /* :90 */
+            rt[0][n] = c_make(ct * exb - st * eyb, 0.0);                          /* :92 */
+            rt[1][n] = c_make(st * exb + ct * eyb, 0.0);                          /* :93 */
+        }
+        orc_fft_exec(plan, rt[0], 1, rf[0], 1, -1);                               /* :97 */
+        orc_fft_exec(plan, rt[1], 1, rf[1], 1, -1);                               /* :98 */
+        for (int n = 1; n < N; n++) {
+            /* rf = -(0,1)/ltau(n) * rf / ntau     :101-102 */
+            cplx mil = c_make(-0.0 / ltau[n], -1.0 / ltau[n]);
+            rf[0][n] = c_rdiv(c_mul(mil, rf[0][n]), (double)N);
+            rf[1][n] = c_rdiv(c_mul(mil, rf[1][n]), (double)N);
+        }
+        orc_fft_exec(plan, rf[0], 1, rt[0], 1, +1);                               /* :105 */
+        orc_fft_exec(plan, rf[1], 1, rt[1], 1, +1);                               /* :106 */
+        for (int n = 0; n < N; n++) {
+            /* yt = v + (rt(n) - rt(1)) * eps      :109-110 */
+            cplx d0 = c_rmul(eps, c_sub(rt[0][n], rt[0][0]));
+            cplx d1 = c_rmul(eps, c_sub(rt[1][n], rt[1][0]));
+            YT[n + (size_t)N * (0 + 2 * m)] = c_make(vx + d0.re, d0.im);
+            YT[n + (size_t)N * (1 + 2 * m)] = c_make(vy + d1.re, d1.im);
+        }
+    }
+    orc_fft_free(plan);
+    }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* compute_f                        fortran/ua_steps.F90:140-198, src/ua_steps.jl:105-145   */
+/* normalise=1: Fortran (FFT then /ntau, :194-195); normalise=0: Julia (fft! only, :142-143) */
+/* ------------------------------------------------------------------------------------ */
+
+void orc_compute_f(int ntau, double eps, int64_t np, const double *b_, const double *xt_, const double *yt_,
+                   const double *et, double *fx_, double *fy_, int normalise)
+{
+    const int N = ntau;
+    double tau[64], ltau[64];
+    orc_ua_tables(N, tau, ltau);
+    const cplx *XT = (const cplx *)xt_, *YT = (const cplx *)yt_;
+    cplx *FX = (cplx *)fx_, *FY = (cplx *)fy_;
+    #pragma omp parallel if (g_threads > 1)
+    {
+    orc_fft_plan *plan = orc_fft_new(N);
+    #pragma omp for schedule(static)
+    for (int64_t m = 0; m < np; m++) {
+        double b = b_[m];
+        for (int n = 0; n < N; n++) {
+            size_t i1 = n + (size_t)N * (0 + 2 * m), i2 = n + (size_t)N * (1 + 2 * m);
+            double xt1 = XT[i1].re, xt2 = XT[i2].re;                              /* :166-167 */
+            cplx yt1 = YT[i1], yt2 = YT[i2];                                      /* :169-170 */
+            double ct = cos(tau[n]), st = sin(tau[n]);
+            FX[i1] = c_rdiv(c_add(c_rmul(ct, yt1), c_rmul(st, yt2)), b);          /* :174 */
+            FX[i2] = c_rdiv(c_add(c_rmul(-st, yt1), c_rmul(ct, yt2)), b);         /* :175 */
+            double interv = (1.0 + 0.5 * sin(xt1) * sin(xt2) - b) / eps;          /* :177 */
+            cplx q1 = c_rmul(interv, c_sub(c_rmul(ct, yt2), c_rmul(st, yt1)));    /* :179 */
+            cplx q2 = c_rmul(interv, c_sub(c_rmul(-ct, yt1), c_rmul(st, yt2)));   /* :180 */
+            cplx tmp1 = c_make(et[i1] + q1.re, q1.im);
+            cplx tmp2 = c_make(et[i2] + q2.re, q2.im);
+            FY[i1] = c_rdiv(c_sub(c_rmul(ct, tmp1), c_rmul(st, tmp2)), b);        /* :182 */
+            FY[i2] = c_rdiv(c_add(c_rmul(st, tmp1), c_rmul(ct, tmp2)), b);        /* :183 */
+        }
+        for (int comp = 0; comp < 2; comp++) {
+            cplx *p1 = FX + (size_t)N * (comp + 2 * m), *p2 = FY + (size_t)N * (comp + 2 * m);
+            orc_fft_exec(plan, p1, 1, p1, 1, -1);                                 /* :187-188 */
+            orc_fft_exec(plan, p2, 1, p2, 1, -1);                                 /* :189-190 */
+            if (normalise)
+                for (int n = 0; n < N; n++) { p1[n] = c_rdiv(p1[n], (double)N); p2[n] = c_rdiv(p2[n], (double)N); } /* :194-195 */
+        }
+    }
+    orc_fft_free(plan);
+    }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* ua_step1 (Fortran form: FFT, exponential Euler, inverse FFT)   fortran/ua_steps.F90:200-236 */
+/* ------------------------------------------------------------------------------------ */
+
+void orc_ua_step1(int ntau, double eps, int64_t np, const double *t_, const double *pl_, double *xt_, double *xf_,
+                  const double *fx_)
+{
+    const int N = ntau;
+    double tau[64], ltau[64];
+    orc_ua_tables(N, tau, ltau);
+    const cplx *PL = (const cplx *)pl_, *FX = (const cplx *)fx_;
+    cplx *XT = (cplx *)xt_, *XF = (cplx *)xf_;
+    #pragma omp parallel if (g_threads > 1)
+    {
+    orc_fft_plan *plan = orc_fft_new(N);
+    cplx rf[2][64];
+    #pragma omp for schedule(static)
+    for (int64_t m = 0; m < np; m++) {
+        cplx *x1 = XT + (size_t)N * (0 + 2 * m), *x2 = XT + (size_t)N * (1 + 2 * m);
+        cplx *f1 = XF + (size_t)N * (0 + 2 * m), *f2 = XF + (size_t)N * (1 + 2 * m);
+        orc_fft_exec(plan, x1, 1, f1, 1, -1);                                     /* :217 */
+        orc_fft_exec(plan, x2, 1, f2, 1, -1);                                     /* :218 */
+        double t = t_[m];                                                         /* :220 */
+        for (int n = 0; n < N; n++) {
+            /* elt = exp(-(0,1)*ltau(n)*t/eps) / ntau     :224-225 */
+            cplx elt = c_expi(((-1.0 * ltau[n]) * t) / eps);
+            elt = c_rdiv(elt, (double)N);
+            cplx pl = PL[n + (size_t)N * m];
+            rf[0][n] = c_add(c_mul(elt, f1[n]), c_mul(pl, FX[n + (size_t)N * (0 + 2 * m)]));   /* :226 */
+            rf[1][n] = c_add(c_mul(elt, f2[n]), c_mul(pl, FX[n + (size_t)N * (1 + 2 * m)]));   /* :227 */
+        }
+        orc_fft_exec(plan, rf[0], 1, x1, 1, +1);                                  /* :231 */
+        orc_fft_exec(plan, rf[1], 1, x2, 1, +1);                                  /* :232 */
+    }
+    orc_fft_free(plan);
+    }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* ua_step2 (corrector)              fortran/ua_steps.F90:238-272                          */
+/* ------------------------------------------------------------------------------------ */
+
+void orc_ua_step2(int ntau, double eps, int64_t np, const double *t_, const double *pl_, const double *ql_,
+                  double *xt_, const double *xf_, const double *fx_, const double *gx_)
+{
+    const int N = ntau;
+    double tau[64], ltau[64];
+    orc_ua_tables(N, tau, ltau);
+    const cplx *PL = (const cplx *)pl_, *QL = (const cplx *)ql_, *FX = (const cplx *)fx_, *GX = (const cplx *)gx_;
+    const cplx *XF = (const cplx *)xf_;
+    cplx *XT = (cplx *)xt_;
+    #pragma omp parallel if (g_threads > 1)
+    {
+    orc_fft_plan *plan = orc_fft_new(N);
+    cplx rf[2][64];
+    #pragma omp for schedule(static)
+    for (int64_t m = 0; m < np; m++) {
+        double t = t_[m];                                                         /* :254 */
+        for (int n = 0; n < N; n++) {
+            cplx elt = c_expi(((-1.0 * ltau[n]) * t) / eps);                      /* :258 */
+            elt = c_rdiv(elt, (double)N);                                         /* :259 */
+            cplx pl = PL[n + (size_t)N * m], ql = QL[n + (size_t)N * m];
+            for (int comp = 0; comp < 2; comp++) {
+                size_t i = n + (size_t)N * (comp + 2 * m);
+                /* elt*xf + pl*fx + ql*(gx-fx)/t     :260-263 */
+                cplx a = c_add(c_mul(elt, XF[i]), c_mul(pl, FX[i]));
+                cplx c = c_rdiv(c_mul(ql, c_sub(GX[i], FX[i])), t);
+                rf[comp][n] = c_add(a, c);
+            }
+        }
+        orc_fft_exec(plan, rf[0], 1, XT + (size_t)N * (0 + 2 * m), 1, +1);        /* :267 */
+        orc_fft_exec(plan, rf[1], 1, XT + (size_t)N * (1 + 2 * m), 1, +1);        /* :268 */
+    }
+    orc_fft_free(plan);
+    }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* compute_v                         fortran/ua_steps.F90:274-307                          */
+/* ------------------------------------------------------------------------------------ */
+
+void orc_compute_v(int ntau, double eps, int64_t np, const double *t_, const double *yt_, double *yf_, double *v)
+{
+    const int N = ntau;
+    double tau[64], ltau[64];
+    orc_ua_tables(N, tau, ltau);
+    const cplx *YT = (const cplx *)yt_;
+    cplx *YF = (cplx *)yf_;
+    #pragma omp parallel if (g_threads > 1)
+    {
+    orc_fft_plan *plan = orc_fft_new(N);
+    #pragma omp for schedule(static)
+    for (int64_t m = 0; m < np; m++) {
+        double t = t_[m];                                                         /* :288 */
+        cplx *f1 = YF + (size_t)N * (0 + 2 * m), *f2 = YF + (size_t)N * (1 + 2 * m);
+        orc_fft_exec(plan, YT + (size_t)N * (0 + 2 * m), 1, f1, 1, -1);           /* :290 */
+        orc_fft_exec(plan, YT + (size_t)N * (1 + 2 * m), 1, f2, 1, -1);           /* :291 */
+        cplx px = c_make(0.0, 0.0), py = c_make(0.0, 0.0);                        /* :293-294 */
+        for (int n = 0; n < N; n++) {
+            cplx elt = c_expi((ltau[n] * t) / eps);                               /* :297 */
+            px = c_add(px, c_mul(c_rdiv(f1[n], (double)N), elt));                 /* :298 */
+            py = c_add(py, c_mul(c_rdiv(f2[n], (double)N), elt));                 /* :299 */
+        }
+        double c = cos(t / eps), s = sin(t / eps);
+        v[2 * m]     = c * px.re + s * py.re;                                     /* :302 real(cos*px+sin*py) */
+        v[2 * m + 1] = c * py.re - s * px.re;                                     /* :303 */
+    }
+    orc_fft_free(plan);
+    }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* The driver loop                   fortran/bupdate.F90:89-128                              */
+/* energy[0] after the initial Poisson, then 2 per step (test/bupdate.jl:65,90,106).        */
+/* sumv (optional): 2 per step = the values bupdate prints (:125).                          */
+/* faithful=1 also performs the third (dead) interpolation of every step (:121).            */
+/* ------------------------------------------------------------------------------------ */
+
+int orc_run_bupdate(const orc_mesh *m, int ntau, double eps, double dt, int nstep, int64_t np, double w,
+                    double *x, double *v, double *e_part_out, double *emesh_out, double *energy, double *sumv,
+                    int wrap, int faithful)
+{
+    const int N = ntau;
+    if (N > 64) return -1;
+    const size_t nrho = (size_t)(m->nx + 1) * (size_t)(m->ny + 1);
+    const size_t big = (size_t)N * 2 * (size_t)np;
+    double *rho = (double *)calloc(nrho, sizeof(double));
+    double *emesh = (double *)calloc(2 * nrho, sizeof(double));
+    double *ep = (double *)calloc(2 * (size_t)np, sizeof(double));
+    double *b = (double *)malloc(sizeof(double) * (size_t)np), *t = (double *)malloc(sizeof(double) * (size_t)np);
+    double *pl = (double *)malloc(sizeof(cplx) * (size_t)N * (size_t)np), *ql = (double *)malloc(sizeof(cplx) * (size_t)N * (size_t)np);
+    double *et = (double *)malloc(sizeof(double) * big);
+    double *xt = (double *)malloc(sizeof(cplx) * big), *xf = (double *)malloc(sizeof(cplx) * big);
+    double *yt = (double *)malloc(sizeof(cplx) * big), *yf = (double *)malloc(sizeof(cplx) * big);
+    double *fx = (double *)malloc(sizeof(cplx) * big), *fy = (double *)malloc(sizeof(cplx) * big);
+    double *gx = (double *)malloc(sizeof(cplx) * big), *gy = (double *)malloc(sizeof(cplx) * big);
+    if (!rho || !emesh || !ep || !b || !t || !pl || !ql || !et || !xt || !xf || !yt || !yf || !fx || !fy || !gx || !gy) return -2;
+
+    int ie = 0;
+    orc_compute_rho_m6(m, np, x, w, rho, wrap);                                   /* bupdate.F90:89 */
+    energy[ie++] = orc_poisson(m, rho, emesh);                                    /* :91 */
+    orc_interpol_eb_m6(m, emesh, np, x, ep, wrap);                                /* :93 */
+
+    for (int istep = 0; istep < nstep; istep++) {
+        orc_preparation(N, eps, dt, np, x, v, ep, b, t, pl, ql, xt, yt);          /* :97 */
+        orc_interpol_eb_m6_tau(m, emesh, N, np, xt, et, wrap);                    /* :99 */
+        orc_compute_f(N, eps, np, b, xt, yt, et, fx, fy, 1);                      /* :101 */
+        orc_ua_step1(N, eps, np, t, pl, xt, xf, fx);                              /* :103 */
+        orc_ua_step1(N, eps, np, t, pl, yt, yf, fy);                              /* :104 */
+        orc_compute_rho_m6_tau(m, N, eps, np, xt, t, w, rho, x, wrap);            /* :106 */
+        energy[ie++] = orc_poisson(m, rho, emesh);                                /* :108 */
+        orc_interpol_eb_m6_tau(m, emesh, N, np, xt, et, wrap);                    /* :110 */
+        orc_compute_f(N, eps, np, b, xt, yt, et, gx, gy, 1);                      /* :112 */
+        orc_ua_step2(N, eps, np, t, pl, ql, xt, xf, fx, gx);                      /* :114 */
+        orc_ua_step2(N, eps, np, t, pl, ql, yt, yf, fy, gy);                      /* :115 */
+        orc_compute_rho_m6_tau(m, N, eps, np, xt, t, w, rho, x, wrap);            /* :117 */
+        energy[ie++] = orc_poisson(m, rho, emesh);                                /* :119 */
+        if (faithful) orc_interpol_eb_m6_tau(m, emesh, N, np, xt, et, wrap);      /* :121 (result never read) */
+        orc_compute_v(N, eps, np, t, yt, yf, v);                                  /* :123 */
+        if (sumv) {
+            double sx = 0.0, sy = 0.0;
+            for (int64_t k = 0; k < np; k++) { sx += v[2 * k]; sy += v[2 * k + 1]; }   /* :125 */
+            sumv[2 * istep] = sx; sumv[2 * istep + 1] = sy;
+        }
+    }
+    if (e_part_out) memcpy(e_part_out, ep, sizeof(double) * 2 * (size_t)np);
+    if (emesh_out) memcpy(emesh_out, emesh, sizeof(double) * 2 * nrho);
+    free(rho); free(emesh); free(ep); free(b); free(t); free(pl); free(ql); free(et);
+    free(xt); free(xf); free(yt); free(yf); free(fx); free(fy); free(gx); free(gy);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* init_particles_2d densities      fortran/particles.F90:68-103, src/plasma.jl:17-48       */
+/* The uniform deviates are supplied by the caller (u must hold enough draws); returns the   */
+/* number of deviates consumed, or -1 if u ran out.  Keeps the reference's draw order.       */
+/* ------------------------------------------------------------------------------------ */
+
+int64_t orc_plasma_from_uniforms(const orc_mesh *m, int64_t np, double alpha, double kx, const double *u, int64_t nu,
+                                 double *x, double *v)
+{
+    const double dimx = m->xmax - m->xmin, dimy = m->ymax - m->ymin;
+    int64_t iu = 0, k = 0;
+    while (k < np) {
+        if (iu + 3 > nu) return -1;
+        double xi = u[iu++] * dimx;
+        double yi = u[iu++] * dimy;
+        double zi = (2.0 + alpha) * u[iu++];
+        double temm = 1.0 + sin(yi) + alpha * cos(kx * xi);
+        if (temm >= zi) { x[2 * k] = xi; x[2 * k + 1] = yi; k++; }
+    }
+    k = 0;
+    while (k < np) {
+        if (iu + 3 > nu) return -1;
+        double xi = (u[iu++] - 0.5) * 10.0;
+        double yi = (u[iu++] - 0.5) * 10.0;
+        double zi = u[iu++];
+        double temm = (exp(-((xi - 2.0) * (xi - 2.0) + yi * yi) / 2.0) + exp(-((xi + 2.0) * (xi + 2.0) + yi * yi) / 2.0)) / 2.0;
+        if (temm >= zi) { v[2 * k] = xi; v[2 * k + 1] = yi; k++; }
+    }
+    return iu;
+}
