@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the UA-PIC time step (BASELINE.json metric: particle-tau updates per second).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload config3|config2|config5] [--impl b200|reference]
+
+One process per GPU (the driver launches N>1 through torch.distributed.run).  A "step" is one full UA step
+(fortran/bupdate.F90:97-123: predictor + corrector, two deposits, two Poisson solves) over every particle-tau
+sample of the workload.  Default workload = the per-GPU shard of BASELINE config 3 (4D Landau load, ntau = 32,
+128 x 128 mesh, M6): 12.5e6 particles per GPU, so that 8 GPUs run exactly the 1e8-particle case the metric is
+quoted on (weak scaling).  1e8 particles do not fit one GPU in the store-full layout (410 GB of barrier-crossing
+state), hence the shard at N = 1.
+
+Prints ONE JSON line (rank 0).  `value` times K steps with all state resident in HBM; `e2e` times the same step
+through the host-facing API with the particles living in pinned HOST memory (x, v, e copied up, x, v and the energy
+copied down, every step); `roofline` is for the dominant fused kernel, CUDA-event timed inside the run;
+`cpu_baseline` is the CPU oracle (a port of the Fortran reference, OpenMP on all host cores) on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+DIMX, DIMY = 4 * np.pi, 2 * np.pi
+DT = np.pi / 16          # bupdate.F90:66
+EPS = 0.1                # bupdate.F90:18
+
+WORKLOADS = {
+    # name: (load, ntau, nx, ny, particles per GPU, description)
+    "config3": ("landau", 32, 128, 128, 12_500_000, "BASELINE config 3 shard: 4D Landau load, ntau=32, 128x128, M6, 12.5e6 particles/GPU (1e8 at 8 GPUs)"),
+    "config2": ("plasma", 16, 128, 64, 1_000_000, "BASELINE config 2: bupdate case, M6, 1e6 particles, ntau=16, 128x64"),
+    "config5": ("landau", 32, 256, 256, 15_625_000, "BASELINE config 5 weak point: 5e8 particle-tau samples/GPU, ntau=32, 256x256, M6"),
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(device)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, smax, power = [], [], []
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f:
+            c = [t.strip() for t in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); smax.append(float(c[2])); power.append(float(c[3]))
+            except ValueError:
+                continue
+            for n, v in zip(names, c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        self.f.close()
+        os.unlink(self.f.name)
+        if sm:
+            # "under load": samples in the upper half of the power range seen
+            pw = np.array(power)
+            load = pw >= (pw.min() + 0.5 * (pw.max() - pw.min())) if pw.max() > pw.min() else np.ones_like(pw, bool)
+            out.update(sm_mhz=float(np.median(np.array(sm)[load])), sm_max_mhz=float(max(smax)), reasons=sorted(reasons),
+                       samples=len(sm), power_w_max=float(pw.max()))
+        return out
+
+
+def cpu_oracle_rate(workload, steps, warmup, sample_particles, threads=None, faithful=True):
+    """particle-tau updates/s of the CPU oracle (port of the Fortran reference) on a bounded sample of the workload"""
+    import oracle
+    load, ntau, nx, ny, _, _ = WORKLOADS[workload]
+    orc = oracle.corc()
+    nthreads = threads or orc.max_threads()
+    orc.set_threads(nthreads)
+    om = oracle.mesh(0, DIMX, nx, 0, DIMY, ny)
+    rng = np.random.default_rng(12345)
+    n = sample_particles
+    if load == "landau":
+        x = np.zeros((2, n), order="F"); v = np.zeros((2, n), order="F")
+        r = rng.random((n, 3))
+        x[0] = r[:, 1] * DIMX + 0.05 * np.sin(0.5 * r[:, 1] * DIMX)      # close enough to the Landau profile for timing
+        x[1] = r[:, 2] * DIMY
+        vv = np.sqrt(-2 * np.log((np.arange(1, n + 1) - 0.5) / n))
+        v[0], v[1] = vv * np.cos(2 * np.pi * r[:, 0]), vv * np.sin(2 * np.pi * r[:, 0])
+    else:
+        x, v, _ = orc.plasma_from_uniforms(om, n, 0.05, 0.5, rng.random(n * 80))
+    sim = orc.sim(om, ntau, EPS, DT, x, v, DIMX * DIMY / n, faithful=faithful)
+    sim.init()
+    for _ in range(warmup):
+        sim.step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        sim.step()
+    dt = time.perf_counter() - t0
+    sim.close()
+    orc.set_threads(1)
+    return n * ntau * steps / dt, dt / steps * 1e3, nthreads
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path.  Neither Julia nor a Fortran compiler nor
+    FFTW exist in this image, so it is the line-by-line C port (oracle/uapic_oracle.c, three gathers per step as the
+    Fortran does), OpenMP over all host cores, on a bounded particle sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    load, ntau, nx, ny, np_gpu, desc = WORKLOADS[args.workload]
+    sample = args.cpu_sample or 200_000
+    rate, ms, threads = cpu_oracle_rate(args.workload, args.steps, args.warmup, sample)
+    line = {
+        "impl": "reference", "metric": "particle-tau updates/sec", "value": rate, "unit": "particle-tau updates/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "ntau": ntau, "mesh": [nx, ny], "eps": EPS, "scheme": "M6",
+                   "note": "CPU port timed on a bounded sample; cost is linear in the particle count"},
+        "cpu_baseline": {"value": rate, "unit": "particle-tau updates/s", "cores": threads, "kind": "port",
+                         "sample": f"{sample} particles x ntau={ntau} x {args.steps} steps of the same workload (Fortran-faithful: 3 gathers/step)"},
+        "e2e": {"value": rate, "unit": "particle-tau updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="config3", choices=sorted(WORKLOADS))
+    ap.add_argument("--particles-per-gpu", type=int, default=0)
+    ap.add_argument("--deposit", default="fp64", choices=["fp64", "fixed"])
+    ap.add_argument("--cpu-sample", type=int, default=0, help="particles in the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import uapic_b200 as ub
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: uapic_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    load, ntau, nx, ny, np_gpu, desc = WORKLOADS[args.workload]
+    if args.particles_per_gpu:
+        np_gpu = args.particles_per_gpu
+        desc += f" [particles/GPU overridden to {np_gpu}]"
+    np_global = np_gpu * world
+    mesh = ub.Mesh(0, DIMX, nx, 0, DIMY, ny)
+    lo, hi = ub.dist.shard_range(np_global, rank, world)
+    stream = torch.cuda.current_stream().cuda_stream
+    s = ub.Session(mesh, ntau, EPS, DT, hi - lo, nbpart_global=np_global, device=local, stream=stream,
+                   deposit_mode=ub.DEPOSIT_FIXED_POINT if args.deposit == "fixed" else ub.DEPOSIT_FP64_ATOMIC)
+    if world > 1:
+        ub.dist.attach_torch_allreduce(s)
+    s.generate_particles(load, seed=20190101, first_global_index=lo)
+    s.init_fields()
+    s.step(args.warmup)
+    s.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if dist is None:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    sampler = ClockSampler(local) if rank == 0 else None
+
+    # ---- device-resident throughput ------------------------------------------------------------------
+    s.enable_timing(True)
+    launches0 = s.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    s.step(args.steps)
+    ev1.record()
+    barrier()
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    launches = s.launch_count - launches0
+    ms_a, ms_b, nt = s.phase_times()
+    s.enable_timing(False)
+    ms_step = ms_total / args.steps
+    units_step = np_global * ntau
+    value = units_step / (ms_step * 1e-3)
+
+    # ---- end to end through the host-facing API, particles in pinned host memory ------------------------
+    e2e = None
+    if not args.no_e2e:
+        n_loc = hi - lo
+        hx = torch.empty((n_loc, 2), dtype=torch.float64).pin_memory()
+        hv = torch.empty((n_loc, 2), dtype=torch.float64).pin_memory()
+        he = torch.empty((n_loc, 2), dtype=torch.float64).pin_memory()
+        s.download_particles_ptr(hx.data_ptr(), hv.data_ptr())
+        he.numpy()[:] = s.download_particle_e().T
+        e2e_steps = max(3, min(args.steps, 5))
+
+        def one():
+            s.upload_particles_ptr(hx.data_ptr(), hv.data_ptr())
+            s.upload_particle_e_ptr(he.data_ptr())
+            s.step(1)
+            s.download_particles_ptr(hx.data_ptr(), hv.data_ptr())
+            return s.energy_history()[-1]
+
+        for _ in range(2):
+            one()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            nrj = one()
+        torch.cuda.synchronize()
+        ms_e2e = max_over_ranks((time.perf_counter() - t0) * 1e3) / e2e_steps
+        e2e = {"value": units_step / (ms_e2e * 1e-3), "unit": "particle-tau updates/s", "ms_per_step": ms_e2e,
+               "h2d_bytes_per_step": int(3 * 16 * n_loc), "d2h_bytes_per_step": int(2 * 16 * n_loc + 8 * s.energy_history().size),
+               "steps": e2e_steps, "last_energy": float(nrj),
+               "note": "x, v, e (2,np) uploaded from pinned host memory and x, v + energy history read back every step, per rank"}
+    clocks = sampler.stop() if sampler else None
+
+    if rank == 0:
+        hbm, hbm_src = peaks()
+        n_loc = hi - lo
+        bytes_a = n_loc * ntau * 128 + n_loc * 64          # reads x,v,e (48 B/particle); writes 128 B/sample + (t,b)
+        bytes_b = n_loc * ntau * 128 + n_loc * 48          # reads 128 B/sample + (t,b); writes x,v
+        per_a, per_b = ms_a / max(nt, 1), ms_b / max(nt, 1)
+        dom = ("uapic::k_phase_b", bytes_b, per_b) if per_b >= per_a else ("uapic::k_phase_a", bytes_a, per_a)
+        achieved = dom[1] / (dom[2] * 1e-3) / 1e9 if dom[2] > 0 else 0.0
+        b_alg = 256 + 112 / ntau
+        line = {
+            "metric": "particle-tau updates/sec", "value": value, "unit": "particle-tau updates/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": desc, "load": load, "ntau": ntau, "mesh": [nx, ny], "eps": EPS, "dt": DT, "scheme": "M6",
+                       "particles_per_gpu": np_gpu, "particles_total": np_global, "deposit": args.deposit,
+                       "storage": "store-full (128 B per particle-tau across the intra-step barrier)",
+                       "l2": f"inputs larger than L2: {s.device_bytes / 1e9:.1f} GB of particle state per GPU streamed every step",
+                       "parallelism": f"particle shards x{world}, allreduce(rho) over NCCL" if world > 1 else "single GPU"},
+            "e2e": e2e,
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": hbm, "unit": "GB/s",
+                         "frac": achieved / hbm, "traffic": None, "peak_source": hbm_src,
+                         "ms_per_launch": dom[2], "algorithmic_bytes_per_launch": int(dom[1]),
+                         "phase_a_ms": per_a, "phase_b_ms": per_b,
+                         "whole_step_frac_of_hbm": value * b_alg / 1e9 / hbm,
+                         "algorithmic_bytes_per_update": b_alg},
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            sample = args.cpu_sample or 100_000
+            rate, ms_cpu, threads = cpu_oracle_rate(args.workload, 2, 1, sample)
+            line["cpu_baseline"] = {"value": rate, "unit": "particle-tau updates/s", "cores": threads, "kind": "port",
+                                    "sample": f"{sample} particles x ntau={ntau} x 2 steps of the same workload, C port of fortran/bupdate.F90 with OpenMP (3 gathers/step)"}
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line), flush=True)
+    s.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,202 @@
+/*
+ * uapic_b200.h -- C ABI of libuapic_b200.so: the UA-PIC time step of JuliaVlasov/UAPIC.jl
+ * (fortran/bupdate.F90, test/bupdate.jl) as hand-written sm_100a CUDA.
+ *
+ * The reference has no FFI boundary of its own for this path: the boundary it offers is the
+ * exported Julia function set.  Every entry point below names the Julia
+ * function (and the Fortran routine it shadows) that a maintainer would rebind to it with
+ * `ccall`; INTEGRATION.md shows those bindings.
+ *
+ * Conventions
+ *  - all arrays are COLUMN-MAJOR host buffers exactly as Julia/Fortran hold them:
+ *      ComplexF64 (ntau,2,nbpart)  -> `double*` with interleaved (re,im), tau fastest
+ *      Float64    (ntau,2,nbpart), (2,nbpart), (2,nx+1,ny+1), (nx+1,ny+1)
+ *  - every function returns 0 on success, a negative UAPIC_E* code otherwise;
+ *    uapic_last_error() gives the message of the last failure on the calling thread.
+ *  - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *    UAPIC_ENODEVICE.
+ *  - ntau must be a power of two in [2, 32] (one tau sample per lane of a warp).
+ *  - stage functions are synchronous (H2D, kernel, D2H inside the call); the session API keeps
+ *    all state resident in HBM and is the performance path.
+ */
+#ifndef UAPIC_B200_H
+#define UAPIC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UAPIC_OK            0
+#define UAPIC_EINVAL       -1   /* bad argument (ntau not a power of two, null pointer, ...) */
+#define UAPIC_ENODEVICE    -2   /* no CUDA device / wrong architecture */
+#define UAPIC_ECUDA        -3   /* a CUDA runtime call or kernel failed */
+#define UAPIC_ENOMEM       -4   /* device allocation failed */
+#define UAPIC_ESTATE       -5   /* session used in the wrong order */
+#define UAPIC_EUNSUPPORTED -6   /* valid request this build does not implement */
+
+/* periodic wrap convention */
+#define UAPIC_WRAP_FORTRAN 0    /* px = x/dx; px = modulo(px,nx); stored x unwrapped  (compute_rho_m6.F90:86-93) */
+#define UAPIC_WRAP_JULIA   1    /* x = mod(x-xmin,dimx); px = x/dx; stored x wrapped   (src/compute_rho.jl:63-70) */
+
+/* charge accumulation */
+#define UAPIC_DEPOSIT_FP64_ATOMIC 0   /* fp64 atomics: fastest, summation order not reproducible */
+#define UAPIC_DEPOSIT_FIXED_POINT 1   /* int64 fixed point: bit-identical run to run and for any GPU count */
+
+/* shape functions */
+#define UAPIC_SCHEME_M6  0      /* quintic spline, the scheme the reference ships (compute_rho_m6.F90:28-45) */
+#define UAPIC_SCHEME_CIC 1      /* bilinear; build-defined from performance/test_cic.F90:73-81 (no reference parity) */
+
+/* what crosses the intra-step barrier */
+#define UAPIC_STORE_FULL   0    /* 128 B per particle-tau kept in HBM between predictor and corrector */
+#define UAPIC_STORE_HYBRID 1    /* 16 B per particle-tau (E at the tau samples); predictor recomputed */
+
+typedef struct uapic_mesh {
+    double  xmin, xmax, ymin, ymax;   /* src/meshfields.jl:5-12, fortran/meshfields.F90:7-14 */
+    int32_t nx, ny;
+} uapic_mesh_t;
+
+/* message of the last error raised on this thread ("" if none) */
+const char *uapic_last_error(void);
+/* library version, and the SM architecture the kernels were compiled for (100 = sm_100a) */
+int uapic_version(void);
+int uapic_compiled_arch(void);
+/* 2^S used by UAPIC_DEPOSIT_FIXED_POINT for a given total deposited mass (nbpart_global*w): every tap is rounded to a
+   multiple of 2^-S and accumulated in int64, so sums are order independent (pure host arithmetic, no device needed) */
+int uapic_fixed_point_scale(double total_mass, double *scale);
+/* number of usable CUDA devices (0 and UAPIC_ENODEVICE when none) */
+int uapic_device_count(int *count);
+
+/* ------------------------------------------------------------------------------------------
+ * Stage API: one entry point per exported Julia function on the hot path.
+ * ------------------------------------------------------------------------------------------ */
+
+/* compute_rho_m6!(fields, particles)            src/compute_rho.jl:181-316, compute_rho_m6.F90:205-335
+   x (2,nbpart) is rewritten in place only for UAPIC_WRAP_JULIA.  rho (nx+1,ny+1) out.  rho_total may be NULL. */
+int uapic_compute_rho_m6(const uapic_mesh_t *mesh, int64_t nbpart, double *x, double w, double *rho,
+                         int wrap, int deposit_mode, double *rho_total);
+
+/* interpol_eb_m6!(particles, fields)            src/interpolation.jl:125-247, interpolation_m6.F90:193-327
+   e (2,nx+1,ny+1) in, ep (2,nbpart) out; x rewritten only for UAPIC_WRAP_JULIA. */
+int uapic_interpol_eb_m6(const uapic_mesh_t *mesh, const double *e, int64_t nbpart, double *x, double *ep, int wrap);
+
+/* (p::Poisson)(fields)                          src/poisson.jl:62-83, poisson_2d.f90:85-111
+   rho (nx+1,ny+1) in, e (2,nx+1,ny+1) out, *energy = sum(e1^2+e2^2)*dx*dy over the ghosted array. */
+int uapic_poisson(const uapic_mesh_t *mesh, const double *rho, double *e, double *energy);
+
+/* preparation!(ua, dt, particles, xt, yt)       src/ua_steps.jl:3-78, ua_steps.F90:15-115
+   in: x,v,e (2,nbpart).  out: b,t (nbpart); pl,ql ComplexF64 (ntau,nbpart); xt,yt ComplexF64 (ntau,2,nbpart). */
+int uapic_preparation(int ntau, double eps, double dt, int64_t nbpart, const double *x, const double *v,
+                      const double *e, double *b, double *t, double *pl, double *ql, double *xt, double *yt);
+
+/* update_particles_e!  = interpol_eb_m6!(et, fields, xt, nbpart, ntau)
+                                                 src/ua_steps.jl:82-90, src/interpolation.jl:3-123, interpolation_m6.F90:40-191 */
+int uapic_interpol_eb_m6_tau(const uapic_mesh_t *mesh, const double *e, int ntau, int64_t nbpart,
+                             const double *xt, double *et, int wrap);
+
+/* compute_f!(fx, fy, ua, particles, xt, yt, et) src/ua_steps.jl:105-145, ua_steps.F90:140-198
+   normalise = 0: Julia (unnormalised fft!); 1: Fortran (fft then /ntau). */
+int uapic_compute_f(int ntau, double eps, int64_t nbpart, const double *b, const double *xt, const double *yt,
+                    const double *et, double *fx, double *fy, int normalise);
+
+/* mul!(x̃t, ftau, xt) / ifft!(xt,1)              test/bupdate.jl:79,82,85-86,102
+   nvec length-ntau complex vectors; sign -1 forward, +1 backward; normalise divides by ntau. */
+int uapic_fft_tau(int ntau, int64_t nvec, const double *in, double *out, int sign, int normalise);
+
+/* ua_step!(xt, x̃t, ua, particles, fx)           src/ua_steps.jl:149-170   (Fourier in, Fourier out) */
+int uapic_ua_step_predict(int ntau, double eps, int64_t nbpart, const double *t, const double *pl,
+                          const double *xf, const double *fx, double *xt);
+/* ua_step!(xt, x̃t, ua, particles, fx, gx)       src/ua_steps.jl:172-200 */
+int uapic_ua_step_correct(int ntau, double eps, int64_t nbpart, const double *t, const double *pl, const double *ql,
+                          const double *xf, const double *fx, const double *gx, double *xt);
+
+/* Fortran forms: ua_step1 / ua_step2            ua_steps.F90:200-236, 238-272
+   ua_step1: xf <- FFT(xt); xt <- IFFT(elt/ntau*xf + pl*fx)      (fx normalised by 1/ntau)
+   ua_step2: xt <- IFFT(elt/ntau*xf + pl*fx + ql*(gx-fx)/t) */
+int uapic_ua_step1(int ntau, double eps, int64_t nbpart, const double *t, const double *pl, double *xt, double *xf,
+                   const double *fx);
+int uapic_ua_step2(int ntau, double eps, int64_t nbpart, const double *t, const double *pl, const double *ql,
+                   double *xt, const double *xf, const double *fx, const double *gx);
+
+/* update_particles_x! = compute_rho_m6!(fields, particles, xt, ua)
+                                                 src/ua_steps.jl:94-101, src/compute_rho.jl:29-179, compute_rho_m6.F90:47-203
+   xt time-domain ComplexF64 (ntau,2,nbpart), t (nbpart) in; rho (nx+1,ny+1) and x (2,nbpart) out. */
+int uapic_compute_rho_m6_tau(const uapic_mesh_t *mesh, int ntau, double eps, int64_t nbpart, const double *xt,
+                             const double *t, double w, double *rho, double *x, int wrap, int deposit_mode,
+                             double *rho_total);
+
+/* compute_v!(yt, particles, ua)                 src/ua_steps.jl:204-224 (yt_is_fourier = 1)
+   compute_v(ua, particles, yt, yf)              ua_steps.F90:274-307    (yt_is_fourier = 0: FFT first) */
+int uapic_compute_v(int ntau, double eps, int64_t nbpart, const double *t, const double *yt, int yt_is_fourier,
+                    double *v);
+
+/* ------------------------------------------------------------------------------------------
+ * Session API: the whole loop of fortran/bupdate.F90:89-128 / test/bupdate.jl:63-114 with all
+ * state resident in HBM.  One session per GPU (one process per GPU); the only inter-GPU step is
+ * the sum of the raw rho mesh, delegated to a caller-supplied collective.
+ * ------------------------------------------------------------------------------------------ */
+
+typedef struct uapic_session uapic_session_t;
+
+typedef struct uapic_config {
+    uapic_mesh_t mesh;
+    int32_t ntau;            /* power of two, 2..32 */
+    int32_t wrap;            /* UAPIC_WRAP_*          */
+    int32_t deposit_mode;    /* UAPIC_DEPOSIT_*       */
+    int32_t scheme;          /* UAPIC_SCHEME_*        */
+    int32_t storage_mode;    /* UAPIC_STORE_*         */
+    int32_t device;          /* CUDA ordinal          */
+    double  eps;             /* bupdate.F90:18        */
+    double  dt;              /* bupdate.F90:66        */
+    int64_t nbpart;          /* particles held by THIS session (its shard) */
+    double  weight;          /* particles%w = dimx*dimy/nbpart_global (particles.F90:52) */
+    double  total_mass;      /* nbpart_global*weight: bounds the fixed-point scale; 0 -> dimx*dimy */
+    void   *stream;          /* cudaStream_t to run on (NULL = the legacy default stream) */
+} uapic_config_t;
+
+/* sum `count` elements at device pointer `buf` over all ranks, in place, ordered on `stream`.
+   dtype: 0 = float64, 1 = int64.  Return 0 on success. */
+typedef int (*uapic_allreduce_fn)(void *ctx, void *buf, int64_t count, int dtype, void *stream);
+
+int uapic_session_create(const uapic_config_t *cfg, uapic_session_t **out);
+int uapic_session_destroy(uapic_session_t *s);
+int uapic_session_set_allreduce(uapic_session_t *s, uapic_allreduce_fn fn, void *ctx);
+
+/* x, v (2,nbpart) host (pageable or pinned) -> device SoA */
+int uapic_session_upload_particles(uapic_session_t *s, const double *x, const double *v);
+/* particles.e (2,nbpart), the field at the particles frozen after init (bupdate.F90:93): lets a caller that keeps
+   the particles on the host hand the full per-step input (x, v, e) back to a session */
+int uapic_session_upload_particle_e(uapic_session_t *s, const double *ep);
+/* per-kernel device timing: when enabled, CUDA events bracket the two fused phase kernels of every step;
+   phase_times returns the accumulated milliseconds and the number of steps they cover, then resets them */
+int uapic_session_enable_timing(uapic_session_t *s, int enable);
+int uapic_session_phase_times(uapic_session_t *s, double *ms_phase_a, double *ms_phase_b, int64_t *steps);
+/* device-side loaders (counter-based RNG; particle index offset = first global index of this shard)
+   kind 0: init_particles_2d / plasma densities (particles.F90:68-103, src/plasma.jl:17-48)
+   kind 1: Landau load (the intent of src/landau.jl:19-43)                                         */
+int uapic_session_generate_particles(uapic_session_t *s, int kind, uint64_t seed, int64_t first_global_index,
+                                     double alpha, double kx);
+/* compute_rho_m6_real -> solve_poisson -> interpolate_eb_m6_real     bupdate.F90:89-93 */
+int uapic_session_init_fields(uapic_session_t *s);
+/* nsteps iterations of the loop body bupdate.F90:97-123 (dead third interpolation skipped) */
+int uapic_session_step(uapic_session_t *s, int nsteps);
+/* block until everything queued on the session's stream has finished */
+int uapic_session_synchronize(uapic_session_t *s);
+
+int uapic_session_download_particles(uapic_session_t *s, double *x, double *v);
+int uapic_session_download_particle_e(uapic_session_t *s, double *ep);
+int uapic_session_download_fields(uapic_session_t *s, double *e, double *rho);
+/* electric energy after every Poisson solve so far: 1 + 2*steps values (test/bupdate.jl:65,90,106) */
+int uapic_session_energy_history(uapic_session_t *s, double *out, int64_t capacity, int64_t *count);
+/* sum(v[1,:]), sum(v[2,:]) of this shard, the numbers bupdate prints every step (bupdate.F90:125) */
+int uapic_session_sum_v(uapic_session_t *s, double *sumv2);
+/* kernels launched by this session so far (for bench.py's gpu_launches) */
+int uapic_session_launch_count(uapic_session_t *s, int64_t *count);
+/* bytes of HBM the session holds */
+int uapic_session_device_bytes(uapic_session_t *s, int64_t *bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UAPIC_B200_H */

@@ -67,10 +67,13 @@ class _COracle:
         L.orc_f_m6.argtypes = [C.c_double]
         L.orc_compute_rho_m6.restype = C.c_double
         L.orc_compute_rho_m6_tau.restype = C.c_double
+        L.orc_compute_rho_m6_fixed.restype = C.c_double
         L.orc_poisson.restype = C.c_double
         L.orc_run_bupdate.restype = C.c_int
         L.orc_plasma_from_uniforms.restype = C.c_int64
         L.orc_get_max_threads.restype = C.c_int
+        L.orc_sim_create.restype = C.c_void_p
+        L.orc_sim_init.restype = C.c_double
 
     # -- helpers -------------------------------------------------------------------------------
     def set_threads(self, n):
@@ -100,6 +103,10 @@ class _COracle:
     # -- mesh <-> particles --------------------------------------------------------------------
     def compute_rho_m6(self, m, x, w, rho, wrap=WRAP_FORTRAN):
         return self.lib.orc_compute_rho_m6(C.byref(m), C.c_int64(x.shape[1]), _p(x), C.c_double(w), _p(rho), C.c_int(wrap))
+
+    def compute_rho_m6_fixed(self, m, x, w, scale, rho, wrap=WRAP_FORTRAN):
+        return self.lib.orc_compute_rho_m6_fixed(C.byref(m), C.c_int64(x.shape[1]), _p(x), C.c_double(w), C.c_double(scale),
+                                                 _p(rho), C.c_int(wrap))
 
     def interpol_eb_m6(self, m, e, x, ep, wrap=WRAP_FORTRAN):
         self.lib.orc_interpol_eb_m6(C.byref(m), _p(e), C.c_int64(x.shape[1]), _p(x), _p(ep), C.c_int(wrap))
@@ -175,6 +182,10 @@ class _COracle:
             raise RuntimeError(f"orc_run_bupdate failed rc={rc}")
         return energy, sumv, ep, emesh
 
+    def sim(self, m, ntau, eps, dt, x, v, w, wrap=WRAP_FORTRAN, faithful=True):
+        """persistent-state driver (init / step separately timed by bench.py's CPU baseline)"""
+        return _Sim(self, m, ntau, eps, dt, x, v, w, wrap, faithful)
+
     def plasma_from_uniforms(self, m, npart, alpha, kx, u):
         x = np.zeros((2, npart), order="F")
         v = np.zeros((2, npart), order="F")
@@ -183,6 +194,32 @@ class _COracle:
         if used < 0:
             raise RuntimeError("not enough uniform deviates")
         return x, v, int(used)
+
+
+class _Sim:
+    def __init__(self, orc, m, ntau, eps, dt, x, v, w, wrap, faithful):
+        self.orc, self.x, self.v = orc, x, v
+        self.h = orc.lib.orc_sim_create(C.byref(m), C.c_int(ntau), C.c_double(eps), C.c_double(dt), C.c_int64(x.shape[1]),
+                                        C.c_double(w), _p(x), _p(v), C.c_int(wrap), C.c_int(int(faithful)))
+        if not self.h:
+            raise MemoryError("orc_sim_create failed")
+
+    def init(self):
+        return float(self.orc.lib.orc_sim_init(C.c_void_p(self.h)))
+
+    def step(self):
+        e2 = np.zeros(2)
+        sv = np.zeros(2)
+        self.orc.lib.orc_sim_step(C.c_void_p(self.h), _p(e2), _p(sv))
+        return e2, sv
+
+    def close(self):
+        if self.h:
+            self.orc.lib.orc_sim_destroy(C.c_void_p(self.h))
+            self.h = None
+
+    def __del__(self):
+        self.close()
 
 
 _corc = None

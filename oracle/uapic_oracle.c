@@ -353,6 +353,41 @@ double orc_compute_rho_m6(const orc_mesh *m, int64_t np, double *x, double w, do
     return rho_epilogue(m, rho);
 }
 
+/* Deterministic (fixed-point) deposit: NOT in the reference.  It restates the product's build-defined
+   UAPIC_DEPOSIT_FIXED_POINT mode so that mode can be checked bit for bit: every tap cx*cy*w (reference
+   operation order) is rounded to a multiple of 1/scale and summed in int64; rho_total is the exact integer
+   sum; the epilogue is otherwise compute_rho_m6.F90:191-200.  pos = positions (2,np) already evaluated. */
+double orc_compute_rho_m6_fixed(const orc_mesh *m, int64_t np, const double *x, double w, double scale, double *rho, int wrap)
+{
+    const int nx = m->nx, ny = m->ny;
+    const size_t ld = (size_t)(nx + 1), nrho = ld * (size_t)(ny + 1);
+    const double dx = mesh_dx(m), dy = mesh_dy(m);
+    int64_t *acc = (int64_t *)calloc(nrho, sizeof(int64_t));
+    for (int64_t k = 0; k < np; k++) {
+        m6_stencil s;
+        m6_setup(m, dx, dy, x[2 * k], x[2 * k + 1], wrap, &s, NULL, NULL);
+        for (int a = 0; a < 7; a++)
+            for (int b = 0; b < 7; b++)
+                acc[(size_t)s.ix[a] + ld * (size_t)s.jy[b]] += (int64_t)llrint(s.cx[a] * s.cy[b] * w * scale);
+    }
+    int64_t itot = 0;
+    for (int j = 0; j < ny; j++) for (int i = 0; i < nx; i++) itot += acc[i + ld * j];
+    const double total = (double)itot * (1.0 / scale);
+    const double sub = total / (m->xmax - m->xmin) / (m->ymax - m->ymin);
+    const double dxdy = dx * dy;
+    for (int j = 0; j < ny; j++)
+        for (int i = 0; i < nx; i++) {
+            double raw = (double)acc[i + ld * j] * (1.0 / scale);
+            double val = raw / dxdy;
+            rho[i + ld * j] = val - sub;
+        }
+    for (int i = 0; i < nx; i++) rho[i + ld * ny] = rho[i];
+    for (int j = 0; j < ny; j++) rho[nx + ld * j] = rho[ld * j];
+    rho[nx + ld * ny] = rho[0];
+    free(acc);
+    return total;
+}
+
 /* ------------------------------------------------------------------------------------ */
 /* interpolate_eb_m6_real     fortran/interpolation_m6.F90:193-327, src/interpolation.jl:125-247 */
 /* ------------------------------------------------------------------------------------ */
@@ -754,57 +789,105 @@ void orc_compute_v(int ntau, double eps, int64_t np, const double *t_, const dou
 /* faithful=1 also performs the third (dead) interpolation of every step (:121).            */
 /* ------------------------------------------------------------------------------------ */
 
+typedef struct {
+    orc_mesh m; int ntau; double eps, dt, w; int64_t np; int wrap, faithful;
+    double *x, *v;                     /* caller-owned (2,np) */
+    double *rho, *emesh, *ep, *b, *t, *pl, *ql, *et, *xt, *xf, *yt, *yf, *fx, *fy, *gx, *gy;
+} orc_sim;
+
+void orc_sim_destroy(orc_sim *s)
+{
+    if (!s) return;
+    free(s->rho); free(s->emesh); free(s->ep); free(s->b); free(s->t); free(s->pl); free(s->ql); free(s->et);
+    free(s->xt); free(s->xf); free(s->yt); free(s->yf); free(s->fx); free(s->fy); free(s->gx); free(s->gy);
+    free(s);
+}
+
+/* allocations of bupdate.F90:71-87 */
+orc_sim *orc_sim_create(const orc_mesh *m, int ntau, double eps, double dt, int64_t np, double w, double *x, double *v,
+                        int wrap, int faithful)
+{
+    if (ntau > 64) return NULL;
+    orc_sim *s = (orc_sim *)calloc(1, sizeof(orc_sim));
+    if (!s) return NULL;
+    s->m = *m; s->ntau = ntau; s->eps = eps; s->dt = dt; s->w = w; s->np = np; s->wrap = wrap; s->faithful = faithful;
+    s->x = x; s->v = v;
+    const size_t nrho = (size_t)(m->nx + 1) * (size_t)(m->ny + 1);
+    const size_t big = (size_t)ntau * 2 * (size_t)np;
+    s->rho = (double *)calloc(nrho, sizeof(double));
+    s->emesh = (double *)calloc(2 * nrho, sizeof(double));
+    s->ep = (double *)calloc(2 * (size_t)np + 1, sizeof(double));
+    s->b = (double *)malloc(sizeof(double) * ((size_t)np + 1));
+    s->t = (double *)malloc(sizeof(double) * ((size_t)np + 1));
+    s->pl = (double *)malloc(sizeof(cplx) * ((size_t)ntau * (size_t)np + 1));
+    s->ql = (double *)malloc(sizeof(cplx) * ((size_t)ntau * (size_t)np + 1));
+    s->et = (double *)malloc(sizeof(double) * (big + 1));
+    s->xt = (double *)malloc(sizeof(cplx) * (big + 1)); s->xf = (double *)malloc(sizeof(cplx) * (big + 1));
+    s->yt = (double *)malloc(sizeof(cplx) * (big + 1)); s->yf = (double *)malloc(sizeof(cplx) * (big + 1));
+    s->fx = (double *)malloc(sizeof(cplx) * (big + 1)); s->fy = (double *)malloc(sizeof(cplx) * (big + 1));
+    s->gx = (double *)malloc(sizeof(cplx) * (big + 1)); s->gy = (double *)malloc(sizeof(cplx) * (big + 1));
+    if (!s->rho || !s->emesh || !s->ep || !s->b || !s->t || !s->pl || !s->ql || !s->et || !s->xt || !s->xf || !s->yt ||
+        !s->yf || !s->fx || !s->fy || !s->gx || !s->gy) { orc_sim_destroy(s); return NULL; }
+    return s;
+}
+
+/* bupdate.F90:89-93 ; returns the electric energy of the initial field */
+double orc_sim_init(orc_sim *s)
+{
+    orc_compute_rho_m6(&s->m, s->np, s->x, s->w, s->rho, s->wrap);                /* :89 */
+    double nrj = orc_poisson(&s->m, s->rho, s->emesh);                             /* :91 */
+    orc_interpol_eb_m6(&s->m, s->emesh, s->np, s->x, s->ep, s->wrap);             /* :93 */
+    return nrj;
+}
+
+/* one pass of the loop body bupdate.F90:97-125 ; energy2 gets the two Poisson energies, sumv2 (optional) what :125 prints */
+void orc_sim_step(orc_sim *s, double *energy2, double *sumv2)
+{
+    const orc_mesh *m = &s->m;
+    const int N = s->ntau; const double eps = s->eps; const int64_t np = s->np; const int wrap = s->wrap;
+    orc_preparation(N, eps, s->dt, np, s->x, s->v, s->ep, s->b, s->t, s->pl, s->ql, s->xt, s->yt);   /* :97 */
+    orc_interpol_eb_m6_tau(m, s->emesh, N, np, s->xt, s->et, wrap);               /* :99 */
+    orc_compute_f(N, eps, np, s->b, s->xt, s->yt, s->et, s->fx, s->fy, 1);        /* :101 */
+    orc_ua_step1(N, eps, np, s->t, s->pl, s->xt, s->xf, s->fx);                   /* :103 */
+    orc_ua_step1(N, eps, np, s->t, s->pl, s->yt, s->yf, s->fy);                   /* :104 */
+    orc_compute_rho_m6_tau(m, N, eps, np, s->xt, s->t, s->w, s->rho, s->x, wrap); /* :106 */
+    energy2[0] = orc_poisson(m, s->rho, s->emesh);                                /* :108 */
+    orc_interpol_eb_m6_tau(m, s->emesh, N, np, s->xt, s->et, wrap);               /* :110 */
+    orc_compute_f(N, eps, np, s->b, s->xt, s->yt, s->et, s->gx, s->gy, 1);        /* :112 */
+    orc_ua_step2(N, eps, np, s->t, s->pl, s->ql, s->xt, s->xf, s->fx, s->gx);     /* :114 */
+    orc_ua_step2(N, eps, np, s->t, s->pl, s->ql, s->yt, s->yf, s->fy, s->gy);     /* :115 */
+    orc_compute_rho_m6_tau(m, N, eps, np, s->xt, s->t, s->w, s->rho, s->x, wrap); /* :117 */
+    energy2[1] = orc_poisson(m, s->rho, s->emesh);                                /* :119 */
+    if (s->faithful) orc_interpol_eb_m6_tau(m, s->emesh, N, np, s->xt, s->et, wrap);   /* :121 (result never read) */
+    orc_compute_v(N, eps, np, s->t, s->yt, s->yf, s->v);                          /* :123 */
+    if (sumv2) {
+        double sx = 0.0, sy = 0.0;
+        for (int64_t k = 0; k < np; k++) { sx += s->v[2 * k]; sy += s->v[2 * k + 1]; }   /* :125 */
+        sumv2[0] = sx; sumv2[1] = sy;
+    }
+}
+
+void orc_sim_get(const orc_sim *s, double *e_part_out, double *emesh_out)
+{
+    const size_t nrho = (size_t)(s->m.nx + 1) * (size_t)(s->m.ny + 1);
+    if (e_part_out) memcpy(e_part_out, s->ep, sizeof(double) * 2 * (size_t)s->np);
+    if (emesh_out) memcpy(emesh_out, s->emesh, sizeof(double) * 2 * nrho);
+}
+
 int orc_run_bupdate(const orc_mesh *m, int ntau, double eps, double dt, int nstep, int64_t np, double w,
                     double *x, double *v, double *e_part_out, double *emesh_out, double *energy, double *sumv,
                     int wrap, int faithful)
 {
-    const int N = ntau;
-    if (N > 64) return -1;
-    const size_t nrho = (size_t)(m->nx + 1) * (size_t)(m->ny + 1);
-    const size_t big = (size_t)N * 2 * (size_t)np;
-    double *rho = (double *)calloc(nrho, sizeof(double));
-    double *emesh = (double *)calloc(2 * nrho, sizeof(double));
-    double *ep = (double *)calloc(2 * (size_t)np, sizeof(double));
-    double *b = (double *)malloc(sizeof(double) * (size_t)np), *t = (double *)malloc(sizeof(double) * (size_t)np);
-    double *pl = (double *)malloc(sizeof(cplx) * (size_t)N * (size_t)np), *ql = (double *)malloc(sizeof(cplx) * (size_t)N * (size_t)np);
-    double *et = (double *)malloc(sizeof(double) * big);
-    double *xt = (double *)malloc(sizeof(cplx) * big), *xf = (double *)malloc(sizeof(cplx) * big);
-    double *yt = (double *)malloc(sizeof(cplx) * big), *yf = (double *)malloc(sizeof(cplx) * big);
-    double *fx = (double *)malloc(sizeof(cplx) * big), *fy = (double *)malloc(sizeof(cplx) * big);
-    double *gx = (double *)malloc(sizeof(cplx) * big), *gy = (double *)malloc(sizeof(cplx) * big);
-    if (!rho || !emesh || !ep || !b || !t || !pl || !ql || !et || !xt || !xf || !yt || !yf || !fx || !fy || !gx || !gy) return -2;
-
+    orc_sim *s = orc_sim_create(m, ntau, eps, dt, np, w, x, v, wrap, faithful);
+    if (!s) return -2;
     int ie = 0;
-    orc_compute_rho_m6(m, np, x, w, rho, wrap);                                   /* bupdate.F90:89 */
-    energy[ie++] = orc_poisson(m, rho, emesh);                                    /* :91 */
-    orc_interpol_eb_m6(m, emesh, np, x, ep, wrap);                                /* :93 */
-
+    energy[ie++] = orc_sim_init(s);
     for (int istep = 0; istep < nstep; istep++) {
-        orc_preparation(N, eps, dt, np, x, v, ep, b, t, pl, ql, xt, yt);          /* :97 */
-        orc_interpol_eb_m6_tau(m, emesh, N, np, xt, et, wrap);                    /* :99 */
-        orc_compute_f(N, eps, np, b, xt, yt, et, fx, fy, 1);                      /* :101 */
-        orc_ua_step1(N, eps, np, t, pl, xt, xf, fx);                              /* :103 */
-        orc_ua_step1(N, eps, np, t, pl, yt, yf, fy);                              /* :104 */
-        orc_compute_rho_m6_tau(m, N, eps, np, xt, t, w, rho, x, wrap);            /* :106 */
-        energy[ie++] = orc_poisson(m, rho, emesh);                                /* :108 */
-        orc_interpol_eb_m6_tau(m, emesh, N, np, xt, et, wrap);                    /* :110 */
-        orc_compute_f(N, eps, np, b, xt, yt, et, gx, gy, 1);                      /* :112 */
-        orc_ua_step2(N, eps, np, t, pl, ql, xt, xf, fx, gx);                      /* :114 */
-        orc_ua_step2(N, eps, np, t, pl, ql, yt, yf, fy, gy);                      /* :115 */
-        orc_compute_rho_m6_tau(m, N, eps, np, xt, t, w, rho, x, wrap);            /* :117 */
-        energy[ie++] = orc_poisson(m, rho, emesh);                                /* :119 */
-        if (faithful) orc_interpol_eb_m6_tau(m, emesh, N, np, xt, et, wrap);      /* :121 (result never read) */
-        orc_compute_v(N, eps, np, t, yt, yf, v);                                  /* :123 */
-        if (sumv) {
-            double sx = 0.0, sy = 0.0;
-            for (int64_t k = 0; k < np; k++) { sx += v[2 * k]; sy += v[2 * k + 1]; }   /* :125 */
-            sumv[2 * istep] = sx; sumv[2 * istep + 1] = sy;
-        }
+        orc_sim_step(s, energy + ie, sumv ? sumv + 2 * istep : NULL);
+        ie += 2;
     }
-    if (e_part_out) memcpy(e_part_out, ep, sizeof(double) * 2 * (size_t)np);
-    if (emesh_out) memcpy(emesh_out, emesh, sizeof(double) * 2 * nrho);
-    free(rho); free(emesh); free(ep); free(b); free(t); free(pl); free(ql); free(et);
-    free(xt); free(xf); free(yt); free(yf); free(fx); free(fy); free(gx); free(gy);
+    orc_sim_get(s, e_part_out, emesh_out);
+    orc_sim_destroy(s);
     return 0;
 }
 

@@ -1,0 +1,735 @@
+// uapic_capi.cu -- the C ABI declared in include/uapic_b200.h: host-side glue only (allocation, H2D/D2H,
+// launch ordering).  No compute happens on the host and there is no CPU fallback.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/uapic_b200.h"
+#include "uapic_internal.h"
+
+using namespace uapic;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(expr)                                                                                              \
+    do {                                                                                                      \
+        cudaError_t _e = (expr);                                                                              \
+        if (_e != cudaSuccess)                                                                                \
+            return fail(_e == cudaErrorMemoryAllocation ? UAPIC_ENOMEM : UAPIC_ECUDA, "%s failed: %s (%s:%d)", \
+                        #expr, cudaGetErrorString(_e), __FILE__, __LINE__);                                   \
+    } while (0)
+
+struct DeviceInfo { int ok; int sm_count; int major, minor; };
+
+int device_info(int device, DeviceInfo *out) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return fail(UAPIC_ENODEVICE, "no CUDA device available (%s); libuapic_b200 has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= n) return fail(UAPIC_EINVAL, "device %d out of range (0..%d)", device, n - 1);
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(UAPIC_ENODEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    out->ok = 1; out->sm_count = prop.multiProcessorCount; out->major = prop.major; out->minor = prop.minor;
+    return UAPIC_OK;
+}
+
+int check_mesh(const uapic_mesh_t *mesh) {
+    if (!mesh) return fail(UAPIC_EINVAL, "mesh is null");
+    if (mesh->nx < 2 || mesh->ny < 2) return fail(UAPIC_EINVAL, "mesh needs nx, ny >= 2 (got %d x %d)", mesh->nx, mesh->ny);
+    if (!(mesh->xmax > mesh->xmin) || !(mesh->ymax > mesh->ymin)) return fail(UAPIC_EINVAL, "mesh extent must be positive");
+    return UAPIC_OK;
+}
+
+MeshDev make_mesh(const uapic_mesh_t *mesh) {
+    MeshDev m;
+    m.xmin = mesh->xmin; m.ymin = mesh->ymin;
+    m.dimx = mesh->xmax - mesh->xmin; m.dimy = mesh->ymax - mesh->ymin;
+    m.dx = (mesh->xmax - mesh->xmin) / (double)mesh->nx;      // meshfields.F90:71
+    m.dy = (mesh->ymax - mesh->ymin) / (double)mesh->ny;      // meshfields.F90:72
+    m.nx = mesh->nx; m.ny = mesh->ny; m.ld = mesh->nx + 1;
+    return m;
+}
+
+int check_ntau(int ntau) {
+    if (!ntau_supported(ntau)) return fail(UAPIC_EINVAL, "ntau must be a power of two in [2,32] (got %d)", ntau);
+    return UAPIC_OK;
+}
+
+// RAII device buffer
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t n) {
+        bytes = n;
+        if (n == 0) { p = nullptr; return cudaSuccess; }
+        return cudaMalloc(&p, n);
+    }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+// scratch context for the synchronous stage API (device 0 of the current context, default stream)
+struct StageCtx {
+    LaunchCtx lc;
+    int init() {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) { cudaGetLastError(); dev = 0; }
+        DeviceInfo di{};
+        int rc = device_info(dev, &di);
+        if (rc) return rc;
+        lc.stream = 0; lc.sm_count = di.sm_count; lc.launches = nullptr;
+        return UAPIC_OK;
+    }
+};
+
+#define STAGE_BEGIN()            \
+    StageCtx sc;                 \
+    {                            \
+        int _rc = sc.init();     \
+        if (_rc) return _rc;     \
+    }
+
+int up(DevBuf &d, const void *h, size_t bytes) {
+    CU(d.alloc(bytes));
+    if (bytes && h) CU(cudaMemcpy(d.p, h, bytes, cudaMemcpyHostToDevice));
+    return UAPIC_OK;
+}
+int down(void *h, const DevBuf &d, size_t bytes) {
+    if (bytes && h) CU(cudaMemcpy(h, d.p, bytes, cudaMemcpyDeviceToHost));
+    return UAPIC_OK;
+}
+#define TRY(x) do { int _r = (x); if (_r) return _r; } while (0)
+
+double fixed_point_scale(double total_mass) {
+    // partial sums never exceed the total deposited mass; keep one guard bit below 2^62
+    int e = 0;
+    std::frexp(total_mass > 0 ? total_mass : 1.0, &e);   // total_mass < 2^e
+    int S = 61 - e;
+    if (S > 60) S = 60;
+    if (S < 8) S = 8;
+    return std::ldexp(1.0, S);
+}
+
+struct RawRho {
+    DevBuf buf;
+    RhoAcc acc{};
+    int init(const MeshDev &m, int deposit_mode, double total_mass, cudaStream_t stream) {
+        const size_t n = (size_t)m.ld * (m.ny + 1);
+        CU(buf.alloc(n * 8));
+        CU(cudaMemsetAsync(buf.p, 0, n * 8, stream));
+        if (deposit_mode == UAPIC_DEPOSIT_FIXED_POINT) {
+            acc.f64 = nullptr; acc.i64 = buf.as<unsigned long long>(); acc.scale = fixed_point_scale(total_mass);
+        } else if (deposit_mode == UAPIC_DEPOSIT_FP64_ATOMIC) {
+            acc.f64 = buf.as<double>(); acc.i64 = nullptr; acc.scale = 1.0;
+        } else {
+            return fail(UAPIC_EINVAL, "unknown deposit_mode %d", deposit_mode);
+        }
+        return UAPIC_OK;
+    }
+};
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+const char *uapic_last_error(void) { return g_err.c_str(); }
+int uapic_version(void) { return 100; }
+int uapic_compiled_arch(void) { return 100; }
+
+int uapic_fixed_point_scale(double total_mass, double *scale) {
+    if (!scale) return fail(UAPIC_EINVAL, "scale is null");
+    *scale = fixed_point_scale(total_mass);
+    return UAPIC_OK;
+}
+
+int uapic_device_count(int *count) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { cudaGetLastError(); n = 0; }
+    if (count) *count = n;
+    if (n <= 0) return fail(UAPIC_ENODEVICE, "no CUDA device available; libuapic_b200 has no CPU fallback");
+    return UAPIC_OK;
+}
+
+// ---- stage API ---------------------------------------------------------------------------------------------
+
+int uapic_compute_rho_m6(const uapic_mesh_t *mesh, int64_t nbpart, double *x, double w, double *rho, int wrap,
+                         int deposit_mode, double *rho_total) {
+    TRY(check_mesh(mesh));
+    if (!x || !rho || nbpart < 0) return fail(UAPIC_EINVAL, "uapic_compute_rho_m6: null pointer or negative nbpart");
+    STAGE_BEGIN();
+    const MeshDev m = make_mesh(mesh);
+    const size_t nrho = (size_t)m.ld * (m.ny + 1);
+    DevBuf dx, drho, dtot;
+    RawRho raw;
+    TRY(up(dx, x, sizeof(double) * 2 * (size_t)nbpart));
+    TRY(raw.init(m, deposit_mode, m.dimx * m.dimy > w * (double)nbpart ? m.dimx * m.dimy : w * (double)nbpart, 0));
+    CU(drho.alloc(nrho * 8));
+    CU(dtot.alloc(8));
+    CU(launch_deposit(sc.lc, m, nbpart, dx.as<double>(), w, raw.acc, wrap));
+    CU(launch_rho_epilogue(sc.lc, m, raw.acc, drho.as<double>(), dtot.as<double>()));
+    CU(cudaDeviceSynchronize());
+    TRY(down(rho, drho, nrho * 8));
+    if (rho_total) TRY(down(rho_total, dtot, 8));
+    if (wrap == UAPIC_WRAP_JULIA) TRY(down(x, dx, sizeof(double) * 2 * (size_t)nbpart));
+    return UAPIC_OK;
+}
+
+int uapic_interpol_eb_m6(const uapic_mesh_t *mesh, const double *e, int64_t nbpart, double *x, double *ep, int wrap) {
+    TRY(check_mesh(mesh));
+    if (!e || !x || !ep || nbpart < 0) return fail(UAPIC_EINVAL, "uapic_interpol_eb_m6: null pointer or negative nbpart");
+    STAGE_BEGIN();
+    const MeshDev m = make_mesh(mesh);
+    const size_t nrho = (size_t)m.ld * (m.ny + 1);
+    DevBuf de, dx, dep;
+    TRY(up(de, e, nrho * 16));
+    TRY(up(dx, x, sizeof(double) * 2 * (size_t)nbpart));
+    CU(dep.alloc(sizeof(double) * 2 * (size_t)nbpart));
+    CU(launch_gather(sc.lc, m, de.as<double>(), nbpart, dx.as<double>(), dep.as<double>(), wrap));
+    CU(cudaDeviceSynchronize());
+    TRY(down(ep, dep, sizeof(double) * 2 * (size_t)nbpart));
+    if (wrap == UAPIC_WRAP_JULIA) TRY(down(x, dx, sizeof(double) * 2 * (size_t)nbpart));
+    return UAPIC_OK;
+}
+
+int uapic_poisson(const uapic_mesh_t *mesh, const double *rho, double *e, double *energy) {
+    TRY(check_mesh(mesh));
+    if (!rho || !e) return fail(UAPIC_EINVAL, "uapic_poisson: null pointer");
+    if (!poisson_size_supported(mesh->nx) || !poisson_size_supported(mesh->ny))
+        return fail(UAPIC_EUNSUPPORTED, "Poisson mesh %d x %d: sizes must be powers of two <= 1024 or any n <= 512", mesh->nx, mesh->ny);
+    STAGE_BEGIN();
+    const MeshDev m = make_mesh(mesh);
+    const size_t nrho = (size_t)m.ld * (m.ny + 1);
+    const size_t nk = (size_t)(m.nx / 2 + 1) * m.ny;
+    DevBuf drho, de, drk, dek, dnrj;
+    TRY(up(drho, rho, nrho * 8));
+    CU(de.alloc(nrho * 16));
+    CU(drk.alloc(nk * 16));
+    CU(dek.alloc(nk * 32));
+    CU(dnrj.alloc(8));
+    PoissonWork pw{drk.as<double2>(), dek.as<double2>()};
+    CU(launch_poisson(sc.lc, m, pw, drho.as<double>(), de.as<double>(), dnrj.as<double>()));
+    CU(cudaDeviceSynchronize());
+    TRY(down(e, de, nrho * 16));
+    if (energy) TRY(down(energy, dnrj, 8));
+    return UAPIC_OK;
+}
+
+int uapic_preparation(int ntau, double eps, double dt, int64_t nbpart, const double *x, const double *v, const double *e,
+                      double *b, double *t, double *pl, double *ql, double *xt, double *yt) {
+    TRY(check_ntau(ntau));
+    if (!x || !v || !e || !b || !t || !pl || !ql || !xt || !yt || nbpart < 0)
+        return fail(UAPIC_EINVAL, "uapic_preparation: null pointer or negative nbpart");
+    STAGE_BEGIN();
+    const size_t np = (size_t)nbpart, big = 16 * (size_t)ntau * 2 * np;
+    DevBuf dx, dv, de, db, dtt, dpl, dql, dxt, dyt;
+    TRY(up(dx, x, 16 * np)); TRY(up(dv, v, 16 * np)); TRY(up(de, e, 16 * np));
+    CU(db.alloc(8 * np)); CU(dtt.alloc(8 * np));
+    CU(dpl.alloc(16 * (size_t)ntau * np)); CU(dql.alloc(16 * (size_t)ntau * np));
+    CU(dxt.alloc(big)); CU(dyt.alloc(big));
+    CU(launch_preparation(sc.lc, ntau, eps, dt, nbpart, dx.as<double>(), dv.as<double>(), de.as<double>(), db.as<double>(),
+                          dtt.as<double>(), dpl.as<double>(), dql.as<double>(), dxt.as<double>(), dyt.as<double>()));
+    CU(cudaDeviceSynchronize());
+    TRY(down(b, db, 8 * np)); TRY(down(t, dtt, 8 * np));
+    TRY(down(pl, dpl, 16 * (size_t)ntau * np)); TRY(down(ql, dql, 16 * (size_t)ntau * np));
+    TRY(down(xt, dxt, big)); TRY(down(yt, dyt, big));
+    return UAPIC_OK;
+}
+
+int uapic_interpol_eb_m6_tau(const uapic_mesh_t *mesh, const double *e, int ntau, int64_t nbpart, const double *xt,
+                             double *et, int wrap) {
+    TRY(check_mesh(mesh));
+    if (ntau < 1 || !e || !xt || !et || nbpart < 0) return fail(UAPIC_EINVAL, "uapic_interpol_eb_m6_tau: bad argument");
+    STAGE_BEGIN();
+    const MeshDev m = make_mesh(mesh);
+    const size_t nrho = (size_t)m.ld * (m.ny + 1), ns = (size_t)ntau * 2 * (size_t)nbpart;
+    DevBuf de, dxt, det;
+    TRY(up(de, e, nrho * 16));
+    TRY(up(dxt, xt, ns * 16));
+    CU(det.alloc(ns * 8));
+    CU(launch_gather_tau(sc.lc, m, de.as<double>(), ntau, nbpart, dxt.as<double>(), det.as<double>(), wrap));
+    CU(cudaDeviceSynchronize());
+    TRY(down(et, det, ns * 8));
+    return UAPIC_OK;
+}
+
+int uapic_compute_f(int ntau, double eps, int64_t nbpart, const double *b, const double *xt, const double *yt,
+                    const double *et, double *fx, double *fy, int normalise) {
+    TRY(check_ntau(ntau));
+    if (!b || !xt || !yt || !et || !fx || !fy || nbpart < 0) return fail(UAPIC_EINVAL, "uapic_compute_f: bad argument");
+    STAGE_BEGIN();
+    const size_t np = (size_t)nbpart, ns = (size_t)ntau * 2 * np;
+    DevBuf db, dxt, dyt, det, dfx, dfy;
+    TRY(up(db, b, 8 * np)); TRY(up(dxt, xt, 16 * ns)); TRY(up(dyt, yt, 16 * ns)); TRY(up(det, et, 8 * ns));
+    CU(dfx.alloc(16 * ns)); CU(dfy.alloc(16 * ns));
+    CU(launch_compute_f(sc.lc, ntau, eps, nbpart, db.as<double>(), dxt.as<double>(), dyt.as<double>(), det.as<double>(),
+                        dfx.as<double>(), dfy.as<double>(), normalise));
+    CU(cudaDeviceSynchronize());
+    TRY(down(fx, dfx, 16 * ns)); TRY(down(fy, dfy, 16 * ns));
+    return UAPIC_OK;
+}
+
+int uapic_fft_tau(int ntau, int64_t nvec, const double *in, double *out, int sign, int normalise) {
+    TRY(check_ntau(ntau));
+    if (!in || !out || nvec < 0 || (sign != 1 && sign != -1)) return fail(UAPIC_EINVAL, "uapic_fft_tau: bad argument");
+    STAGE_BEGIN();
+    const size_t ns = (size_t)ntau * (size_t)nvec;
+    DevBuf din, dout;
+    TRY(up(din, in, 16 * ns));
+    CU(dout.alloc(16 * ns));
+    CU(launch_fft_tau(sc.lc, ntau, nvec, din.as<double>(), dout.as<double>(), sign, normalise));
+    CU(cudaDeviceSynchronize());
+    TRY(down(out, dout, 16 * ns));
+    return UAPIC_OK;
+}
+
+static int step_pointwise(int ntau, double eps, int64_t nbpart, const double *t, const double *pl, const double *ql,
+                          const double *xf, const double *fx, const double *gx, double *xt) {
+    if (ntau < 2 || (ntau & 1)) return fail(UAPIC_EINVAL, "ntau must be even (got %d)", ntau);
+    if (!t || !pl || !xf || !fx || !xt || nbpart < 0) return fail(UAPIC_EINVAL, "ua_step: bad argument");
+    STAGE_BEGIN();
+    const size_t np = (size_t)nbpart, ns = (size_t)ntau * 2 * np;
+    DevBuf dt_, dpl, dql, dxf, dfx, dgx, dout;
+    TRY(up(dt_, t, 8 * np)); TRY(up(dpl, pl, 16 * (size_t)ntau * np));
+    if (gx) { TRY(up(dql, ql, 16 * (size_t)ntau * np)); TRY(up(dgx, gx, 16 * ns)); }
+    TRY(up(dxf, xf, 16 * ns)); TRY(up(dfx, fx, 16 * ns));
+    CU(dout.alloc(16 * ns));
+    CU(launch_step_pointwise(sc.lc, ntau, eps, nbpart, dt_.as<double>(), dpl.as<double>(), gx ? dql.as<double>() : nullptr,
+                             dxf.as<double>(), dfx.as<double>(), gx ? dgx.as<double>() : nullptr, dout.as<double>()));
+    CU(cudaDeviceSynchronize());
+    TRY(down(xt, dout, 16 * ns));
+    return UAPIC_OK;
+}
+
+int uapic_ua_step_predict(int ntau, double eps, int64_t nbpart, const double *t, const double *pl, const double *xf,
+                          const double *fx, double *xt) {
+    return step_pointwise(ntau, eps, nbpart, t, pl, nullptr, xf, fx, nullptr, xt);
+}
+
+int uapic_ua_step_correct(int ntau, double eps, int64_t nbpart, const double *t, const double *pl, const double *ql,
+                          const double *xf, const double *fx, const double *gx, double *xt) {
+    if (!ql || !gx) return fail(UAPIC_EINVAL, "uapic_ua_step_correct: null pointer");
+    return step_pointwise(ntau, eps, nbpart, t, pl, ql, xf, fx, gx, xt);
+}
+
+static int step_fortran(int ntau, double eps, int64_t nbpart, const double *t, const double *pl, const double *ql,
+                        double *xt, double *xf, const double *fx, const double *gx, int corrector) {
+    TRY(check_ntau(ntau));
+    if (!t || !pl || !xt || !xf || !fx || nbpart < 0) return fail(UAPIC_EINVAL, "ua_step1/2: bad argument");
+    STAGE_BEGIN();
+    const size_t np = (size_t)nbpart, ns = (size_t)ntau * 2 * np;
+    DevBuf dt_, dpl, dql, dxt, dxf, dfx, dgx;
+    TRY(up(dt_, t, 8 * np)); TRY(up(dpl, pl, 16 * (size_t)ntau * np));
+    TRY(up(dfx, fx, 16 * ns));
+    if (corrector) {
+        TRY(up(dql, ql, 16 * (size_t)ntau * np)); TRY(up(dgx, gx, 16 * ns)); TRY(up(dxf, xf, 16 * ns));
+        CU(dxt.alloc(16 * ns));
+    } else {
+        TRY(up(dxt, xt, 16 * ns));
+        CU(dxf.alloc(16 * ns));
+    }
+    CU(launch_step_fortran(sc.lc, ntau, eps, nbpart, dt_.as<double>(), dpl.as<double>(), corrector ? dql.as<double>() : nullptr,
+                           dxt.as<double>(), dxf.as<double>(), dfx.as<double>(), corrector ? dgx.as<double>() : nullptr, corrector));
+    CU(cudaDeviceSynchronize());
+    TRY(down(xt, dxt, 16 * ns));
+    if (!corrector) TRY(down(xf, dxf, 16 * ns));
+    return UAPIC_OK;
+}
+
+int uapic_ua_step1(int ntau, double eps, int64_t nbpart, const double *t, const double *pl, double *xt, double *xf,
+                   const double *fx) {
+    return step_fortran(ntau, eps, nbpart, t, pl, nullptr, xt, xf, fx, nullptr, 0);
+}
+
+int uapic_ua_step2(int ntau, double eps, int64_t nbpart, const double *t, const double *pl, const double *ql, double *xt,
+                   const double *xf, const double *fx, const double *gx) {
+    if (!ql || !gx) return fail(UAPIC_EINVAL, "uapic_ua_step2: null pointer");
+    return step_fortran(ntau, eps, nbpart, t, pl, ql, xt, const_cast<double *>(xf), fx, gx, 1);
+}
+
+int uapic_compute_rho_m6_tau(const uapic_mesh_t *mesh, int ntau, double eps, int64_t nbpart, const double *xt,
+                             const double *t, double w, double *rho, double *x, int wrap, int deposit_mode,
+                             double *rho_total) {
+    TRY(check_mesh(mesh));
+    TRY(check_ntau(ntau));
+    if (!xt || !t || !rho || !x || nbpart < 0) return fail(UAPIC_EINVAL, "uapic_compute_rho_m6_tau: bad argument");
+    STAGE_BEGIN();
+    const MeshDev m = make_mesh(mesh);
+    const size_t np = (size_t)nbpart, ns = (size_t)ntau * 2 * np, nrho = (size_t)m.ld * (m.ny + 1);
+    DevBuf dxt, dt_, dx, drho, dtot;
+    RawRho raw;
+    TRY(up(dxt, xt, 16 * ns)); TRY(up(dt_, t, 8 * np));
+    CU(dx.alloc(16 * np)); CU(drho.alloc(8 * nrho)); CU(dtot.alloc(8));
+    TRY(raw.init(m, deposit_mode, m.dimx * m.dimy > w * (double)nbpart ? m.dimx * m.dimy : w * (double)nbpart, 0));
+    CU(launch_deposit_tau(sc.lc, m, ntau, eps, nbpart, dxt.as<double>(), dt_.as<double>(), w, raw.acc, dx.as<double>(), wrap));
+    CU(launch_rho_epilogue(sc.lc, m, raw.acc, drho.as<double>(), dtot.as<double>()));
+    CU(cudaDeviceSynchronize());
+    TRY(down(rho, drho, 8 * nrho)); TRY(down(x, dx, 16 * np));
+    if (rho_total) TRY(down(rho_total, dtot, 8));
+    return UAPIC_OK;
+}
+
+int uapic_compute_v(int ntau, double eps, int64_t nbpart, const double *t, const double *yt, int yt_is_fourier, double *v) {
+    TRY(check_ntau(ntau));
+    if (!t || !yt || !v || nbpart < 0) return fail(UAPIC_EINVAL, "uapic_compute_v: bad argument");
+    STAGE_BEGIN();
+    const size_t np = (size_t)nbpart, ns = (size_t)ntau * 2 * np;
+    DevBuf dt_, dyt, dv;
+    TRY(up(dt_, t, 8 * np)); TRY(up(dyt, yt, 16 * ns));
+    CU(dv.alloc(16 * np));
+    CU(launch_compute_v(sc.lc, ntau, eps, nbpart, dt_.as<double>(), dyt.as<double>(), yt_is_fourier, dv.as<double>()));
+    CU(cudaDeviceSynchronize());
+    TRY(down(v, dv, 16 * np));
+    return UAPIC_OK;
+}
+
+}  // extern "C"
+
+// ================================================================================================
+// session
+// ================================================================================================
+
+struct uapic_session {
+    uapic_config_t cfg;
+    MeshDev m;
+    LaunchCtx lc;
+    int64_t launches = 0;
+    int64_t np_global = 0;
+    DevBuf x, v, ep, store, tb, raw, rho, emesh, rk, ek, energy, sumv;
+    RhoAcc acc{};
+    int64_t n_energy = 0, cap_energy = 0;
+    uapic_allreduce_fn reduce = nullptr;
+    void *reduce_ctx = nullptr;
+    bool have_particles = false, fields_ready = false;
+    int64_t bytes = 0;
+    // optional per-kernel timing
+    bool timing = false;
+    std::vector<cudaEvent_t> ev;     // 4 per step: A0 A1 B0 B1
+    double ms_a = 0, ms_b = 0;
+    int64_t timed_steps = 0;
+    ~uapic_session() { for (cudaEvent_t e : ev) cudaEventDestroy(e); }
+};
+
+namespace {
+
+int session_alloc(uapic_session *s, DevBuf &b, size_t n) {
+    cudaError_t e = b.alloc(n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(UAPIC_ENOMEM, "device allocation of %.3f GB failed (%s); session already holds %.3f GB", (double)n / 1e9,
+                    cudaGetErrorString(e), (double)s->bytes / 1e9);
+    }
+    s->bytes += (int64_t)n;
+    return UAPIC_OK;
+}
+
+int session_bind(uapic_session *s) {
+    CU(cudaSetDevice(s->cfg.device));
+    return UAPIC_OK;
+}
+
+int session_clear_raw(uapic_session *s) {
+    CU(cudaMemsetAsync(s->raw.p, 0, s->raw.bytes, s->lc.stream));
+    return UAPIC_OK;
+}
+
+// raw deposits -> (sum over ranks) -> neutralised rho -> E, energy appended      compute_rho_m6.F90:191-200 + poisson_2d.f90:85-111
+int session_field_solve(uapic_session *s) {
+    if (s->reduce) {
+        const int64_t n = (int64_t)s->m.ld * (s->m.ny + 1);
+        int rc = s->reduce(s->reduce_ctx, s->raw.p, n, s->acc.i64 ? 1 : 0, (void *)s->lc.stream);
+        if (rc) return fail(UAPIC_ECUDA, "allreduce callback failed with code %d", rc);
+    }
+    CU(launch_rho_epilogue(s->lc, s->m, s->acc, s->rho.as<double>(), nullptr));
+    if (s->n_energy >= s->cap_energy) return fail(UAPIC_ESTATE, "energy history full (%lld entries)", (long long)s->cap_energy);
+    PoissonWork pw{s->rk.as<double2>(), s->ek.as<double2>()};
+    CU(launch_poisson(s->lc, s->m, pw, s->rho.as<double>(), s->emesh.as<double>(), s->energy.as<double>() + s->n_energy));
+    s->n_energy++;
+    return UAPIC_OK;
+}
+
+PhaseParams session_params(uapic_session *s) {
+    PhaseParams p;
+    p.m = s->m; p.eps = s->cfg.eps; p.dt = s->cfg.dt; p.weight = s->cfg.weight; p.np = s->cfg.nbpart;
+    p.wrap = s->cfg.wrap; p.ntau = s->cfg.ntau;
+    p.x = s->x.as<double2>(); p.v = s->v.as<double2>(); p.ep = s->ep.as<double2>();
+    p.emesh = s->emesh.as<double2>(); p.store = s->store.as<double2>(); p.tb = s->tb.as<double2>();
+    p.rho = s->acc;
+    return p;
+}
+
+}  // namespace
+
+extern "C" {
+
+int uapic_session_create(const uapic_config_t *cfg, uapic_session_t **out) {
+    if (!cfg || !out) return fail(UAPIC_EINVAL, "uapic_session_create: null pointer");
+    *out = nullptr;
+    TRY(check_mesh(&cfg->mesh));
+    TRY(check_ntau(cfg->ntau));
+    if (cfg->nbpart < 0) return fail(UAPIC_EINVAL, "nbpart must be >= 0");
+    if (!(cfg->eps > 0) || !(cfg->dt > 0) || !(cfg->weight > 0)) return fail(UAPIC_EINVAL, "eps, dt and weight must be positive");
+    if (cfg->scheme != UAPIC_SCHEME_M6) return fail(UAPIC_EUNSUPPORTED, "only UAPIC_SCHEME_M6 is implemented in the session path");
+    if (cfg->storage_mode != UAPIC_STORE_FULL) return fail(UAPIC_EUNSUPPORTED, "only UAPIC_STORE_FULL is implemented");
+    if (cfg->wrap != UAPIC_WRAP_FORTRAN && cfg->wrap != UAPIC_WRAP_JULIA) return fail(UAPIC_EINVAL, "unknown wrap %d", cfg->wrap);
+    if (!poisson_size_supported(cfg->mesh.nx) || !poisson_size_supported(cfg->mesh.ny))
+        return fail(UAPIC_EUNSUPPORTED, "Poisson mesh %d x %d unsupported", cfg->mesh.nx, cfg->mesh.ny);
+    DeviceInfo di{};
+    TRY(device_info(cfg->device, &di));
+    CU(cudaSetDevice(cfg->device));
+
+    uapic_session *s = new (std::nothrow) uapic_session();
+    if (!s) return fail(UAPIC_ENOMEM, "host allocation failed");
+    s->cfg = *cfg;
+    s->m = make_mesh(&cfg->mesh);
+    s->lc.stream = (cudaStream_t)cfg->stream;
+    s->lc.sm_count = di.sm_count;
+    s->lc.launches = &s->launches;
+    const double total_mass = cfg->total_mass > 0 ? cfg->total_mass : s->m.dimx * s->m.dimy;
+    s->np_global = (int64_t)llround(total_mass / cfg->weight);
+
+    const size_t np = (size_t)cfg->nbpart, N = (size_t)cfg->ntau;
+    const size_t nrho = (size_t)s->m.ld * (s->m.ny + 1), nk = (size_t)(s->m.nx / 2 + 1) * s->m.ny;
+    int rc = UAPIC_OK;
+    s->cap_energy = 1 << 16;
+    if (!rc) rc = session_alloc(s, s->x, 16 * (np ? np : 1));
+    if (!rc) rc = session_alloc(s, s->v, 16 * (np ? np : 1));
+    if (!rc) rc = session_alloc(s, s->ep, 16 * (np ? np : 1));
+    if (!rc) rc = session_alloc(s, s->tb, 16 * (np ? np : 1));
+    if (!rc) rc = session_alloc(s, s->store, 16 * 8 * N * (np ? np : 1));
+    if (!rc) rc = session_alloc(s, s->raw, 8 * nrho);
+    if (!rc) rc = session_alloc(s, s->rho, 8 * nrho);
+    if (!rc) rc = session_alloc(s, s->emesh, 16 * nrho);
+    if (!rc) rc = session_alloc(s, s->rk, 16 * nk);
+    if (!rc) rc = session_alloc(s, s->ek, 32 * nk);
+    if (!rc) rc = session_alloc(s, s->energy, 8 * (size_t)s->cap_energy);
+    if (!rc) rc = session_alloc(s, s->sumv, 16);
+    if (rc) { delete s; return rc; }
+    if (cfg->deposit_mode == UAPIC_DEPOSIT_FIXED_POINT) {
+        s->acc.f64 = nullptr; s->acc.i64 = s->raw.as<unsigned long long>(); s->acc.scale = fixed_point_scale(total_mass);
+    } else if (cfg->deposit_mode == UAPIC_DEPOSIT_FP64_ATOMIC) {
+        s->acc.f64 = s->raw.as<double>(); s->acc.i64 = nullptr; s->acc.scale = 1.0;
+    } else {
+        delete s;
+        return fail(UAPIC_EINVAL, "unknown deposit_mode %d", cfg->deposit_mode);
+    }
+    cudaError_t e = cudaMemsetAsync(s->emesh.p, 0, 16 * nrho, s->lc.stream);
+    if (e != cudaSuccess) { delete s; return fail(UAPIC_ECUDA, "memset failed: %s", cudaGetErrorString(e)); }
+    *out = s;
+    return UAPIC_OK;
+}
+
+int uapic_session_destroy(uapic_session_t *s) {
+    if (!s) return UAPIC_OK;
+    cudaSetDevice(s->cfg.device);
+    cudaStreamSynchronize(s->lc.stream);
+    delete s;
+    return UAPIC_OK;
+}
+
+int uapic_session_set_allreduce(uapic_session_t *s, uapic_allreduce_fn fn, void *ctx) {
+    if (!s) return fail(UAPIC_EINVAL, "session is null");
+    s->reduce = fn; s->reduce_ctx = ctx;
+    return UAPIC_OK;
+}
+
+int uapic_session_upload_particles(uapic_session_t *s, const double *x, const double *v) {
+    if (!s || !x || !v) return fail(UAPIC_EINVAL, "uapic_session_upload_particles: null pointer");
+    TRY(session_bind(s));
+    const size_t n = 16 * (size_t)s->cfg.nbpart;
+    CU(cudaMemcpyAsync(s->x.p, x, n, cudaMemcpyHostToDevice, s->lc.stream));
+    CU(cudaMemcpyAsync(s->v.p, v, n, cudaMemcpyHostToDevice, s->lc.stream));
+    CU(cudaStreamSynchronize(s->lc.stream));
+    s->have_particles = true;
+    return UAPIC_OK;
+}
+
+int uapic_session_upload_particle_e(uapic_session_t *s, const double *ep) {
+    if (!s || !ep) return fail(UAPIC_EINVAL, "uapic_session_upload_particle_e: null pointer");
+    TRY(session_bind(s));
+    CU(cudaMemcpyAsync(s->ep.p, ep, 16 * (size_t)s->cfg.nbpart, cudaMemcpyHostToDevice, s->lc.stream));
+    CU(cudaStreamSynchronize(s->lc.stream));
+    return UAPIC_OK;
+}
+
+namespace {
+int drain_timing(uapic_session *s) {
+    if (s->ev.empty()) return UAPIC_OK;
+    CU(cudaStreamSynchronize(s->lc.stream));
+    for (size_t i = 0; i + 3 < s->ev.size(); i += 4) {
+        float a = 0, b = 0;
+        CU(cudaEventElapsedTime(&a, s->ev[i], s->ev[i + 1]));
+        CU(cudaEventElapsedTime(&b, s->ev[i + 2], s->ev[i + 3]));
+        s->ms_a += a; s->ms_b += b; s->timed_steps++;
+    }
+    for (cudaEvent_t e : s->ev) cudaEventDestroy(e);
+    s->ev.clear();
+    return UAPIC_OK;
+}
+}  // namespace
+
+int uapic_session_enable_timing(uapic_session_t *s, int enable) {
+    if (!s) return fail(UAPIC_EINVAL, "session is null");
+    TRY(session_bind(s));
+    TRY(drain_timing(s));
+    s->timing = enable != 0;
+    s->ms_a = s->ms_b = 0; s->timed_steps = 0;
+    return UAPIC_OK;
+}
+
+int uapic_session_phase_times(uapic_session_t *s, double *ms_phase_a, double *ms_phase_b, int64_t *steps) {
+    if (!s) return fail(UAPIC_EINVAL, "session is null");
+    TRY(session_bind(s));
+    TRY(drain_timing(s));
+    if (ms_phase_a) *ms_phase_a = s->ms_a;
+    if (ms_phase_b) *ms_phase_b = s->ms_b;
+    if (steps) *steps = s->timed_steps;
+    s->ms_a = s->ms_b = 0; s->timed_steps = 0;
+    return UAPIC_OK;
+}
+
+int uapic_session_generate_particles(uapic_session_t *s, int kind, uint64_t seed, int64_t first_global_index, double alpha,
+                                     double kx) {
+    if (!s) return fail(UAPIC_EINVAL, "session is null");
+    if (kind != 0 && kind != 1) return fail(UAPIC_EINVAL, "unknown load kind %d", kind);
+    TRY(session_bind(s));
+    CU(launch_generate(s->lc, s->m, kind, seed, first_global_index, s->cfg.nbpart, s->np_global, alpha, kx, s->x.as<double>(),
+                       s->v.as<double>()));
+    s->have_particles = true;
+    return UAPIC_OK;
+}
+
+int uapic_session_init_fields(uapic_session_t *s) {
+    if (!s) return fail(UAPIC_EINVAL, "session is null");
+    if (!s->have_particles) return fail(UAPIC_ESTATE, "upload or generate particles before uapic_session_init_fields");
+    TRY(session_bind(s));
+    s->n_energy = 0;
+    TRY(session_clear_raw(s));
+    CU(launch_deposit(s->lc, s->m, s->cfg.nbpart, s->x.as<double>(), s->cfg.weight, s->acc, s->cfg.wrap));   // bupdate.F90:89
+    TRY(session_field_solve(s));                                                                              // :91
+    CU(launch_gather(s->lc, s->m, s->emesh.as<double>(), s->cfg.nbpart, s->x.as<double>(), s->ep.as<double>(), s->cfg.wrap));  // :93
+    s->fields_ready = true;
+    return UAPIC_OK;
+}
+
+int uapic_session_step(uapic_session_t *s, int nsteps) {
+    if (!s) return fail(UAPIC_EINVAL, "session is null");
+    if (!s->fields_ready) return fail(UAPIC_ESTATE, "call uapic_session_init_fields before uapic_session_step");
+    if (nsteps < 0) return fail(UAPIC_EINVAL, "nsteps must be >= 0");
+    TRY(session_bind(s));
+    const PhaseParams p = session_params(s);
+    for (int it = 0; it < nsteps; ++it) {
+        cudaEvent_t e4[4] = {nullptr, nullptr, nullptr, nullptr};
+        if (s->timing) {
+            if (s->ev.size() >= 4096) TRY(drain_timing(s));
+            for (int q = 0; q < 4; ++q) { CU(cudaEventCreate(&e4[q])); s->ev.push_back(e4[q]); }
+        }
+        TRY(session_clear_raw(s));
+        if (s->timing) CU(cudaEventRecord(e4[0], s->lc.stream));
+        CU(launch_phase_a(s->lc, p));          // bupdate.F90:97-106
+        if (s->timing) CU(cudaEventRecord(e4[1], s->lc.stream));
+        TRY(session_field_solve(s));           // :108
+        TRY(session_clear_raw(s));
+        if (s->timing) CU(cudaEventRecord(e4[2], s->lc.stream));
+        CU(launch_phase_b(s->lc, p));          // :110-117, :123
+        if (s->timing) CU(cudaEventRecord(e4[3], s->lc.stream));
+        TRY(session_field_solve(s));           // :119
+    }
+    return UAPIC_OK;
+}
+
+int uapic_session_synchronize(uapic_session_t *s) {
+    if (!s) return fail(UAPIC_EINVAL, "session is null");
+    TRY(session_bind(s));
+    CU(cudaStreamSynchronize(s->lc.stream));
+    return UAPIC_OK;
+}
+
+int uapic_session_download_particles(uapic_session_t *s, double *x, double *v) {
+    if (!s) return fail(UAPIC_EINVAL, "session is null");
+    TRY(session_bind(s));
+    const size_t n = 16 * (size_t)s->cfg.nbpart;
+    if (x) CU(cudaMemcpyAsync(x, s->x.p, n, cudaMemcpyDeviceToHost, s->lc.stream));
+    if (v) CU(cudaMemcpyAsync(v, s->v.p, n, cudaMemcpyDeviceToHost, s->lc.stream));
+    CU(cudaStreamSynchronize(s->lc.stream));
+    return UAPIC_OK;
+}
+
+int uapic_session_download_particle_e(uapic_session_t *s, double *ep) {
+    if (!s || !ep) return fail(UAPIC_EINVAL, "null pointer");
+    TRY(session_bind(s));
+    CU(cudaMemcpyAsync(ep, s->ep.p, 16 * (size_t)s->cfg.nbpart, cudaMemcpyDeviceToHost, s->lc.stream));
+    CU(cudaStreamSynchronize(s->lc.stream));
+    return UAPIC_OK;
+}
+
+int uapic_session_download_fields(uapic_session_t *s, double *e, double *rho) {
+    if (!s) return fail(UAPIC_EINVAL, "session is null");
+    TRY(session_bind(s));
+    const size_t nrho = (size_t)s->m.ld * (s->m.ny + 1);
+    if (e) CU(cudaMemcpyAsync(e, s->emesh.p, 16 * nrho, cudaMemcpyDeviceToHost, s->lc.stream));
+    if (rho) CU(cudaMemcpyAsync(rho, s->rho.p, 8 * nrho, cudaMemcpyDeviceToHost, s->lc.stream));
+    CU(cudaStreamSynchronize(s->lc.stream));
+    return UAPIC_OK;
+}
+
+int uapic_session_energy_history(uapic_session_t *s, double *out, int64_t capacity, int64_t *count) {
+    if (!s) return fail(UAPIC_EINVAL, "session is null");
+    TRY(session_bind(s));
+    if (count) *count = s->n_energy;
+    if (out) {
+        const int64_t n = s->n_energy < capacity ? s->n_energy : capacity;
+        if (n > 0) CU(cudaMemcpyAsync(out, s->energy.p, 8 * (size_t)n, cudaMemcpyDeviceToHost, s->lc.stream));
+        CU(cudaStreamSynchronize(s->lc.stream));
+    }
+    return UAPIC_OK;
+}
+
+int uapic_session_sum_v(uapic_session_t *s, double *sumv2) {
+    if (!s || !sumv2) return fail(UAPIC_EINVAL, "null pointer");
+    TRY(session_bind(s));
+    CU(launch_sum_v(s->lc, s->cfg.nbpart, s->v.as<double>(), s->sumv.as<double>()));
+    CU(cudaMemcpyAsync(sumv2, s->sumv.p, 16, cudaMemcpyDeviceToHost, s->lc.stream));
+    CU(cudaStreamSynchronize(s->lc.stream));
+    return UAPIC_OK;
+}
+
+int uapic_session_launch_count(uapic_session_t *s, int64_t *count) {
+    if (!s || !count) return fail(UAPIC_EINVAL, "null pointer");
+    *count = s->launches;
+    return UAPIC_OK;
+}
+
+int uapic_session_device_bytes(uapic_session_t *s, int64_t *bytes) {
+    if (!s || !bytes) return fail(UAPIC_EINVAL, "null pointer");
+    *bytes = s->bytes;
+    return UAPIC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,75 @@
+// uapic_internal.h -- launcher declarations shared by uapic_kernels.cu and uapic_capi.cu (device pointers only)
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "uapic_device.cuh"
+
+namespace uapic {
+
+struct LaunchCtx {
+    cudaStream_t stream;
+    int sm_count;
+    int64_t *launches;   // host counter, may be null
+};
+
+inline bool ntau_supported(int ntau) { return ntau == 2 || ntau == 4 || ntau == 8 || ntau == 16 || ntau == 32; }
+
+// ---- stage kernels (reference-shaped arrays, natural-order Fourier arrays) ----------------------------------
+cudaError_t launch_preparation(const LaunchCtx &c, int ntau, double eps, double dt, int64_t np, const double *x,
+                               const double *v, const double *e, double *b, double *t, double *pl, double *ql,
+                               double *xt, double *yt);
+cudaError_t launch_gather_tau(const LaunchCtx &c, const MeshDev &m, const double *emesh, int ntau, int64_t np,
+                              const double *xt, double *et, int wrap);
+cudaError_t launch_compute_f(const LaunchCtx &c, int ntau, double eps, int64_t np, const double *b, const double *xt,
+                             const double *yt, const double *et, double *fx, double *fy, int normalise);
+cudaError_t launch_fft_tau(const LaunchCtx &c, int ntau, int64_t nvec, const double *in, double *out, int sign,
+                           int normalise);
+cudaError_t launch_step_pointwise(const LaunchCtx &c, int ntau, double eps, int64_t np, const double *t,
+                                  const double *pl, const double *ql, const double *xf, const double *fx,
+                                  const double *gx, double *out);
+cudaError_t launch_step_fortran(const LaunchCtx &c, int ntau, double eps, int64_t np, const double *t,
+                                const double *pl, const double *ql, double *xt, double *xf, const double *fx,
+                                const double *gx, int corrector);
+cudaError_t launch_deposit_tau(const LaunchCtx &c, const MeshDev &m, int ntau, double eps, int64_t np,
+                               const double *xt, const double *t, double w, const RhoAcc &acc, double *x, int wrap);
+cudaError_t launch_compute_v(const LaunchCtx &c, int ntau, double eps, int64_t np, const double *t, const double *yt,
+                             int yt_is_fourier, double *v);
+cudaError_t launch_deposit(const LaunchCtx &c, const MeshDev &m, int64_t np, double *x, double w, const RhoAcc &acc,
+                           int wrap);
+cudaError_t launch_gather(const LaunchCtx &c, const MeshDev &m, const double *emesh, int64_t np, double *x, double *ep,
+                          int wrap);
+
+// ---- mesh kernels ---------------------------------------------------------------------------------------------
+// raw accumulation (fp64 or fixed point) -> neutralised rho with ghosts; rho_total (1 double) may be null
+cudaError_t launch_rho_epilogue(const LaunchCtx &c, const MeshDev &m, const RhoAcc &acc, double *rho, double *rho_total);
+struct PoissonWork { double2 *rk; double2 *ek; };   // rk: (nx/2+1)*ny ; ek: 2*(nx/2+1)*ny
+cudaError_t launch_poisson(const LaunchCtx &c, const MeshDev &m, const PoissonWork &w, const double *rho, double *emesh,
+                           double *energy);
+bool poisson_size_supported(int n);
+
+// ---- fused phase kernels (session path) -----------------------------------------------------------------------
+struct PhaseParams {
+    MeshDev m;
+    double eps, dt, weight;
+    int64_t np;
+    int wrap;
+    int ntau;
+    double2 *x;            // (2,np): read by A, written by B
+    double2 *v;            // (2,np): read by A, written by B
+    const double2 *ep;     // (2,np): particles.e, frozen after init
+    const double2 *emesh;  // (2,nx+1,ny+1)
+    double2 *store;        // np * 8 * ntau complex: what crosses the intra-step barrier
+    double2 *tb;           // (t,b) per particle
+    RhoAcc rho;
+};
+cudaError_t launch_phase_a(const LaunchCtx &c, const PhaseParams &p);
+cudaError_t launch_phase_b(const LaunchCtx &c, const PhaseParams &p);
+
+// ---- loaders / diagnostics --------------------------------------------------------------------------------------
+cudaError_t launch_generate(const LaunchCtx &c, const MeshDev &m, int kind, uint64_t seed, int64_t first, int64_t np,
+                            int64_t np_global, double alpha, double kx, double *x, double *v);
+cudaError_t launch_sum_v(const LaunchCtx &c, int64_t np, const double *v, double *out2);
+
+}  // namespace uapic

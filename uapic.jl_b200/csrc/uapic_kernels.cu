@@ -1,0 +1,883 @@
+// uapic_kernels.cu -- all CUDA kernels of libuapic_b200 (sm_100a).
+//
+//  1. stage kernels: one per reference routine, reference-shaped arrays (parity + the Julia stage API)
+//  2. mesh kernels : rho epilogue, Poisson (shared-memory FFTs), energy
+//  3. fused phase kernels: the session (performance) path
+//  4. loaders / diagnostics
+//
+// Reference citations are to /root/reference (fortran/*.F90, src/*.jl); see DESIGN.md for the mapping.
+#include "uapic_internal.h"
+
+namespace uapic {
+
+namespace {
+
+constexpr int kBlock = 256;
+
+inline int grid_for(const LaunchCtx &c, int64_t work_items, int items_per_block, int max_blocks_per_sm = 8) {
+    int64_t need = (work_items + items_per_block - 1) / items_per_block;
+    int64_t cap = (int64_t)c.sm_count * max_blocks_per_sm;
+    if (need < 1) need = 1;
+    return (int)(need < cap ? need : cap);
+}
+inline void count(const LaunchCtx &c, int n = 1) { if (c.launches) *c.launches += n; }
+
+#define UAPIC_DISPATCH_N(ntau, CALL)                      \
+    switch (ntau) {                                       \
+        case 2:  { constexpr int N = 2;  CALL; } break;   \
+        case 4:  { constexpr int N = 4;  CALL; } break;   \
+        case 8:  { constexpr int N = 8;  CALL; } break;   \
+        case 16: { constexpr int N = 16; CALL; } break;   \
+        case 32: { constexpr int N = 32; CALL; } break;   \
+        default: return cudaErrorInvalidValue;            \
+    }
+
+// warp/particle bookkeeping for "lane = tau sample" kernels
+template <int N> struct WarpMap {
+    static constexpr int G = 32 / N;   // particles per warp
+    int lane, g;
+    int64_t first, stride;             // first particle of this warp, particles per grid sweep
+    DEVINL WarpMap() {
+        lane = threadIdx.x & 31;
+        g = lane / N;
+        const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+        const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+        first = warp * G;
+        stride = nwarps * G;
+    }
+};
+
+DEVINL double2 ld2(const double *p, int64_t i) { return reinterpret_cast<const double2 *>(p)[i]; }
+DEVINL void st2(double *p, int64_t i, cd z) { reinterpret_cast<double2 *>(p)[i] = make_double2(z.re, z.im); }
+DEVINL cd ldc(const double *p, int64_t i) { const double2 d = ld2(p, i); return mk(d.x, d.y); }
+
+// =================================================================================================
+// 1. stage kernels
+// =================================================================================================
+
+// preparation                                         ua_steps.F90:15-115 / src/ua_steps.jl:3-78
+template <int N>
+__global__ void __launch_bounds__(kBlock) k_preparation(double eps, double dt, int64_t np, const double *x, const double *v,
+                                                        const double *e, double *b, double *t, double *pl, double *ql,
+                                                        double *xt, double *yt) {
+    TauLane<N> L; L.init(threadIdx.x & 31);
+    WarpMap<N> W;
+    for (int64_t base = W.first; base < np; base += W.stride) {
+        const int64_t kraw = base + W.g;
+        const bool valid = kraw < np;
+        const int64_t k = valid ? kraw : np - 1;
+        Pcl p;
+        const double2 xx = ld2(x, k), vv = ld2(v, k), ee = ld2(e, k);
+        p.x1 = xx.x; p.x2 = xx.y; p.vx = vv.x; p.vy = vv.y; p.ex = ee.x; p.ey = ee.y;
+        double xt1, xt2, interv; cd yt1, yt2;
+        prep_particle<N>(L, eps, dt, p, xt1, xt2, yt1, yt2, interv);
+        const cd elt = elt_minus<N>(L, p.t, eps);
+        cd plv, qlv;
+        pl_ql<N>(L, p.t, eps, elt, plv, qlv);
+        if (valid) {
+            if (L.j == 0) { b[k] = p.b; t[k] = p.t; }
+            st2(pl, L.k + (int64_t)N * k, plv);
+            st2(ql, L.k + (int64_t)N * k, qlv);
+            st2(xt, L.j + (int64_t)N * (0 + 2 * k), mk(xt1, 0.0));
+            st2(xt, L.j + (int64_t)N * (1 + 2 * k), mk(xt2, 0.0));
+            st2(yt, L.j + (int64_t)N * (0 + 2 * k), yt1);
+            st2(yt, L.j + (int64_t)N * (1 + 2 * k), yt2);
+        }
+    }
+}
+
+// interpolate_eb_m6_complex                           interpolation_m6.F90:40-191 / src/interpolation.jl:3-123
+__global__ void __launch_bounds__(kBlock) k_gather_tau(MeshDev m, const double2 *__restrict__ emesh, int ntau, int64_t np,
+                                                       const double *__restrict__ xt, double *__restrict__ et, int wrap) {
+    const int64_t total = (int64_t)ntau * np;
+    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < total; s += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t k = s / ntau;
+        const int n = (int)(s - k * ntau);
+        const int64_t i1 = n + (int64_t)ntau * (0 + 2 * k), i2 = n + (int64_t)ntau * (1 + 2 * k);
+        double xw, yw;
+        const Cell c = m6_cell_exact(m, xt[2 * i1], xt[2 * i2], wrap, xw, yw);   // real(x(n,1,k)), real(x(n,2,k))
+        double e1, e2;
+        m6_gather_exact(m, emesh, c, e1, e2);
+        et[i1] = e1; et[i2] = e2;
+    }
+}
+
+// compute_f                                           ua_steps.F90:140-198 / src/ua_steps.jl:105-145
+template <int N>
+__global__ void __launch_bounds__(kBlock) k_compute_f(double eps, int64_t np, const double *b, const double *xt, const double *yt,
+                                                      const double *et, double *fx, double *fy, int normalise) {
+    TauLane<N> L; L.init(threadIdx.x & 31);
+    WarpMap<N> W;
+    const double sc = normalise ? 1.0 / (double)N : 1.0;
+    for (int64_t base = W.first; base < np; base += W.stride) {
+        const int64_t kraw = base + W.g;
+        const bool valid = kraw < np;
+        const int64_t k = valid ? kraw : np - 1;
+        const int64_t i1 = L.j + (int64_t)N * (0 + 2 * k), i2 = L.j + (int64_t)N * (1 + 2 * k);
+        const double bb = b[k];
+        const double x1 = xt[2 * i1], x2 = xt[2 * i2];
+        const cd y1 = ldc(yt, i1), y2 = ldc(yt, i2);
+        const double interv = (1.0 + 0.5 * sin(x1) * sin(x2) - bb) / eps;                 // :177
+        cd f1, f2, g1, g2;
+        force_terms<N>(L, 1.0 / bb, interv, y1, y2, et[i1], et[i2], f1, f2, g1, g2);
+        f1 = rmul(sc, fft_fwd<N>(f1, L)); f2 = rmul(sc, fft_fwd<N>(f2, L));               // :187-195
+        g1 = rmul(sc, fft_fwd<N>(g1, L)); g2 = rmul(sc, fft_fwd<N>(g2, L));
+        if (valid) {
+            const int64_t o1 = L.k + (int64_t)N * (0 + 2 * k), o2 = L.k + (int64_t)N * (1 + 2 * k);
+            st2(fx, o1, f1); st2(fx, o2, f2); st2(fy, o1, g1); st2(fy, o2, g2);
+        }
+    }
+}
+
+// mul!(x̃t, ftau, xt) / ifft!(xt,1)                    test/bupdate.jl:79,85
+template <int N>
+__global__ void __launch_bounds__(kBlock) k_fft_tau(int64_t nvec, const double *in, double *out, int sign, int normalise) {
+    TauLane<N> L; L.init(threadIdx.x & 31);
+    WarpMap<N> W;
+    const double sc = normalise ? 1.0 / (double)N : 1.0;
+    for (int64_t base = W.first; base < nvec; base += W.stride) {
+        const int64_t kraw = base + W.g;
+        const bool valid = kraw < nvec;
+        const int64_t k = valid ? kraw : nvec - 1;
+        if (sign < 0) {
+            cd z = rmul(sc, fft_fwd<N>(ldc(in, L.j + (int64_t)N * k), L));
+            if (valid) st2(out, L.k + (int64_t)N * k, z);
+        } else {
+            cd z = rmul(sc, fft_bwd<N>(ldc(in, L.k + (int64_t)N * k), L));
+            if (valid) st2(out, L.j + (int64_t)N * k, z);
+        }
+    }
+}
+
+// ua_step! (Julia, pointwise in tau-Fourier space)     src/ua_steps.jl:149-200 ; gx == null -> predictor
+__global__ void __launch_bounds__(kBlock) k_step_pointwise(int ntau, double eps, int64_t np, const double *t, const double *pl,
+                                                           const double *ql, const double *xf, const double *fx,
+                                                           const double *gx, double *out) {
+    const int64_t total = (int64_t)ntau * np;
+    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < total; s += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t k = s / ntau;
+        const int n = (int)(s - k * ntau);
+        const double l = (n < ntau / 2) ? (double)n : (double)(n - ntau);
+        const double tt = t[k];
+        double sn, cs;
+        sincos(-(l * tt) / eps, &sn, &cs);                                               // :162, :185
+        const cd elt = mk(cs, sn);
+        const cd plv = ldc(pl, n + (int64_t)ntau * k);
+        for (int c = 0; c < 2; ++c) {
+            const int64_t i = n + (int64_t)ntau * (c + 2 * k);
+            const cd f = ldc(fx, i);
+            cd r = cfma(plv, f, cmul(elt, ldc(xf, i)));                                  // :163-164
+            if (gx) {
+                const cd qlv = ldc(ql, n + (int64_t)ntau * k);
+                const cd d = csub(ldc(gx, i), f);
+                const cd q = cmul(qlv, d);
+                r = mk(r.re + q.re / tt, r.im + q.im / tt);                              // :190-191
+            }
+            st2(out, i, r);
+        }
+    }
+}
+
+// ua_step1 / ua_step2 (Fortran forms)                  ua_steps.F90:200-272
+template <int N>
+__global__ void __launch_bounds__(kBlock) k_step_fortran(double eps, int64_t np, const double *t, const double *pl, const double *ql,
+                                                         double *xt, double *xf, const double *fx, const double *gx,
+                                                         int corrector) {
+    TauLane<N> L; L.init(threadIdx.x & 31);
+    WarpMap<N> W;
+    for (int64_t base = W.first; base < np; base += W.stride) {
+        const int64_t kraw = base + W.g;
+        const bool valid = kraw < np;
+        const int64_t k = valid ? kraw : np - 1;
+        const double tt = t[k];
+        const cd elt = rmul(1.0 / (double)N, elt_minus<N>(L, tt, eps));                  // :224-225, :258-259
+        const cd plv = ldc(pl, L.k + (int64_t)N * k);
+        cd out[2];
+        for (int c = 0; c < 2; ++c) {
+            const int64_t it = L.j + (int64_t)N * (c + 2 * k), is = L.k + (int64_t)N * (c + 2 * k);
+            cd xfv;
+            if (!corrector) {
+                xfv = fft_fwd<N>(ldc(xt, it), L);                                        // :217-218
+                if (valid) st2(xf, is, xfv);
+            } else {
+                xfv = ldc(xf, is);
+            }
+            const cd f = ldc(fx, is);
+            cd r = cfma(plv, f, cmul(elt, xfv));                                         // :226, :260
+            if (corrector) {
+                const cd q = cmul(ldc(ql, L.k + (int64_t)N * k), csub(ldc(gx, is), f));
+                r = mk(r.re + q.re / tt, r.im + q.im / tt);                              // :261
+            }
+            out[c] = fft_bwd<N>(r, L);                                                   // :231-232, :267-268
+        }
+        if (valid) {
+            st2(xt, L.j + (int64_t)N * (0 + 2 * k), out[0]);
+            st2(xt, L.j + (int64_t)N * (1 + 2 * k), out[1]);
+        }
+    }
+}
+
+// compute_rho_m6_complex (per-particle part)           compute_rho_m6.F90:70-187 / src/compute_rho.jl:43-165
+template <int N>
+__global__ void __launch_bounds__(kBlock) k_deposit_tau(MeshDev m, double eps, int64_t np, const double *xt, const double *t, double w,
+                                                        RhoAcc acc, double *x, int wrap) {
+    TauLane<N> L; L.init(threadIdx.x & 31);
+    WarpMap<N> W;
+    for (int64_t base = W.first; base < np; base += W.stride) {
+        const int64_t kraw = base + W.g;
+        const bool valid = kraw < np;
+        const int64_t k = valid ? kraw : np - 1;
+        const double tt = t[k];
+        const cd elt = elt_minus<N>(L, tt, eps);
+        const double sc = 1.0 / (double)N;
+        const cd f1 = rmul(sc, fft_fwd<N>(ldc(xt, L.j + (int64_t)N * (0 + 2 * k)), L));   // :74
+        const cd f2 = rmul(sc, fft_fwd<N>(ldc(xt, L.j + (int64_t)N * (1 + 2 * k)), L));   // :80
+        const double p1 = eval_tau_star<N>(f1, elt).re;                                  // :76-78
+        const double p2 = eval_tau_star<N>(f2, elt).re;                                  // :82-84
+        double xw, yw;
+        const Cell c = m6_cell_exact(m, p1, p2, wrap, xw, yw);
+        if (valid) {
+            if (L.j == 0) reinterpret_cast<double2 *>(x)[k] = make_double2(xw, yw);      // :86-87
+            m6_scatter(m, acc, c, w, L.j, N);
+        }
+    }
+}
+
+// compute_v                                            ua_steps.F90:274-307 / src/ua_steps.jl:204-224
+template <int N>
+__global__ void __launch_bounds__(kBlock) k_compute_v(double eps, int64_t np, const double *t, const double *yt, int yt_is_fourier,
+                                                      double *v) {
+    TauLane<N> L; L.init(threadIdx.x & 31);
+    WarpMap<N> W;
+    for (int64_t base = W.first; base < np; base += W.stride) {
+        const int64_t kraw = base + W.g;
+        const bool valid = kraw < np;
+        const int64_t k = valid ? kraw : np - 1;
+        const double tt = t[k];
+        const cd elt = elt_minus<N>(L, tt, eps);
+        cd y1, y2;
+        if (yt_is_fourier) {
+            y1 = ldc(yt, L.k + (int64_t)N * (0 + 2 * k));
+            y2 = ldc(yt, L.k + (int64_t)N * (1 + 2 * k));
+        } else {
+            y1 = fft_fwd<N>(ldc(yt, L.j + (int64_t)N * (0 + 2 * k)), L);                 // :290
+            y2 = fft_fwd<N>(ldc(yt, L.j + (int64_t)N * (1 + 2 * k)), L);                 // :291
+        }
+        const double sc = 1.0 / (double)N;
+        const double px = eval_tau_star<N>(rmul(sc, y1), elt).re;                        // :296-300
+        const double py = eval_tau_star<N>(rmul(sc, y2), elt).re;
+        double sn, cs;
+        sincos(tt / eps, &sn, &cs);
+        if (valid && L.j == 0)
+            reinterpret_cast<double2 *>(v)[k] = make_double2(cs * px + sn * py, cs * py - sn * px);   // :302-303
+    }
+}
+
+// compute_rho_m6_real (per-particle part)              compute_rho_m6.F90:221-327 / src/compute_rho.jl:195-300
+__global__ void __launch_bounds__(kBlock) k_deposit(MeshDev m, int64_t np, double *x, double w, RhoAcc acc, int wrap) {
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < np; k += (int64_t)gridDim.x * blockDim.x) {
+        const double2 xx = ld2(x, k);
+        double xw, yw;
+        const Cell c = m6_cell_exact(m, xx.x, xx.y, wrap, xw, yw);
+        if (wrap == kWrapJulia) reinterpret_cast<double2 *>(x)[k] = make_double2(xw, yw);
+        m6_scatter(m, acc, c, w, 0, 1);
+    }
+}
+
+// interpolate_eb_m6_real                               interpolation_m6.F90:193-327 / src/interpolation.jl:125-247
+__global__ void __launch_bounds__(kBlock) k_gather(MeshDev m, const double2 *__restrict__ emesh, int64_t np, double *x, double *ep,
+                                                   int wrap) {
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < np; k += (int64_t)gridDim.x * blockDim.x) {
+        const double2 xx = ld2(x, k);
+        double xw, yw;
+        const Cell c = m6_cell_exact(m, xx.x, xx.y, wrap, xw, yw);
+        if (wrap == kWrapJulia) reinterpret_cast<double2 *>(x)[k] = make_double2(xw, yw);
+        double e1, e2;
+        m6_gather_exact(m, emesh, c, e1, e2);
+        reinterpret_cast<double2 *>(ep)[k] = make_double2(e1, e2);
+    }
+}
+
+// =================================================================================================
+// 2. mesh kernels
+// =================================================================================================
+
+constexpr int kMeshBlock = 1024;
+
+// deterministic block sum (fixed tree), result valid on every thread
+DEVINL double block_sum(double v, double *sh) {
+    const int tid = threadIdx.x;
+    sh[tid] = v;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if (tid < s) sh[tid] += sh[tid + s];
+        __syncthreads();
+    }
+    const double r = sh[0];
+    __syncthreads();
+    return r;
+}
+
+// compute_rho_m6.F90:191-200 : ghost copy -> /(dx*dy) -> subtract the mean.  Single CTA: the mesh is <= 0.5 MB and
+// the sum must have a fixed order.
+__global__ void __launch_bounds__(kMeshBlock) k_rho_epilogue(MeshDev m, RhoAcc acc, double *rho, double *rho_total) {
+    __shared__ double sh[kMeshBlock];
+    const int nx = m.nx, ny = m.ny, ld = m.ld;
+    const double dxdy = m.dx * m.dy;
+    const double inv_scale = acc.i64 ? 1.0 / acc.scale : 1.0;
+    double part = 0.0;
+    long long ipart = 0;
+    for (int idx = threadIdx.x; idx < nx * ny; idx += blockDim.x) {
+        const int j = idx / nx, i = idx - j * nx;
+        const int q = i + ld * j;
+        double raw;
+        if (acc.i64) { const long long r = (long long)acc.i64[q]; ipart += r; raw = (double)r * inv_scale; }
+        else raw = acc.f64[q];
+        const double val = raw / dxdy;
+        rho[q] = val;
+        part += val;
+    }
+    double total;
+    if (acc.i64) {
+        // fixed point: sum(rho)*dx*dy == sum(raw) exactly, and the integer sum has no order -> bit-reproducible
+        long long *ish = reinterpret_cast<long long *>(sh);
+        ish[threadIdx.x] = ipart;
+        __syncthreads();
+        for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+            if (threadIdx.x < s) ish[threadIdx.x] += ish[threadIdx.x + s];
+            __syncthreads();
+        }
+        total = (double)ish[0] * inv_scale;
+        __syncthreads();
+    } else {
+        total = block_sum(part, sh) * m.dx * m.dy;
+    }
+    const double sub = total / m.dimx / m.dimy;
+    for (int idx = threadIdx.x; idx < nx * ny; idx += blockDim.x) {
+        const int j = idx / nx, i = idx - j * nx;
+        rho[i + ld * j] -= sub;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nx; i += blockDim.x) rho[i + ld * ny] = rho[i];
+    for (int j = threadIdx.x; j < ny; j += blockDim.x) rho[nx + ld * j] = rho[ld * j];
+    if (threadIdx.x == 0) {
+        rho[nx + ld * ny] = rho[0];
+        if (rho_total) *rho_total = total;
+    }
+}
+
+// ---- shared-memory FFT of one line (power of two: radix-2; otherwise direct DFT) -----------------------------
+DEVINL void line_twiddles(cd *tw, int n) {   // tw[k] = exp(-2 pi i k/n), k < n
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+        double s, c;
+        sincospi(-2.0 * (double)k / (double)n, &s, &c);
+        tw[k] = mk(c, s);
+    }
+}
+
+// in-place transform of a[0..n) ; tmp[0..n) scratch ; sign -1 forward / +1 backward ; ends with __syncthreads
+DEVINL void line_fft(cd *a, cd *tmp, const cd *tw, int n, int sign) {
+    const bool pow2 = (n & (n - 1)) == 0;
+    __syncthreads();
+    if (pow2) {
+        int logn = 0;
+        while ((1 << logn) < n) ++logn;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const int r = (int)(__brev((unsigned)i) >> (32 - logn));
+            if (logn > 0 && i < r) { const cd u = a[i]; a[i] = a[r]; a[r] = u; }
+        }
+        __syncthreads();
+        for (int len = 2; len <= n; len <<= 1) {
+            const int half = len >> 1, step = n / len;
+            for (int bfly = threadIdx.x; bfly < n / 2; bfly += blockDim.x) {
+                const int k = bfly & (half - 1);
+                const int s = (bfly / half) * len;
+                cd w = tw[k * step];
+                if (sign > 0) w.im = -w.im;
+                const cd u = a[s + k];
+                const cd v = cmul(w, a[s + k + half]);
+                a[s + k] = cadd(u, v);
+                a[s + k + half] = csub(u, v);
+            }
+            __syncthreads();
+        }
+    } else {
+        for (int k = threadIdx.x; k < n; k += blockDim.x) {
+            cd acc = mk(0.0, 0.0);
+            for (int j = 0; j < n; ++j) {
+                cd w = tw[(int)(((long long)k * j) % n)];
+                if (sign > 0) w.im = -w.im;
+                acc = cadd(acc, cmul(w, a[j]));
+            }
+            tmp[k] = acc;
+        }
+        __syncthreads();
+        for (int k = threadIdx.x; k < n; k += blockDim.x) a[k] = tmp[k];
+        __syncthreads();
+    }
+}
+
+// r2c along x for row j                                poisson_2d.f90:96 (first half)
+__global__ void k_poisson_rows_fwd(MeshDev m, const double *__restrict__ rho, double2 *__restrict__ rk) {
+    extern __shared__ double2 smem_raw[];
+    cd *a = reinterpret_cast<cd *>(smem_raw);
+    cd *tmp = a + m.nx;
+    cd *tw = tmp + m.nx;
+    const int j = blockIdx.x, nx = m.nx, nh = nx / 2 + 1;
+    line_twiddles(tw, nx);
+    for (int i = threadIdx.x; i < nx; i += blockDim.x) a[i] = mk(rho[i + m.ld * j], 0.0);
+    line_fft(a, tmp, tw, nx, -1);
+    for (int i = threadIdx.x; i < nh; i += blockDim.x) rk[i + (size_t)nh * j] = make_double2(a[i].re, a[i].im);
+}
+
+// along y for column ik: forward, multiply by -i*k/k^2, backward for both components     poisson_2d.f90:96-102
+__global__ void k_poisson_cols(MeshDev m, const double2 *__restrict__ rk, double2 *__restrict__ ek) {
+    extern __shared__ double2 smem_raw[];
+    const int ny = m.ny, nx = m.nx, nh = nx / 2 + 1;
+    cd *a = reinterpret_cast<cd *>(smem_raw);
+    cd *bx = a + ny;
+    cd *by = bx + ny;
+    cd *tmp = by + ny;
+    cd *tw = tmp + ny;
+    const int ik = blockIdx.x;
+    const double pi = 3.14159265358979323846;
+    const double kx0 = 2.0 * pi / m.dimx, ky0 = 2.0 * pi / m.dimy;                        // :48-49
+    line_twiddles(tw, ny);
+    for (int jk = threadIdx.x; jk < ny; jk += blockDim.x) {
+        const double2 r = rk[ik + (size_t)nh * jk];
+        a[jk] = mk(r.x, r.y);
+    }
+    line_fft(a, tmp, tw, ny, -1);
+    for (int jk = threadIdx.x; jk < ny; jk += blockDim.x) {
+        double kx = (double)ik * kx0;                                                    // :59
+        const double ky = (jk < ny / 2) ? (double)jk * ky0 : (double)(jk - ny) * ky0;    // :62, :66
+        if (ik == 0 && jk == 0) kx = 1.0;                                                // :70
+        const double k2 = kx * kx + ky * ky;                                             // :71
+        const double kkx = kx / k2, kky = ky / k2;                                       // :72-73
+        const cd r = a[jk];
+        bx[jk] = mk(kkx * r.im, -kkx * r.re);                                            // (0,-1)*kx*rho   :98
+        by[jk] = mk(kky * r.im, -kky * r.re);                                            // :99
+    }
+    line_fft(bx, tmp, tw, ny, +1);
+    line_fft(by, tmp, tw, ny, +1);
+    const size_t plane = (size_t)nh * ny;
+    for (int jk = threadIdx.x; jk < ny; jk += blockDim.x) {
+        ek[ik + (size_t)nh * jk] = make_double2(bx[jk].re, bx[jk].im);
+        ek[plane + ik + (size_t)nh * jk] = make_double2(by[jk].re, by[jk].im);
+    }
+}
+
+// c2r along x for row j, component blockIdx.y; FFTW c2r semantics: Im of the DC / Nyquist bins ignored.
+// Also writes the ghost column, the ghost row (from row 0) and the 1/(nx*ny) scale      poisson_2d.f90:101-109
+__global__ void k_poisson_rows_bwd(MeshDev m, const double2 *__restrict__ ek, double *__restrict__ emesh) {
+    extern __shared__ double2 smem_raw[];
+    cd *a = reinterpret_cast<cd *>(smem_raw);
+    cd *tmp = a + m.nx;
+    cd *tw = tmp + m.nx;
+    const int j = blockIdx.x, comp = blockIdx.y, nx = m.nx, ny = m.ny, nh = nx / 2 + 1;
+    const double2 *src = ek + (size_t)comp * nh * ny + (size_t)nh * j;
+    line_twiddles(tw, nx);
+    for (int i = threadIdx.x; i < nx; i += blockDim.x) {
+        cd z;
+        if (i < nh) {
+            z = mk(src[i].x, src[i].y);
+            if (i == 0 || (2 * i == nx)) z.im = 0.0;
+        } else {
+            z = mk(src[nx - i].x, -src[nx - i].y);
+        }
+        a[i] = z;
+    }
+    line_fft(a, tmp, tw, nx, +1);
+    const double sc = 1.0 / (double)(nx * ny);
+    for (int i = threadIdx.x; i <= nx; i += blockDim.x) {
+        const double val = a[i == nx ? 0 : i].re * sc;
+        emesh[comp + 2 * ((size_t)i + (size_t)m.ld * j)] = val;
+        if (j == 0) emesh[comp + 2 * ((size_t)i + (size_t)m.ld * ny)] = val;
+    }
+}
+
+// src/poisson.jl:80-81 : sum over the ghosted array of e1^2+e2^2, times dx*dy (fixed summation order)
+__global__ void __launch_bounds__(kMeshBlock) k_energy(MeshDev m, const double2 *__restrict__ emesh, double *energy) {
+    __shared__ double sh[kMeshBlock];
+    const int n = m.ld * (m.ny + 1);
+    double part = 0.0;
+    for (int q = threadIdx.x; q < n; q += blockDim.x) {
+        const double2 ev = emesh[q];
+        part += ev.x * ev.x + ev.y * ev.y;
+    }
+    const double tot = block_sum(part, sh);
+    if (threadIdx.x == 0) *energy = tot * m.dx * m.dy;
+}
+
+// =================================================================================================
+// 3. fused phase kernels (session path)
+// =================================================================================================
+//
+// HBM layout of the barrier-crossing store: per particle 8 complex arrays of N, tau fastest:
+//   [k][0..3][n] = predicted xt1, xt2, yt1, yt2 (time domain, natural order)
+//   [k][4..7][s] = fhat_x1, fhat_x2, fhat_y1, fhat_y2 (tau-Fourier, slot order = lane order, normalised by 1/N)
+// A warp writes/reads 8 x 16 x N contiguous bytes per particle: fully coalesced 16-byte accesses.
+
+constexpr int kPhaseBlock = 256;
+
+// Phase A = preparation + gather(E_old) + compute_f + ua_step1 (x and y) + predictor deposit
+//           ua_steps.F90:15-236, interpolation_m6.F90:40-191, compute_rho_m6.F90:47-189
+template <int N>
+__global__ void __launch_bounds__(kPhaseBlock) k_phase_a(PhaseParams P) {
+    TauLane<N> L; L.init(threadIdx.x & 31);
+    WarpMap<N> W;
+    const double invN = 1.0 / (double)N;
+    for (int64_t base = W.first; base < P.np; base += W.stride) {
+        const int64_t kraw = base + W.g;
+        const bool valid = kraw < P.np;
+        const int64_t k = valid ? kraw : P.np - 1;
+        Pcl p;
+        {
+            const double2 xx = P.x[k], vv = P.v[k], ee = P.ep[k];
+            p.x1 = xx.x; p.x2 = xx.y; p.vx = vv.x; p.vy = vv.y; p.ex = ee.x; p.ey = ee.y;
+        }
+        double xt1, xt2, interv; cd yt1, yt2;
+        prep_particle<N>(L, P.eps, P.dt, p, xt1, xt2, yt1, yt2, interv);
+
+        double et1, et2;
+        {
+            double xw, yw;
+            const Cell c = m6_cell_fast(P.m, xt1, xt2, P.wrap, xw, yw);
+            m6_gather_fast(P.m, P.emesh, c, et1, et2);
+        }
+        cd fx1, fx2, fy1, fy2;
+        force_terms<N>(L, 1.0 / p.b, interv, yt1, yt2, et1, et2, fx1, fx2, fy1, fy2);
+        fx1 = rmul(invN, fft_fwd<N>(fx1, L)); fx2 = rmul(invN, fft_fwd<N>(fx2, L));
+        fy1 = rmul(invN, fft_fwd<N>(fy1, L)); fy2 = rmul(invN, fft_fwd<N>(fy2, L));
+
+        const cd elt = elt_minus<N>(L, p.t, P.eps);
+        cd pl, ql;
+        pl_ql<N>(L, p.t, P.eps, elt, pl, ql);
+        const cd eN = rmul(invN, elt);
+
+        // ua_step1 in Fourier space: xhat = elt/N * FFT(xt) + pl * fhat        ua_steps.F90:217-227
+        cd xh1 = cfma(pl, fx1, cmul(eN, fft_fwd<N>(mk(xt1, 0.0), L)));
+        cd xh2 = cfma(pl, fx2, cmul(eN, fft_fwd<N>(mk(xt2, 0.0), L)));
+        cd yh1 = cfma(pl, fy1, cmul(eN, fft_fwd<N>(yt1, L)));
+        cd yh2 = cfma(pl, fy2, cmul(eN, fft_fwd<N>(yt2, L)));
+
+        // predictor deposit: position at tau* = t/eps straight from the Fourier coefficients
+        // (FFT(IFFT(xhat))/N == xhat)                                            compute_rho_m6.F90:74-87
+        const double pos1 = eval_tau_star<N>(xh1, elt).re;
+        const double pos2 = eval_tau_star<N>(xh2, elt).re;
+
+        xh1 = fft_bwd<N>(xh1, L); xh2 = fft_bwd<N>(xh2, L);                       // :231-232
+        yh1 = fft_bwd<N>(yh1, L); yh2 = fft_bwd<N>(yh2, L);
+
+        if (valid) {
+            double2 *s = P.store + (size_t)k * 8 * N + L.j;
+            s[0 * N] = make_double2(xh1.re, xh1.im);
+            s[1 * N] = make_double2(xh2.re, xh2.im);
+            s[2 * N] = make_double2(yh1.re, yh1.im);
+            s[3 * N] = make_double2(yh2.re, yh2.im);
+            s[4 * N] = make_double2(fx1.re, fx1.im);
+            s[5 * N] = make_double2(fx2.re, fx2.im);
+            s[6 * N] = make_double2(fy1.re, fy1.im);
+            s[7 * N] = make_double2(fy2.re, fy2.im);
+            if (L.j == 0) P.tb[k] = make_double2(p.t, p.b);
+            double xw, yw;
+            const Cell c = m6_cell_exact(P.m, pos1, pos2, P.wrap, xw, yw);
+            m6_scatter(P.m, P.rho, c, P.weight, L.j, N);
+        }
+    }
+}
+
+// Phase B = gather(E_new) + compute_f + ua_step2 (x and y) + corrector deposit + compute_v
+//           ua_steps.F90:117-307
+template <int N>
+__global__ void __launch_bounds__(kPhaseBlock) k_phase_b(PhaseParams P) {
+    TauLane<N> L; L.init(threadIdx.x & 31);
+    WarpMap<N> W;
+    const double invN = 1.0 / (double)N;
+    for (int64_t base = W.first; base < P.np; base += W.stride) {
+        const int64_t kraw = base + W.g;
+        const bool valid = kraw < P.np;
+        const int64_t k = valid ? kraw : P.np - 1;
+        const double2 *s = P.store + (size_t)k * 8 * N + L.j;
+        const double2 tb = P.tb[k];
+        const double t = tb.x, b = tb.y;
+        cd xt1 = mk(s[0 * N].x, s[0 * N].y), xt2 = mk(s[1 * N].x, s[1 * N].y);
+        cd yt1 = mk(s[2 * N].x, s[2 * N].y), yt2 = mk(s[3 * N].x, s[3 * N].y);
+        const cd fx1 = mk(s[4 * N].x, s[4 * N].y), fx2 = mk(s[5 * N].x, s[5 * N].y);
+        const cd fy1 = mk(s[6 * N].x, s[6 * N].y), fy2 = mk(s[7 * N].x, s[7 * N].y);
+
+        double et1, et2;
+        {
+            double xw, yw;
+            const Cell c = m6_cell_fast(P.m, xt1.re, xt2.re, P.wrap, xw, yw);
+            m6_gather_fast(P.m, P.emesh, c, et1, et2);
+        }
+        const double interv = (1.0 + 0.5 * sin(xt1.re) * sin(xt2.re) - b) / P.eps;       // ua_steps.F90:177
+        cd gx1, gx2, gy1, gy2;
+        force_terms<N>(L, 1.0 / b, interv, yt1, yt2, et1, et2, gx1, gx2, gy1, gy2);
+        gx1 = rmul(invN, fft_fwd<N>(gx1, L)); gx2 = rmul(invN, fft_fwd<N>(gx2, L));
+        gy1 = rmul(invN, fft_fwd<N>(gy1, L)); gy2 = rmul(invN, fft_fwd<N>(gy2, L));
+
+        // elt/N*xf + pl*fhat == FFT(predicted xt)/N : the predictor's Fourier image need not be stored
+        xt1 = rmul(invN, fft_fwd<N>(xt1, L)); xt2 = rmul(invN, fft_fwd<N>(xt2, L));
+        yt1 = rmul(invN, fft_fwd<N>(yt1, L)); yt2 = rmul(invN, fft_fwd<N>(yt2, L));
+
+        const cd elt = elt_minus<N>(L, t, P.eps);
+        cd pl, ql;
+        pl_ql<N>(L, t, P.eps, elt, pl, ql);
+        const cd qt = rmul(1.0 / t, ql);
+        // ua_step2: + ql*(ghat - fhat)/t                                            ua_steps.F90:260-263
+        xt1 = cfma(qt, csub(gx1, fx1), xt1); xt2 = cfma(qt, csub(gx2, fx2), xt2);
+        yt1 = cfma(qt, csub(gy1, fy1), yt1); yt2 = cfma(qt, csub(gy2, fy2), yt2);
+
+        const double pos1 = eval_tau_star<N>(xt1, elt).re;                               // compute_rho_m6.F90:74-87
+        const double pos2 = eval_tau_star<N>(xt2, elt).re;
+        const double px = eval_tau_star<N>(yt1, elt).re;                                 // ua_steps.F90:293-300
+        const double py = eval_tau_star<N>(yt2, elt).re;
+        double sn, cs;
+        sincos(t / P.eps, &sn, &cs);
+
+        if (valid) {
+            double xw, yw;
+            const Cell c = m6_cell_exact(P.m, pos1, pos2, P.wrap, xw, yw);
+            if (L.j == 0) {
+                P.x[k] = make_double2(xw, yw);
+                P.v[k] = make_double2(cs * px + sn * py, cs * py - sn * px);             // ua_steps.F90:302-303
+            }
+            m6_scatter(P.m, P.rho, c, P.weight, L.j, N);
+        }
+    }
+}
+
+// =================================================================================================
+// 4. loaders / diagnostics
+// =================================================================================================
+
+DEVINL uint64_t splitmix64(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+// counter-based uniform in [0,1): keyed by (seed, particle, stream, draw)
+DEVINL double uniform01(uint64_t seed, uint64_t particle, uint32_t stream, uint32_t draw) {
+    uint64_t h = splitmix64(seed ^ splitmix64(particle * 0xD1342543DE82EF95ull + stream));
+    h = splitmix64(h + draw);
+    return (double)(h >> 11) * (1.0 / 9007199254740992.0);
+}
+
+// kind 0: rejection sampling of particles.F90:68-103 / src/plasma.jl:17-48 ; kind 1: Landau (src/landau.jl:19-43 intent)
+__global__ void __launch_bounds__(kBlock) k_generate(MeshDev m, int kind, uint64_t seed, int64_t first, int64_t np, int64_t np_global,
+                                                     double alpha, double kx, double *x, double *v) {
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < np; k += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t id = (uint64_t)(first + k);
+        double x1, x2, v1, v2;
+        if (kind == 0) {
+            uint32_t d = 0;
+            for (;;) {
+                const double xi = uniform01(seed, id, 0, d) * m.dimx;
+                const double yi = uniform01(seed, id, 0, d + 1) * m.dimy;
+                const double zi = (2.0 + alpha) * uniform01(seed, id, 0, d + 2);
+                d += 3;
+                if (1.0 + sin(yi) + alpha * cos(kx * xi) >= zi) { x1 = xi; x2 = yi; break; }
+            }
+            d = 0;
+            for (;;) {
+                const double xi = (uniform01(seed, id, 1, d) - 0.5) * 10.0;
+                const double yi = (uniform01(seed, id, 1, d + 1) - 0.5) * 10.0;
+                const double zi = uniform01(seed, id, 1, d + 2);
+                d += 3;
+                const double temm = (exp(-((xi - 2.0) * (xi - 2.0) + yi * yi) / 2.0) + exp(-((xi + 2.0) * (xi + 2.0) + yi * yi) / 2.0)) / 2.0;
+                if (temm >= zi) { v1 = xi; v2 = yi; break; }
+            }
+            x1 += m.xmin; x2 += m.ymin;
+        } else {
+            const double r1 = uniform01(seed, id, 2, 0), r2 = uniform01(seed, id, 2, 1), r3 = uniform01(seed, id, 2, 2);
+            // Newton on  x + alpha*sin(kx*x)/kx = r2 * 2*pi/kx          src/landau.jl:19-28
+            const double target = r2 * (2.0 * 3.14159265358979323846 / kx);
+            double x0 = target;
+            for (int it = 0; it < 50; ++it) {
+                const double pfun = x0 + alpha * sin(kx * x0) / kx;
+                const double f = 1.0 + alpha * cos(kx * x0);
+                const double xn = x0 - (pfun - target) / f;
+                const bool done = fabs(xn - x0) <= 1e-12;
+                x0 = xn;
+                if (done) break;
+            }
+            x1 = m.xmin + x0;
+            x2 = m.ymin + r3 * m.dimy;
+            const double vv = sqrt(-2.0 * log(((double)id + 0.5) / (double)np_global));  // landau.jl:35
+            double sn, cs;
+            sincospi(2.0 * r1, &sn, &cs);
+            v1 = vv * cs; v2 = vv * sn;
+        }
+        reinterpret_cast<double2 *>(x)[k] = make_double2(x1, x2);
+        reinterpret_cast<double2 *>(v)[k] = make_double2(v1, v2);
+    }
+}
+
+// sum(v[1,:]), sum(v[2,:])  (bupdate.F90:125) -- fixed-order single-CTA reduction
+__global__ void __launch_bounds__(kMeshBlock) k_sum_v(int64_t np, const double2 *__restrict__ v, double *out2) {
+    __shared__ double sh[kMeshBlock];
+    double a = 0.0, b = 0.0;
+    for (int64_t k = threadIdx.x; k < np; k += blockDim.x) { const double2 vv = v[k]; a += vv.x; b += vv.y; }
+    const double sa = block_sum(a, sh);
+    const double sb = block_sum(b, sh);
+    if (threadIdx.x == 0) { out2[0] = sa; out2[1] = sb; }
+}
+
+}  // namespace
+
+// =================================================================================================
+// launchers
+// =================================================================================================
+
+cudaError_t launch_preparation(const LaunchCtx &c, int ntau, double eps, double dt, int64_t np, const double *x,
+                               const double *v, const double *e, double *b, double *t, double *pl, double *ql,
+                               double *xt, double *yt) {
+    if (np <= 0) return cudaSuccess;
+    UAPIC_DISPATCH_N(ntau, (k_preparation<N><<<grid_for(c, np, (kBlock / 32) * (32 / N)), kBlock, 0, c.stream>>>(
+                               eps, dt, np, x, v, e, b, t, pl, ql, xt, yt)));
+    count(c);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_gather_tau(const LaunchCtx &c, const MeshDev &m, const double *emesh, int ntau, int64_t np,
+                              const double *xt, double *et, int wrap) {
+    if (np <= 0) return cudaSuccess;
+    k_gather_tau<<<grid_for(c, np * ntau, kBlock), kBlock, 0, c.stream>>>(m, reinterpret_cast<const double2 *>(emesh), ntau, np, xt,
+                                                                          et, wrap);
+    count(c);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_compute_f(const LaunchCtx &c, int ntau, double eps, int64_t np, const double *b, const double *xt,
+                             const double *yt, const double *et, double *fx, double *fy, int normalise) {
+    if (np <= 0) return cudaSuccess;
+    UAPIC_DISPATCH_N(ntau, (k_compute_f<N><<<grid_for(c, np, (kBlock / 32) * (32 / N)), kBlock, 0, c.stream>>>(
+                               eps, np, b, xt, yt, et, fx, fy, normalise)));
+    count(c);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fft_tau(const LaunchCtx &c, int ntau, int64_t nvec, const double *in, double *out, int sign,
+                           int normalise) {
+    if (nvec <= 0) return cudaSuccess;
+    UAPIC_DISPATCH_N(ntau, (k_fft_tau<N><<<grid_for(c, nvec, (kBlock / 32) * (32 / N)), kBlock, 0, c.stream>>>(nvec, in, out, sign,
+                                                                                                           normalise)));
+    count(c);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_step_pointwise(const LaunchCtx &c, int ntau, double eps, int64_t np, const double *t,
+                                  const double *pl, const double *ql, const double *xf, const double *fx,
+                                  const double *gx, double *out) {
+    if (np <= 0) return cudaSuccess;
+    k_step_pointwise<<<grid_for(c, np * ntau, kBlock), kBlock, 0, c.stream>>>(ntau, eps, np, t, pl, ql, xf, fx, gx, out);
+    count(c);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_step_fortran(const LaunchCtx &c, int ntau, double eps, int64_t np, const double *t,
+                                const double *pl, const double *ql, double *xt, double *xf, const double *fx,
+                                const double *gx, int corrector) {
+    if (np <= 0) return cudaSuccess;
+    UAPIC_DISPATCH_N(ntau, (k_step_fortran<N><<<grid_for(c, np, (kBlock / 32) * (32 / N)), kBlock, 0, c.stream>>>(
+                               eps, np, t, pl, ql, xt, xf, fx, gx, corrector)));
+    count(c);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_deposit_tau(const LaunchCtx &c, const MeshDev &m, int ntau, double eps, int64_t np,
+                               const double *xt, const double *t, double w, const RhoAcc &acc, double *x, int wrap) {
+    if (np <= 0) return cudaSuccess;
+    UAPIC_DISPATCH_N(ntau, (k_deposit_tau<N><<<grid_for(c, np, (kBlock / 32) * (32 / N)), kBlock, 0, c.stream>>>(m, eps, np, xt, t, w,
+                                                                                                           acc, x, wrap)));
+    count(c);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_compute_v(const LaunchCtx &c, int ntau, double eps, int64_t np, const double *t, const double *yt,
+                             int yt_is_fourier, double *v) {
+    if (np <= 0) return cudaSuccess;
+    UAPIC_DISPATCH_N(ntau, (k_compute_v<N><<<grid_for(c, np, (kBlock / 32) * (32 / N)), kBlock, 0, c.stream>>>(eps, np, t, yt,
+                                                                                                         yt_is_fourier, v)));
+    count(c);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_deposit(const LaunchCtx &c, const MeshDev &m, int64_t np, double *x, double w, const RhoAcc &acc,
+                           int wrap) {
+    if (np <= 0) return cudaSuccess;
+    k_deposit<<<grid_for(c, np, kBlock), kBlock, 0, c.stream>>>(m, np, x, w, acc, wrap);
+    count(c);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_gather(const LaunchCtx &c, const MeshDev &m, const double *emesh, int64_t np, double *x, double *ep,
+                          int wrap) {
+    if (np <= 0) return cudaSuccess;
+    k_gather<<<grid_for(c, np, kBlock), kBlock, 0, c.stream>>>(m, reinterpret_cast<const double2 *>(emesh), np, x, ep, wrap);
+    count(c);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_rho_epilogue(const LaunchCtx &c, const MeshDev &m, const RhoAcc &acc, double *rho, double *rho_total) {
+    k_rho_epilogue<<<1, kMeshBlock, 0, c.stream>>>(m, acc, rho, rho_total);
+    count(c);
+    return cudaGetLastError();
+}
+
+bool poisson_size_supported(int n) {
+    if (n < 2) return false;
+    const bool pow2 = (n & (n - 1)) == 0;
+    return pow2 ? n <= 1024 : n <= 512;
+}
+
+cudaError_t launch_poisson(const LaunchCtx &c, const MeshDev &m, const PoissonWork &w, const double *rho, double *emesh,
+                           double *energy) {
+    if (!poisson_size_supported(m.nx) || !poisson_size_supported(m.ny)) return cudaErrorInvalidValue;
+    const int tx = m.nx >= 512 ? 256 : (m.nx >= 128 ? 128 : 64);
+    const int ty = m.ny >= 512 ? 256 : (m.ny >= 128 ? 128 : 64);
+    const size_t shx = sizeof(double2) * (size_t)m.nx * 3;
+    const size_t shy = sizeof(double2) * (size_t)m.ny * 5;
+    k_poisson_rows_fwd<<<m.ny, tx, shx, c.stream>>>(m, rho, w.rk);
+    k_poisson_cols<<<m.nx / 2 + 1, ty, shy, c.stream>>>(m, w.rk, w.ek);
+    k_poisson_rows_bwd<<<dim3(m.ny, 2), tx, shx, c.stream>>>(m, w.ek, emesh);
+    count(c, 3);
+    if (energy) {
+        k_energy<<<1, kMeshBlock, 0, c.stream>>>(m, reinterpret_cast<const double2 *>(emesh), energy);
+        count(c);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_phase_a(const LaunchCtx &c, const PhaseParams &p) {
+    if (p.np <= 0) return cudaSuccess;
+    UAPIC_DISPATCH_N(p.ntau, (k_phase_a<N><<<grid_for(c, p.np, (kPhaseBlock / 32) * (32 / N), 4), kPhaseBlock, 0, c.stream>>>(p)));
+    count(c);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_phase_b(const LaunchCtx &c, const PhaseParams &p) {
+    if (p.np <= 0) return cudaSuccess;
+    UAPIC_DISPATCH_N(p.ntau, (k_phase_b<N><<<grid_for(c, p.np, (kPhaseBlock / 32) * (32 / N), 4), kPhaseBlock, 0, c.stream>>>(p)));
+    count(c);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_generate(const LaunchCtx &c, const MeshDev &m, int kind, uint64_t seed, int64_t first, int64_t np,
+                            int64_t np_global, double alpha, double kx, double *x, double *v) {
+    if (np <= 0) return cudaSuccess;
+    k_generate<<<grid_for(c, np, kBlock), kBlock, 0, c.stream>>>(m, kind, seed, first, np, np_global, alpha, kx, x, v);
+    count(c);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sum_v(const LaunchCtx &c, int64_t np, const double *v, double *out2) {
+    k_sum_v<<<1, kMeshBlock, 0, c.stream>>>(np, reinterpret_cast<const double2 *>(v), out2);
+    count(c);
+    return cudaGetLastError();
+}
+
+}  // namespace uapic

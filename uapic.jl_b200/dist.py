@@ -1,0 +1,54 @@
+"""Multi-GPU plumbing: particles are sharded by contiguous index ranges, one process per GPU; the per-deposit
+exchange is one all-reduce (sum) of the raw rho mesh over NCCL/NVLink (`gloo` on CPU for the host-logic tests).
+Everything after the sum (ghost fold, neutralisation, Poisson, energy) runs redundantly and identically on
+every rank, so no broadcast is needed.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_range(nbpart_global: int, rank: int, world_size: int) -> tuple[int, int]:
+    """contiguous slice [lo, hi) of the global particle index space owned by `rank`"""
+    lo = nbpart_global * rank // world_size
+    hi = nbpart_global * (rank + 1) // world_size
+    return lo, hi
+
+
+class _CudaView:
+    """expose a raw device pointer through __cuda_array_interface__ so torch can alias it without a copy"""
+
+    def __init__(self, ptr: int, count: int, typestr: str):
+        self.__cuda_array_interface__ = {"shape": (count,), "typestr": typestr, "data": (ptr, False), "version": 3,
+                                         "strides": None}
+
+
+def attach_torch_allreduce(session, group=None):
+    """make `session` sum its raw rho mesh over the ranks of `group` with torch.distributed (NCCL).
+    The session must run on torch's current CUDA stream so the collective is ordered with the kernels."""
+    import torch
+    import torch.distributed as dist
+
+    cache = {}
+
+    def fn(ptr, count, dtype, stream):
+        key = (ptr, count, dtype)
+        t = cache.get(key)
+        if t is None:
+            t = torch.as_tensor(_CudaView(ptr, count, "<f8" if dtype == 0 else "<i8"), device=torch.device("cuda", torch.cuda.current_device()))
+            cache[key] = t
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        return 0
+
+    session.set_allreduce(fn)
+    return fn
+
+
+def allreduce_host(array: np.ndarray, group=None) -> np.ndarray:
+    """sum a host mesh over ranks (gloo): used by the CPU tests of the sharding logic"""
+    import torch
+    import torch.distributed as dist
+
+    t = torch.from_numpy(np.ascontiguousarray(array))
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t.numpy().reshape(array.shape)

@@ -1,0 +1,180 @@
+"""Particle loads and the `particles.dat` text format (host side; the loop never touches these).
+
+    read_particles / write_particles     src/read_particles.jl:3-35  (one line per particle: ix iy dpx dpy vx vy)
+    plasma                               src/plasma.jl:3-52, fortran/particles.F90:21-105 (rejection sampling)
+    landau_sampling                      the intent of src/landau.jl:5-47 (that file references undefined names)
+
+`test/particles.dat` is missing from the reference checkout (.MISSING_LARGE_BLOBS), so `make_particles_dat`
+regenerates a 204 800-line file with the Fortran program's densities; when the bundled libgfortran is
+loadable its RNG is driven with the reference's 33-word seed (particles.F90:54-66) so the draw sequence is
+the one `init_particles_2d` would make, otherwise a seeded numpy stream is used.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import glob
+import os
+
+import numpy as np
+
+from .api import Mesh, Particles
+
+# fortran/particles.F90:57-64
+FORTRAN_SEED = [-1584649339, -1457681104, 1579121008, -819547200, 249798090, -517237887, 177452147, -981503238,
+                1418301473, 1989625004, 2065424384, -296364178, 1658790794, -435188152, -1643185032, 1461389312,
+                1869073641, 1321930686, 483734018, 1269936416, -1999561453, 906251506, 782514880, 428753705,
+                -2031262823, 263953581, 1026600222, -1118515860, 1633712916, -464192498, -1860714528, 1436611533, 0]
+
+
+def read_particles(filename: str, mesh: Mesh) -> Particles:
+    """src/read_particles.jl:3-35"""
+    data = np.loadtxt(filename, dtype=np.float64, ndmin=2)
+    nbpart = data.shape[0]
+    dimx, dimy = mesh.xmax - mesh.xmin, mesh.ymax - mesh.ymin
+    p = Particles(nbpart, (dimx * dimy) / nbpart)
+    ix, iy, dpx, dpy = data[:, 0], data[:, 1], data[:, 2], data[:, 3]
+    p.v[0], p.v[1] = data[:, 4], data[:, 5]
+    p.x[0] = (dpx + ix) * mesh.dx
+    p.x[1] = (dpy + iy) * mesh.dy
+    return p
+
+
+def write_particles(filename: str, mesh: Mesh, x: np.ndarray, v: np.ndarray) -> None:
+    """inverse of read_particles: `ix iy dpx dpy vx vy` with 17 significant digits"""
+    px, py = (x[0] - 0.0) / mesh.dx, (x[1] - 0.0) / mesh.dy
+    ix, iy = np.floor(px).astype(np.int64), np.floor(py).astype(np.int64)
+    with open(filename, "w") as f:
+        for k in range(x.shape[1]):
+            f.write(f"{ix[k]:d} {iy[k]:d} {px[k] - ix[k]:.17g} {py[k] - iy[k]:.17g} {v[0, k]:.17g} {v[1, k]:.17g}\n")
+
+
+class _Uniforms:
+    """stream of U[0,1) deviates: gfortran's random_number with the reference seed, or a numpy generator"""
+
+    def __init__(self, seed=None, use_gfortran=False):
+        self.gf = None
+        if use_gfortran:
+            import scipy
+            cands = glob.glob(os.path.join(os.path.dirname(scipy.__file__), "..", "scipy.libs", "libgfortran*.so*"))
+            for c in sorted(cands):
+                try:
+                    lib = C.CDLL(c)
+                    arr = (C.c_int32 * 33)(*FORTRAN_SEED)
+                    # _gfortran_random_seed_i4(size, put, get) with gfortran array descriptors is awkward from C;
+                    # the descriptor for a rank-1 int32 array (GCC >= 8 layout):
+                    class Desc(C.Structure):
+                        _fields_ = [("base", C.c_void_p), ("offset", C.c_size_t), ("elem_len", C.c_size_t), ("version", C.c_int),
+                                    ("rank", C.c_int8), ("type", C.c_int8), ("attr", C.c_int16), ("span", C.c_ssize_t),
+                                    ("stride", C.c_ssize_t), ("lbound", C.c_ssize_t), ("ubound", C.c_ssize_t)]
+                    d = Desc(C.addressof(arr), C.c_size_t(-1 & (2 ** 64 - 1)), 4, 0, 1, 1, 0, 4, 1, 1, 33)
+                    lib._gfortran_random_seed_i4(None, C.byref(d), None)
+                    lib._gfortran_random_r8.argtypes = [C.POINTER(C.c_double)]
+                    self.gf = lib
+                    self._keep = (arr, d)
+                    break
+                except (OSError, AttributeError):
+                    continue
+        self.rng = np.random.default_rng(20190101 if seed is None else seed)
+
+    @property
+    def source(self):
+        return "libgfortran random_number, seed of particles.F90:57-64" if self.gf else "numpy PCG64"
+
+    def draw(self, n):
+        if self.gf is None:
+            return self.rng.random(n)
+        out = np.empty(n)
+        tmp = C.c_double()
+        f = self.gf._gfortran_random_r8
+        for i in range(n):
+            f(C.byref(tmp))
+            out[i] = tmp.value
+        return out
+
+
+def plasma(mesh: Mesh, nbpart: int, seed=None, alpha=0.05, kx=0.5, use_gfortran=False, return_source=False):
+    """src/plasma.jl:3-52 / fortran/particles.F90:68-103: x from 1+sin(y)+alpha*cos(kx*x) (bound 2+alpha),
+    v from the two-bump Maxwellian on [-5,5]^2.  Draw order identical to the reference (xi, yi, zi per trial)."""
+    dimx, dimy = mesh.xmax - mesh.xmin, mesh.ymax - mesh.ymin
+    p = Particles(nbpart, (dimx * dimy) / nbpart)
+    u = _Uniforms(seed, use_gfortran)
+
+    def fill(accept_fn, target):
+        k = 0
+        while k < nbpart:
+            n = max(1024, int((nbpart - k) * 1.2 / accept_fn.rate))
+            d = u.draw(3 * n).reshape(n, 3)
+            a, b, ok = accept_fn(d)
+            take = min(int(ok.sum()), nbpart - k)
+            idx = np.flatnonzero(ok)[:take]
+            target[0, k:k + take], target[1, k:k + take] = a[idx], b[idx]
+            k += take
+            # the reference consumes deviates strictly in order; discarding the tail of the last batch only matters
+            # for bit-reproduction of the gfortran stream, which draws one trial at a time below
+        return
+
+    if u.gf is not None:
+        # strict one-trial-at-a-time order, as init_particles_2d
+        k = 0
+        while k < nbpart:
+            d = u.draw(3)
+            xi, yi, zi = d[0] * dimx, d[1] * dimy, (2.0 + alpha) * d[2]
+            if 1.0 + np.sin(yi) + alpha * np.cos(kx * xi) >= zi:
+                p.x[0, k], p.x[1, k] = xi, yi
+                k += 1
+        k = 0
+        while k < nbpart:
+            d = u.draw(3)
+            xi, yi, zi = (d[0] - 0.5) * 10.0, (d[1] - 0.5) * 10.0, d[2]
+            temm = (np.exp(-((xi - 2.0) ** 2 + yi ** 2) / 2.0) + np.exp(-((xi + 2.0) ** 2 + yi ** 2) / 2.0)) / 2.0
+            if temm >= zi:
+                p.v[0, k], p.v[1, k] = xi, yi
+                k += 1
+    else:
+        def acc_x(d):
+            xi, yi, zi = d[:, 0] * dimx, d[:, 1] * dimy, (2.0 + alpha) * d[:, 2]
+            return xi, yi, (1.0 + np.sin(yi) + alpha * np.cos(kx * xi)) >= zi
+        acc_x.rate = 1.0 / (2.0 + alpha)
+
+        def acc_v(d):
+            xi, yi, zi = (d[:, 0] - 0.5) * 10.0, (d[:, 1] - 0.5) * 10.0, d[:, 2]
+            temm = (np.exp(-((xi - 2.0) ** 2 + yi ** 2) / 2.0) + np.exp(-((xi + 2.0) ** 2 + yi ** 2) / 2.0)) / 2.0
+            return xi, yi, temm >= zi
+        acc_v.rate = 2 * np.pi / 100.0
+        fill(acc_x, p.x)
+        fill(acc_v, p.v)
+    if return_source:
+        return p, u.source
+    return p
+
+
+def landau_sampling(mesh: Mesh, nbpart: int, seed=20190102, alpha=0.05, kx=0.5):
+    """the load src/landau.jl:19-43 describes: x1 by inverse CDF of 1+alpha*cos(kx*x) (Newton, tol 1e-12), x2 uniform,
+    |v| = sqrt(-2 ln((i-0.5)/nbpart)), theta uniform.  A seeded pseudo-random stream stands in for the Sobol sequence."""
+    dimx, dimy = mesh.xmax - mesh.xmin, mesh.ymax - mesh.ymin
+    p = Particles(nbpart, (dimx * dimy) / nbpart)
+    rng = np.random.default_rng(seed)
+    r = rng.random((nbpart, 3))
+    target = r[:, 1] * 2 * np.pi / kx
+    x0 = target.copy()
+    for _ in range(50):
+        pf = x0 + alpha * np.sin(kx * x0) / kx
+        f = 1 + alpha * np.cos(kx * x0)
+        xn = x0 - (pf - target) / f
+        done = np.max(np.abs(xn - x0)) <= 1e-12
+        x0 = xn
+        if done:
+            break
+    vv = np.sqrt(-2 * np.log((np.arange(1, nbpart + 1) - 0.5) / nbpart))
+    th = r[:, 0] * 2 * np.pi
+    p.x[0], p.x[1] = mesh.xmin + x0, mesh.ymin + r[:, 2] * dimy
+    p.v[0], p.v[1] = vv * np.cos(th), vv * np.sin(th)
+    return p
+
+
+def make_particles_dat(filename: str, nbpart=204800, use_gfortran=True):
+    """regenerate the missing test/particles.dat fixture (mesh of test/test_particles.jl:7: 128 x 64 on [0,4pi]x[0,2pi])"""
+    mesh = Mesh(0, 4 * np.pi, 128, 0, 2 * np.pi, 64)
+    p, src = plasma(mesh, nbpart, use_gfortran=use_gfortran, return_source=True)
+    write_particles(filename, mesh, p.x, p.v)
+    return src
