@@ -385,4 +385,24 @@ template <int N> DEVINL cd eval_tau_star(cd xhat, cd elt /* exp(-i l t/eps) */) 
     return mk(group_sum<N>(z.re), group_sum<N>(z.im));
 }
 
+// warp/particle bookkeeping for "lane = tau sample" kernels
+template <int N> struct WarpMap {
+    static constexpr int G = 32 / N;   // particles per warp
+    int lane, g;
+    int64_t first, stride;             // first particle of this warp, particles per grid sweep
+    DEVINL WarpMap() {
+        lane = threadIdx.x & 31;
+        g = lane / N;
+        const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+        const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+        first = warp * G;
+        stride = nwarps * G;
+    }
+};
+
+DEVINL double2 ld2(const double *p, int64_t i) { return reinterpret_cast<const double2 *>(p)[i]; }
+DEVINL void st2(double *p, int64_t i, cd z) { reinterpret_cast<double2 *>(p)[i] = make_double2(z.re, z.im); }
+DEVINL cd ldc(const double *p, int64_t i) { const double2 d = ld2(p, i); return mk(d.x, d.y); }
+
+
 }  // namespace uapic

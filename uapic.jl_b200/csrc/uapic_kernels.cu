@@ -32,25 +32,6 @@ inline void count(const LaunchCtx &c, int n = 1) { if (c.launches) *c.launches +
         default: return cudaErrorInvalidValue;            \
     }
 
-// warp/particle bookkeeping for "lane = tau sample" kernels
-template <int N> struct WarpMap {
-    static constexpr int G = 32 / N;   // particles per warp
-    int lane, g;
-    int64_t first, stride;             // first particle of this warp, particles per grid sweep
-    DEVINL WarpMap() {
-        lane = threadIdx.x & 31;
-        g = lane / N;
-        const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-        const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-        first = warp * G;
-        stride = nwarps * G;
-    }
-};
-
-DEVINL double2 ld2(const double *p, int64_t i) { return reinterpret_cast<const double2 *>(p)[i]; }
-DEVINL void st2(double *p, int64_t i, cd z) { reinterpret_cast<double2 *>(p)[i] = make_double2(z.re, z.im); }
-DEVINL cd ldc(const double *p, int64_t i) { const double2 d = ld2(p, i); return mk(d.x, d.y); }
-
 // =================================================================================================
 // 1. stage kernels
 // =================================================================================================
@@ -510,146 +491,6 @@ __global__ void __launch_bounds__(kMeshBlock) k_energy(MeshDev m, const double2 
 }
 
 // =================================================================================================
-// 3. fused phase kernels (session path)
-// =================================================================================================
-//
-// HBM layout of the barrier-crossing store: per particle 8 complex arrays of N, tau fastest:
-//   [k][0..3][n] = predicted xt1, xt2, yt1, yt2 (time domain, natural order)
-//   [k][4..7][s] = fhat_x1, fhat_x2, fhat_y1, fhat_y2 (tau-Fourier, slot order = lane order, normalised by 1/N)
-// A warp writes/reads 8 x 16 x N contiguous bytes per particle: fully coalesced 16-byte accesses.
-
-constexpr int kPhaseBlock = 256;
-
-// Phase A = preparation + gather(E_old) + compute_f + ua_step1 (x and y) + predictor deposit
-//           ua_steps.F90:15-236, interpolation_m6.F90:40-191, compute_rho_m6.F90:47-189
-template <int N>
-__global__ void __launch_bounds__(kPhaseBlock) k_phase_a(PhaseParams P) {
-    TauLane<N> L; L.init(threadIdx.x & 31);
-    WarpMap<N> W;
-    const double invN = 1.0 / (double)N;
-    for (int64_t base = W.first; base < P.np; base += W.stride) {
-        const int64_t kraw = base + W.g;
-        const bool valid = kraw < P.np;
-        const int64_t k = valid ? kraw : P.np - 1;
-        Pcl p;
-        {
-            const double2 xx = P.x[k], vv = P.v[k], ee = P.ep[k];
-            p.x1 = xx.x; p.x2 = xx.y; p.vx = vv.x; p.vy = vv.y; p.ex = ee.x; p.ey = ee.y;
-        }
-        double xt1, xt2, interv; cd yt1, yt2;
-        prep_particle<N>(L, P.eps, P.dt, p, xt1, xt2, yt1, yt2, interv);
-
-        double et1, et2;
-        {
-            double xw, yw;
-            const Cell c = m6_cell_fast(P.m, xt1, xt2, P.wrap, xw, yw);
-            m6_gather_fast(P.m, P.emesh, c, et1, et2);
-        }
-        cd fx1, fx2, fy1, fy2;
-        force_terms<N>(L, 1.0 / p.b, interv, yt1, yt2, et1, et2, fx1, fx2, fy1, fy2);
-        fx1 = rmul(invN, fft_fwd<N>(fx1, L)); fx2 = rmul(invN, fft_fwd<N>(fx2, L));
-        fy1 = rmul(invN, fft_fwd<N>(fy1, L)); fy2 = rmul(invN, fft_fwd<N>(fy2, L));
-
-        const cd elt = elt_minus<N>(L, p.t, P.eps);
-        cd pl, ql;
-        pl_ql<N>(L, p.t, P.eps, elt, pl, ql);
-        const cd eN = rmul(invN, elt);
-
-        // ua_step1 in Fourier space: xhat = elt/N * FFT(xt) + pl * fhat        ua_steps.F90:217-227
-        cd xh1 = cfma(pl, fx1, cmul(eN, fft_fwd<N>(mk(xt1, 0.0), L)));
-        cd xh2 = cfma(pl, fx2, cmul(eN, fft_fwd<N>(mk(xt2, 0.0), L)));
-        cd yh1 = cfma(pl, fy1, cmul(eN, fft_fwd<N>(yt1, L)));
-        cd yh2 = cfma(pl, fy2, cmul(eN, fft_fwd<N>(yt2, L)));
-
-        // predictor deposit: position at tau* = t/eps straight from the Fourier coefficients
-        // (FFT(IFFT(xhat))/N == xhat)                                            compute_rho_m6.F90:74-87
-        const double pos1 = eval_tau_star<N>(xh1, elt).re;
-        const double pos2 = eval_tau_star<N>(xh2, elt).re;
-
-        xh1 = fft_bwd<N>(xh1, L); xh2 = fft_bwd<N>(xh2, L);                       // :231-232
-        yh1 = fft_bwd<N>(yh1, L); yh2 = fft_bwd<N>(yh2, L);
-
-        if (valid) {
-            double2 *s = P.store + (size_t)k * 8 * N + L.j;
-            s[0 * N] = make_double2(xh1.re, xh1.im);
-            s[1 * N] = make_double2(xh2.re, xh2.im);
-            s[2 * N] = make_double2(yh1.re, yh1.im);
-            s[3 * N] = make_double2(yh2.re, yh2.im);
-            s[4 * N] = make_double2(fx1.re, fx1.im);
-            s[5 * N] = make_double2(fx2.re, fx2.im);
-            s[6 * N] = make_double2(fy1.re, fy1.im);
-            s[7 * N] = make_double2(fy2.re, fy2.im);
-            if (L.j == 0) P.tb[k] = make_double2(p.t, p.b);
-            double xw, yw;
-            const Cell c = m6_cell_exact(P.m, pos1, pos2, P.wrap, xw, yw);
-            m6_scatter(P.m, P.rho, c, P.weight, L.j, N);
-        }
-    }
-}
-
-// Phase B = gather(E_new) + compute_f + ua_step2 (x and y) + corrector deposit + compute_v
-//           ua_steps.F90:117-307
-template <int N>
-__global__ void __launch_bounds__(kPhaseBlock) k_phase_b(PhaseParams P) {
-    TauLane<N> L; L.init(threadIdx.x & 31);
-    WarpMap<N> W;
-    const double invN = 1.0 / (double)N;
-    for (int64_t base = W.first; base < P.np; base += W.stride) {
-        const int64_t kraw = base + W.g;
-        const bool valid = kraw < P.np;
-        const int64_t k = valid ? kraw : P.np - 1;
-        const double2 *s = P.store + (size_t)k * 8 * N + L.j;
-        const double2 tb = P.tb[k];
-        const double t = tb.x, b = tb.y;
-        cd xt1 = mk(s[0 * N].x, s[0 * N].y), xt2 = mk(s[1 * N].x, s[1 * N].y);
-        cd yt1 = mk(s[2 * N].x, s[2 * N].y), yt2 = mk(s[3 * N].x, s[3 * N].y);
-        const cd fx1 = mk(s[4 * N].x, s[4 * N].y), fx2 = mk(s[5 * N].x, s[5 * N].y);
-        const cd fy1 = mk(s[6 * N].x, s[6 * N].y), fy2 = mk(s[7 * N].x, s[7 * N].y);
-
-        double et1, et2;
-        {
-            double xw, yw;
-            const Cell c = m6_cell_fast(P.m, xt1.re, xt2.re, P.wrap, xw, yw);
-            m6_gather_fast(P.m, P.emesh, c, et1, et2);
-        }
-        const double interv = (1.0 + 0.5 * sin(xt1.re) * sin(xt2.re) - b) / P.eps;       // ua_steps.F90:177
-        cd gx1, gx2, gy1, gy2;
-        force_terms<N>(L, 1.0 / b, interv, yt1, yt2, et1, et2, gx1, gx2, gy1, gy2);
-        gx1 = rmul(invN, fft_fwd<N>(gx1, L)); gx2 = rmul(invN, fft_fwd<N>(gx2, L));
-        gy1 = rmul(invN, fft_fwd<N>(gy1, L)); gy2 = rmul(invN, fft_fwd<N>(gy2, L));
-
-        // elt/N*xf + pl*fhat == FFT(predicted xt)/N : the predictor's Fourier image need not be stored
-        xt1 = rmul(invN, fft_fwd<N>(xt1, L)); xt2 = rmul(invN, fft_fwd<N>(xt2, L));
-        yt1 = rmul(invN, fft_fwd<N>(yt1, L)); yt2 = rmul(invN, fft_fwd<N>(yt2, L));
-
-        const cd elt = elt_minus<N>(L, t, P.eps);
-        cd pl, ql;
-        pl_ql<N>(L, t, P.eps, elt, pl, ql);
-        const cd qt = rmul(1.0 / t, ql);
-        // ua_step2: + ql*(ghat - fhat)/t                                            ua_steps.F90:260-263
-        xt1 = cfma(qt, csub(gx1, fx1), xt1); xt2 = cfma(qt, csub(gx2, fx2), xt2);
-        yt1 = cfma(qt, csub(gy1, fy1), yt1); yt2 = cfma(qt, csub(gy2, fy2), yt2);
-
-        const double pos1 = eval_tau_star<N>(xt1, elt).re;                               // compute_rho_m6.F90:74-87
-        const double pos2 = eval_tau_star<N>(xt2, elt).re;
-        const double px = eval_tau_star<N>(yt1, elt).re;                                 // ua_steps.F90:293-300
-        const double py = eval_tau_star<N>(yt2, elt).re;
-        double sn, cs;
-        sincos(t / P.eps, &sn, &cs);
-
-        if (valid) {
-            double xw, yw;
-            const Cell c = m6_cell_exact(P.m, pos1, pos2, P.wrap, xw, yw);
-            if (L.j == 0) {
-                P.x[k] = make_double2(xw, yw);
-                P.v[k] = make_double2(cs * px + sn * py, cs * py - sn * px);             // ua_steps.F90:302-303
-            }
-            m6_scatter(P.m, P.rho, c, P.weight, L.j, N);
-        }
-    }
-}
-
-// =================================================================================================
 // 4. loaders / diagnostics
 // =================================================================================================
 
@@ -849,20 +690,6 @@ cudaError_t launch_poisson(const LaunchCtx &c, const MeshDev &m, const PoissonWo
         k_energy<<<1, kMeshBlock, 0, c.stream>>>(m, reinterpret_cast<const double2 *>(emesh), energy);
         count(c);
     }
-    return cudaGetLastError();
-}
-
-cudaError_t launch_phase_a(const LaunchCtx &c, const PhaseParams &p) {
-    if (p.np <= 0) return cudaSuccess;
-    UAPIC_DISPATCH_N(p.ntau, (k_phase_a<N><<<grid_for(c, p.np, (kPhaseBlock / 32) * (32 / N), 4), kPhaseBlock, 0, c.stream>>>(p)));
-    count(c);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_phase_b(const LaunchCtx &c, const PhaseParams &p) {
-    if (p.np <= 0) return cudaSuccess;
-    UAPIC_DISPATCH_N(p.ntau, (k_phase_b<N><<<grid_for(c, p.np, (kPhaseBlock / 32) * (32 / N), 4), kPhaseBlock, 0, c.stream>>>(p)));
-    count(c);
     return cudaGetLastError();
 }
 
