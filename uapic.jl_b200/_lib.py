@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libuapic_b200.so")
+# UAPIC_B200_LIB lets a developer A/B-test another build of the SAME library (still CUDA-only, no fallback)
+LIB_PATH = os.environ.get("UAPIC_B200_LIB") or os.path.join(_HERE, "libuapic_b200.so")
 
 OK = 0
 WRAP_FORTRAN, WRAP_JULIA = 0, 1

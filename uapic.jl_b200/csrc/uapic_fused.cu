@@ -28,9 +28,15 @@ namespace uapic {
 
 namespace {
 
-constexpr int kPhaseBlock = 256;
+#ifndef UAPIC_PHASE_BLOCK
+#define UAPIC_PHASE_BLOCK 256
+#endif
+#ifndef UAPIC_PHASE_MINB
+#define UAPIC_PHASE_MINB 2
+#endif
+constexpr int kPhaseBlock = UAPIC_PHASE_BLOCK;
+constexpr int kPhaseMinBlocks = UAPIC_PHASE_MINB;
 
-DEVINL double flip(double x, unsigned m) { return __hiloint2double(__double2hiint(x) ^ (int)m, __double2loint(x)); }
 
 template <int N> struct FusedLane {
     static constexpr int LOG = Log2<N>::v;
@@ -38,6 +44,7 @@ template <int N> struct FusedLane {
     unsigned sgn[LOG];            // 0x80000000 on the lower lane of each butterfly, per stage
     int src_neg, src_m1, src_p1;  // lanes (inside the group) holding Fourier slots -k, k-1, k+1
     double inv_l, inv_l2, inv_lN; // 1/l, 1/l^2, 1/(l*N) of this lane's slot (0 for k = 0)
+    double s1, sN;                // +-1 and +-1/N: minus on odd lanes (sign convention of fft_*_b below)
 
     DEVINL static int lane_of(int freq) { return (int)(__brev((unsigned)(freq & (N - 1))) >> (32 - LOG)); }
 
@@ -45,6 +52,12 @@ template <int N> struct FusedLane {
         T.init(lane);
 #pragma unroll
         for (int s = 0; s < LOG; ++s) sgn[s] = (T.j & (N >> (s + 1))) ? 0x80000000u : 0u;
+        // lower lanes carry the NEGATED twiddle (see fft_fwd_b); upper lanes keep 1
+#pragma unroll
+        for (int s = 0; s < LOG - 1; ++s)
+            if (T.j & (N >> (s + 1))) { T.twr[s] = -T.twr[s]; T.twi[s] = -T.twi[s]; }
+        s1 = (T.j & 1) ? -1.0 : 1.0;
+        sN = s1 / (double)N;
         src_neg = lane_of(N - T.k);
         src_m1 = lane_of(T.k - 1 + N);
         src_p1 = lane_of(T.k + 1);
@@ -60,18 +73,29 @@ template <int N> DEVINL cd shfl_idx(cd v, int src) {
     return mk(__shfl_sync(kFull, v.re, src, N), __shfl_sync(kFull, v.im, src, N));
 }
 
-// B independent length-N transforms at once: same butterflies as fft_fwd/fft_bwd, interleaved for ILP
+// shuffle a double with lane^h and flip its sign where `m` has the sign bit: the XOR lands on the freshly received
+// high word, so no register-pair shuffling is needed
+DEVINL double shfl_xor_flip(double v, int h, unsigned m) {
+    const int lo = __shfl_xor_sync(kFull, __double2loint(v), h);
+    const int hi = __shfl_xor_sync(kFull, __double2hiint(v), h) ^ (int)m;
+    return __hiloint2double(hi, lo);
+}
+
+// B independent length-N transforms at once, interleaved for ILP.  Sign bookkeeping keeps every butterfly a plain
+// add of the local value and the (possibly sign-flipped) received one:
+//   forward (DIF): d = v + flipL(o), then times the lane's twiddle register, which holds -w on lower lanes
+//                  (lower: (v - o)(-w) = (o - v) w).  The last stage has no twiddle to absorb the sign, so
+//                  OUTPUTS ARE NEGATED ON ODD LANES: multiply them by L.s1 (or L.sN to normalise as well).
+//   backward (DIT): v *= conj(twiddle register) (= -conj(w) on lower lanes), d = v - flipL(o).
+//                  INPUTS MUST BE PRE-NEGATED ON ODD LANES (fold L.s1 into whatever produces them).
 template <int N, int B> DEVINL void fft_fwd_b(cd (&v)[B], const FusedLane<N> &L) {
     constexpr int LOG = FusedLane<N>::LOG;
 #pragma unroll
     for (int s = 0; s < LOG; ++s) {
         const int h = N >> (s + 1);
-        cd o[B];
-#pragma unroll
-        for (int q = 0; q < B; ++q) o[q] = shfl_xor(v[q], h);
 #pragma unroll
         for (int q = 0; q < B; ++q) {
-            cd d = mk(o[q].re + flip(v[q].re, L.sgn[s]), o[q].im + flip(v[q].im, L.sgn[s]));   // upper: v+o ; lower: o-v
+            cd d = mk(v[q].re + shfl_xor_flip(v[q].re, h, L.sgn[s]), v[q].im + shfl_xor_flip(v[q].im, h, L.sgn[s]));
             if (h > 1) d = cmul(d, mk(L.T.twr[s], L.T.twi[s]));
             v[q] = d;
         }
@@ -83,15 +107,12 @@ template <int N, int B> DEVINL void fft_bwd_b(cd (&v)[B], const FusedLane<N> &L)
 #pragma unroll
     for (int s = LOG - 1; s >= 0; --s) {
         const int h = N >> (s + 1);
-        if (h > 1) {
 #pragma unroll
-            for (int q = 0; q < B; ++q) v[q] = cmulc(v[q], mk(L.T.twr[s], L.T.twi[s]));
+        for (int q = 0; q < B; ++q) {
+            cd a = v[q];
+            if (h > 1) a = cmulc(a, mk(L.T.twr[s], L.T.twi[s]));
+            v[q] = mk(a.re - shfl_xor_flip(a.re, h, L.sgn[s]), a.im - shfl_xor_flip(a.im, h, L.sgn[s]));
         }
-        cd o[B];
-#pragma unroll
-        for (int q = 0; q < B; ++q) o[q] = shfl_xor(v[q], h);
-#pragma unroll
-        for (int q = 0; q < B; ++q) v[q] = mk(o[q].re + flip(v[q].re, L.sgn[s]), o[q].im + flip(v[q].im, L.sgn[s]));
     }
 }
 
@@ -239,11 +260,11 @@ struct FusedParams {
 
 // =================================================================================================
 template <int N>
-__global__ void __launch_bounds__(kPhaseBlock, 2) k_phase_a(FusedParams F) {
+__global__ void __launch_bounds__(kPhaseBlock, kPhaseMinBlocks) k_phase_a(FusedParams F) {
     const PhaseParams &P = F.p;
     FusedLane<N> L; L.init(threadIdx.x & 31);
     WarpMap<N> W;
-    const double eps = P.eps, inv_eps = F.inv_eps, invN = 1.0 / (double)N;
+    const double eps = P.eps, inv_eps = F.inv_eps;
     const double ct = L.T.ct, st = L.T.st;
     const int k = L.T.k;
     for (int64_t base = W.first; base < P.np; base += W.stride) {
@@ -265,6 +286,7 @@ __global__ void __launch_bounds__(kPhaseBlock, 2) k_phase_a(FusedParams F) {
         const double eyb = ((-ct * vx - st * vy) * interv + ee.y) * rb;   // :90
         cd z[1] = {mk(ct * exb - st * eyb, st * exb + ct * eyb)};          // r1 + i r2   :92-93
         fft_fwd_b<N, 1>(z, L);                                            // :97-98 (both real signals at once)
+        z[0] = rmul(L.s1, z[0]);
         const cd wn = shfl_idx<N>(z[0], L.src_neg);
         cd c[2];   // filtered coefficients, :100-103 ; slot 0 keeps the unnormalised sums
         if (k == 0) {
@@ -275,7 +297,7 @@ __global__ void __launch_bounds__(kPhaseBlock, 2) k_phase_a(FusedParams F) {
             c[1] = mk(-s * (z[0].re - wn.re), -s * (z[0].im + wn.im));
         }
         const double r10sum = group_bcast0<N>(c[0].re), r20sum = group_bcast0<N>(c[1].re);
-        cd rp[2] = {c[0], c[1]};
+        cd rp[2] = {rmul(L.s1, c[0]), rmul(L.s1, c[1])};
         fft_bwd_b<N, 2>(rp, L);                                           // :105-106
         const cd r10 = group_bcast0<N>(rp[0]), r20 = group_bcast0<N>(rp[1]);
         const cd yt1 = mk(vx + (rp[0].re - r10.re) * eps, (rp[0].im - r10.im) * eps);   // :109
@@ -303,7 +325,7 @@ __global__ void __launch_bounds__(kPhaseBlock, 2) k_phase_a(FusedParams F) {
         cd fy[2];
         fy_time<N>(L, rb, interv, yt1, yt2, et1, et2, fy[0], fy[1]);
         fft_fwd_b<N, 2>(fy, L);
-        fy[0] = rmul(invN, fy[0]); fy[1] = rmul(invN, fy[1]);
+        fy[0] = rmul(L.sN, fy[0]); fy[1] = rmul(L.sN, fy[1]);
 
         // ---- ua_step1 for x and y (ua_steps.F90:215-234) ----
         const cd elt = elt_minus<N>(L.T, t, eps);                         // :224
@@ -317,15 +339,18 @@ __global__ void __launch_bounds__(kPhaseBlock, 2) k_phase_a(FusedParams F) {
             if (k == (1 & (N - 1)) && N > 1 && k != 0) { xh1 = mk(xh1.re - he * vyb, xh1.im - he * vxb); xh2 = mk(xh2.re + he * vxb, xh2.im - he * vyb); }
             if (k == N - 1 && k != 0) { xh1 = mk(xh1.re - he * vyb, xh1.im + he * vxb); xh2 = mk(xh2.re + he * vxb, xh2.im + he * vyb); }
         }
+        // everything below is carried NEGATED ON ODD LANES (input convention of fft_bwd_b); the position sums are
+        // products of two such quantities, so they are unaffected
+        const cd elts = rmul(L.s1, elt), pls = rmul(L.s1, pl);
         cd o4[4];
-        o4[0] = cfma(pl, fx1, cmul(elt, xh1));                            // :226
-        o4[1] = cfma(pl, fx2, cmul(elt, xh2));                            // :227
-        o4[2] = cfma(pl, fy[0], cmul(elt, yh1));
-        o4[3] = cfma(pl, fy[1], cmul(elt, yh2));
+        o4[0] = cfma(pls, fx1, cmul(elts, xh1));                          // :226
+        o4[1] = cfma(pls, fx2, cmul(elts, xh2));                          // :227
+        o4[2] = cfma(pls, fy[0], cmul(elts, yh1));
+        o4[3] = cfma(pls, fy[1], cmul(elts, yh2));
 
         // ---- predictor deposit: position at tau* = t/eps (compute_rho_m6.F90:74-87) ----
-        const double pos1 = group_sum<N>(dot_conj(o4[0], elt));
-        const double pos2 = group_sum<N>(dot_conj(o4[1], elt));
+        const double pos1 = group_sum<N>(dot_conj(o4[0], elts));
+        const double pos2 = group_sum<N>(dot_conj(o4[1], elts));
 
         fft_bwd_b<N, 4>(o4, L);                                           // :231-232
 
@@ -351,11 +376,11 @@ __global__ void __launch_bounds__(kPhaseBlock, 2) k_phase_a(FusedParams F) {
 
 // =================================================================================================
 template <int N>
-__global__ void __launch_bounds__(kPhaseBlock, 2) k_phase_b(FusedParams F) {
+__global__ void __launch_bounds__(kPhaseBlock, kPhaseMinBlocks) k_phase_b(FusedParams F) {
     const PhaseParams &P = F.p;
     FusedLane<N> L; L.init(threadIdx.x & 31);
     WarpMap<N> W;
-    const double eps = P.eps, inv_eps = F.inv_eps, invN = 1.0 / (double)N;
+    const double eps = P.eps, inv_eps = F.inv_eps;
     for (int64_t base = W.first; base < P.np; base += W.stride) {
         const int64_t kraw = base + W.g;
         const bool valid = kraw < P.np;
@@ -382,7 +407,7 @@ __global__ void __launch_bounds__(kPhaseBlock, 2) k_phase_b(FusedParams F) {
         // six forward transforms at once: predicted x, y (-> elt/N*xf + pl*fhat) and gy   (:187-195)
         fft_fwd_b<N, 6>(f6, L);
 #pragma unroll
-        for (int q = 0; q < 6; ++q) f6[q] = rmul(invN, f6[q]);
+        for (int q = 0; q < 6; ++q) f6[q] = rmul(L.sN, f6[q]);
         cd gx1, gx2;
         fx_from_yhat<N>(L, rb, f6[2], f6[3], gx1, gx2);
 
@@ -416,7 +441,7 @@ __global__ void __launch_bounds__(kPhaseBlock, 2) k_phase_b(FusedParams F) {
 inline int phase_grid(const LaunchCtx &c, int64_t np, int N) {
     const int per_block = (kPhaseBlock / 32) * (32 / N);
     int64_t need = (np + per_block - 1) / per_block;
-    const int64_t cap = (int64_t)c.sm_count * 2;
+    const int64_t cap = (int64_t)c.sm_count * kPhaseMinBlocks;
     if (need < 1) need = 1;
     return (int)(need < cap ? need : cap);
 }
