@@ -1,0 +1,108 @@
+"""CPU (gloo, world_size 2) tests of the multi-GPU host logic: contiguous particle sharding and the all-reduce of the
+rho mesh.  The per-shard deposits come from the oracle (the product cannot run without a GPU); what is under test is
+uapic_b200.dist, not the deposit."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch.multiprocessing as mp
+
+import uapic_b200 as ub
+
+from conftest import seeded_load
+
+
+def test_shard_range_partitions_exactly():
+    for n in (0, 1, 7, 204800, 10**8 + 3):
+        for world in (1, 2, 3, 8):
+            edges = [ub.dist.shard_range(n, r, world) for r in range(world)]
+            assert edges[0][0] == 0 and edges[-1][1] == n
+            for a, b in zip(edges[:-1], edges[1:]):
+                assert a[1] == b[0]
+            sizes = [hi - lo for lo, hi in edges]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, npart, out_dir):
+    import torch.distributed as dist
+    import oracle
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    om, x, _ = seeded_load(npart, seed=4)
+    w = 8 * np.pi ** 2 / npart
+    lo, hi = ub.dist.shard_range(npart, rank, world)
+    rho = np.zeros((om.nx + 1, om.ny + 1), order="F")
+    # the epilogue (scale, subtract mean, ghost copy) is linear, so summing per-shard meshes equals the global mesh
+    oracle.corc().compute_rho_m6(om, np.asfortranarray(x[:, lo:hi]), w, rho)
+    total = ub.dist.allreduce_host(rho)
+    if rank == 0:
+        np.save(os.path.join(out_dir, "rho_sum.npy"), total)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_allreduce_of_sharded_deposits_equals_global_deposit(tmp_path):
+    import oracle
+    npart, world = 5001, 2
+    mp.spawn(_worker, args=(world, _free_port(), npart, str(tmp_path)), nprocs=world, join=True)
+    om, x, _ = seeded_load(npart, seed=4)
+    rho = np.zeros((om.nx + 1, om.ny + 1), order="F")
+    oracle.corc().compute_rho_m6(om, x.copy(order="F"), 8 * np.pi ** 2 / npart, rho)
+    got = np.load(tmp_path / "rho_sum.npy")
+    assert np.abs(got - rho).max() < 1e-12 * np.abs(rho).max()
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    """C-ABI contract on a CPU-only box: the .so loads, exports everything include/uapic_b200.h declares, and every
+    compute entry point fails loudly (no CPU fallback)."""
+    import re
+    lib = ub.lib()
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "uapic_b200.h")).read()
+    declared = set(re.findall(r"\b(uapic_[a-z0-9_]+)\s*\(", hdr)) - {"uapic_allreduce_fn"}
+    assert declared == set(ub.EXPORTS), declared ^ set(ub.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert ub.lib().uapic_compiled_arch() == 100
+    assert ub._lib.fixed_point_scale(8 * np.pi ** 2) == 2.0 ** 54
+    if ub.device_count() == 0:
+        m = ub.Mesh(0, 1, 8, 0, 1, 8)
+        with pytest.raises(ub.UapicError) as e:
+            ub.Poisson(m)(ub.MeshFields(m))
+        assert e.value.code == -2          # UAPIC_ENODEVICE
+        with pytest.raises(ub.UapicError):
+            ub.Session(m, 16, 0.1, 0.1, 10)
+
+
+def test_particles_dat_roundtrip(tmp_path):
+    """src/read_particles.jl format: `ix iy dpx dpy vx vy`; test/test_particles.jl:4-14 pins nbpart == 204800 on the real file"""
+    mesh = ub.Mesh(0, 4 * np.pi, 128, 0, 2 * np.pi, 64)
+    p = ub.plasma(mesh, 2000, seed=1)
+    f = tmp_path / "particles.dat"
+    ub.write_particles(str(f), mesh, p.x, p.v)
+    q = ub.read_particles(str(f), mesh)
+    assert q.nbpart == 2000 and q.w == pytest.approx(8 * np.pi ** 2 / 2000)
+    assert np.abs(q.x - p.x).max() < 1e-13 and np.array_equal(q.v, p.v)
+    # densities of fortran/particles.F90:77,94
+    big = ub.plasma(mesh, 100000, seed=2)
+    assert abs(np.sin(big.x[1]).mean() - 0.5) < 0.01 and abs((big.v[0] ** 2).mean() - 5.0) < 0.1
+
+
+def test_gfortran_stream_reproduces_the_reference_seed():
+    """fortran/particles.F90:54-66: the bundled libgfortran accepts the reference's 33-word seed; the draw is deterministic"""
+    mesh = ub.Mesh(0, 4 * np.pi, 128, 0, 2 * np.pi, 64)
+    a, src = ub.plasma(mesh, 300, use_gfortran=True, return_source=True)
+    if "libgfortran" not in src:
+        pytest.skip("libgfortran not loadable here")
+    b = ub.plasma(mesh, 300, use_gfortran=True)
+    assert np.array_equal(a.x, b.x) and np.array_equal(a.v, b.v)
+    assert 0 <= a.x[0].min() and a.x[0].max() < 4 * np.pi
