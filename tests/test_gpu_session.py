@@ -184,3 +184,52 @@ def test_session_state_errors():
             s.step(1)
     with pytest.raises(ub.UapicError):
         ub.Session(mesh, 12, 0.1, DT, 100)
+
+
+def test_stage_api_runs_the_reference_script_sequence():
+    """test/bupdate.jl:63-114 call for call through the stage API (Julia conventions: unnormalised fft!, yt left in Fourier
+    space after the corrector), against the numpy twin of the Julia sources and against the fused session."""
+    from oracle import nporc
+    npart, ntau, eps, nstep = 3000, 16, 0.1, 3
+    _, x0, v0 = seeded_load(npart, seed=61)
+    mesh = ub.Mesh(0, DIMX, 128, 0, DIMY, 64)
+    w = DIMX * DIMY / npart
+    fields = ub.MeshFields(mesh)
+    p = ub.Particles(npart, w)
+    p.x[:], p.v[:] = x0, v0
+    poisson = ub.Poisson(mesh)
+    ua = ub.UA(ntau, eps, npart)
+    shp = (ntau, 2, npart)
+    z = lambda: np.zeros(shp, np.complex128, order="F")  # noqa: E731
+    et = np.zeros(shp, order="F")
+    xt, xft, yt, yft, fx, fy, gx, gy = z(), z(), z(), z(), z(), z(), z(), z()
+    nrj = []
+    ub.compute_rho_m6(fields, p)                               # :63
+    nrj.append(poisson(fields))                                # :65
+    ub.interpol_eb_m6(p, fields)                               # :67
+    for _ in range(nstep):
+        ub.preparation(ua, DT, p, xt, yt)                      # :71
+        ub.update_particles_e(p, et, fields, ua, xt)           # :73
+        ub.compute_f(fx, fy, ua, p, xt, yt, et)                # :77
+        ub.fft_tau(xft, ua, xt)                                # :79
+        ub.ua_step(xt, xft, ua, p, fx)                         # :80
+        ub.fft_tau(yft, ua, yt)                                # :82
+        ub.ua_step(yt, yft, ua, p, fy)                         # :83
+        ub.ifft_tau(xt)                                        # :85
+        ub.ifft_tau(yt)                                        # :86
+        ub.update_particles_x(p, fields, ua, xt)               # :88
+        nrj.append(poisson(fields))                            # :90
+        ub.update_particles_e(p, et, fields, ua, xt)           # :92
+        ub.compute_f(gx, gy, ua, p, xt, yt, et)                # :96
+        ub.ua_step(xt, xft, ua, p, fx, gx)                     # :98
+        ub.ua_step(yt, yft, ua, p, fy, gy)                     # :100
+        ub.ifft_tau(xt)                                        # :102
+        ub.update_particles_x(p, fields, ua, xt)               # :104
+        nrj.append(poisson(fields))                            # :106
+        ub.compute_v(yt, p, ua)                                # :110
+    nrj = np.array(nrj)
+    mm = nporc.Mesh(0, DIMX, 128, 0, DIMY, 64)
+    xo, vo, eno, _, _ = nporc.run_bupdate(mm, ntau, eps, DT, nstep, x0, v0, w)
+    _compare(p.x, p.v, nrj, xo, vo, eno, eps)
+    xs, vs, ens, _ = ub.run_bupdate(mesh, ntau, eps, DT, nstep, x0, v0, w, wrap=ub.WRAP_JULIA)
+    _compare(xs, vs, ens, p.x, p.v, nrj, eps)
