@@ -421,7 +421,7 @@ struct uapic_session {
     LaunchCtx lc;
     int64_t launches = 0;
     int64_t np_global = 0;
-    DevBuf x, v, ep, store, tb, raw, rho, emesh, rk, ek, energy, sumv;
+    DevBuf x, v, ep, store, tb, raw, rho, emesh, ehalo, rk, ek, energy, sumv;
     RhoAcc acc{};
     int64_t n_energy = 0, cap_energy = 0;
     uapic_allreduce_fn reduce = nullptr;
@@ -470,6 +470,7 @@ int session_field_solve(uapic_session *s) {
     if (s->n_energy >= s->cap_energy) return fail(UAPIC_ESTATE, "energy history full (%lld entries)", (long long)s->cap_energy);
     PoissonWork pw{s->rk.as<double2>(), s->ek.as<double2>()};
     CU(launch_poisson(s->lc, s->m, pw, s->rho.as<double>(), s->emesh.as<double>(), s->energy.as<double>() + s->n_energy));
+    CU(launch_extend_emesh(s->lc, s->m, s->emesh.as<double>(), s->ehalo.as<double2>()));
     s->n_energy++;
     return UAPIC_OK;
 }
@@ -479,7 +480,7 @@ PhaseParams session_params(uapic_session *s) {
     p.m = s->m; p.eps = s->cfg.eps; p.dt = s->cfg.dt; p.weight = s->cfg.weight; p.np = s->cfg.nbpart;
     p.wrap = s->cfg.wrap; p.ntau = s->cfg.ntau;
     p.x = s->x.as<double2>(); p.v = s->v.as<double2>(); p.ep = s->ep.as<double2>();
-    p.emesh = s->emesh.as<double2>(); p.store = s->store.as<double2>(); p.tb = s->tb.as<double2>();
+    p.emesh = s->emesh.as<double2>(); p.ehalo = s->ehalo.as<double2>(); p.store = s->store.as<double2>(); p.tb = s->tb.as<double2>();
     p.rho = s->acc;
     return p;
 }
@@ -498,8 +499,8 @@ int uapic_session_create(const uapic_config_t *cfg, uapic_session_t **out) {
     if (cfg->scheme != UAPIC_SCHEME_M6) return fail(UAPIC_EUNSUPPORTED, "only UAPIC_SCHEME_M6 is implemented in the session path");
     if (cfg->storage_mode != UAPIC_STORE_FULL) return fail(UAPIC_EUNSUPPORTED, "only UAPIC_STORE_FULL is implemented");
     if (cfg->wrap != UAPIC_WRAP_FORTRAN && cfg->wrap != UAPIC_WRAP_JULIA) return fail(UAPIC_EINVAL, "unknown wrap %d", cfg->wrap);
-    if (!poisson_size_supported(cfg->mesh.nx) || !poisson_size_supported(cfg->mesh.ny))
-        return fail(UAPIC_EUNSUPPORTED, "Poisson mesh %d x %d unsupported", cfg->mesh.nx, cfg->mesh.ny);
+    if (!poisson_size_supported(cfg->mesh.nx) || !poisson_size_supported(cfg->mesh.ny) || cfg->mesh.nx < 4 || cfg->mesh.ny < 4)
+        return fail(UAPIC_EUNSUPPORTED, "session mesh %d x %d unsupported (need 4 <= n, powers of two <= 1024 or any n <= 512)", cfg->mesh.nx, cfg->mesh.ny);
     DeviceInfo di{};
     TRY(device_info(cfg->device, &di));
     CU(cudaSetDevice(cfg->device));
@@ -526,6 +527,7 @@ int uapic_session_create(const uapic_config_t *cfg, uapic_session_t **out) {
     if (!rc) rc = session_alloc(s, s->raw, 8 * nrho);
     if (!rc) rc = session_alloc(s, s->rho, 8 * nrho);
     if (!rc) rc = session_alloc(s, s->emesh, 16 * nrho);
+    if (!rc) rc = session_alloc(s, s->ehalo, 16 * ehalo_nodes(s->m));
     if (!rc) rc = session_alloc(s, s->rk, 16 * nk);
     if (!rc) rc = session_alloc(s, s->ek, 32 * nk);
     if (!rc) rc = session_alloc(s, s->energy, 8 * (size_t)s->cap_energy);

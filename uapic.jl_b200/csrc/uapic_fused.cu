@@ -43,29 +43,43 @@ template <int N> struct FusedLane {
     TauLane<N> T;
     unsigned sgn[LOG];            // 0x80000000 on the lower lane of each butterfly, per stage
     int src_neg, src_m1, src_p1;  // lanes (inside the group) holding Fourier slots -k, k-1, k+1
-    double inv_l, inv_l2, inv_lN; // 1/l, 1/l^2, 1/(l*N) of this lane's slot (0 for k = 0)
     double s1, sN;                // +-1 and +-1/N: minus on odd lanes (sign convention of fft_*_b below)
+    // rarely used per-lane constants live in shared memory (they only depend on the lane): frees ~22 registers
+    const double2 *tws;           // [LOG-1][32] signed twiddles of this lane
+    const double *invs;           // [3][32]: 1/l, 1/l^2, 1/(l*N) of this lane's slot (0 for k = 0)
+    int lane;
+    DEVINL cd tw(int s) const { const double2 w = tws[s * 32 + lane]; return mk(w.x, w.y); }
+    DEVINL double inv_l() const { return invs[lane]; }
+    DEVINL double inv_l2() const { return invs[32 + lane]; }
+    DEVINL double inv_lN() const { return invs[64 + lane]; }
 
     DEVINL static int lane_of(int freq) { return (int)(__brev((unsigned)(freq & (N - 1))) >> (32 - LOG)); }
 
-    DEVINL void init(int lane) {
+    // sm_tw: 4*32 double2, sm_inv: 3*32 double, both __shared__; call from every thread, ends with __syncthreads
+    DEVINL void init(int lane_, double2 *sm_tw, double *sm_inv) {
+        lane = lane_;
         T.init(lane);
 #pragma unroll
         for (int s = 0; s < LOG; ++s) sgn[s] = (T.j & (N >> (s + 1))) ? 0x80000000u : 0u;
-        // lower lanes carry the NEGATED twiddle (see fft_fwd_b); upper lanes keep 1
-#pragma unroll
-        for (int s = 0; s < LOG - 1; ++s)
-            if (T.j & (N >> (s + 1))) { T.twr[s] = -T.twr[s]; T.twi[s] = -T.twi[s]; }
         s1 = (T.j & 1) ? -1.0 : 1.0;
         sN = s1 / (double)N;
         src_neg = lane_of(N - T.k);
         src_m1 = lane_of(T.k - 1 + N);
         src_p1 = lane_of(T.k + 1);
-        if (T.k != 0) {
-            inv_l = 1.0 / T.lf; inv_l2 = 1.0 / (T.lf * T.lf); inv_lN = 1.0 / (T.lf * (double)N);
-        } else {
-            inv_l = 0.0; inv_l2 = 0.0; inv_lN = 0.0;
+        if (threadIdx.x < 32) {
+            // lower lanes carry the NEGATED twiddle (see fft_fwd_b); upper lanes keep 1
+#pragma unroll
+            for (int s = 0; s < LOG - 1; ++s) {
+                const double sg = (T.j & (N >> (s + 1))) ? -1.0 : 1.0;
+                sm_tw[s * 32 + lane] = make_double2(sg * T.twr[s], sg * T.twi[s]);
+            }
+            const bool nz = T.k != 0;
+            sm_inv[lane] = nz ? 1.0 / T.lf : 0.0;
+            sm_inv[32 + lane] = nz ? 1.0 / (T.lf * T.lf) : 0.0;
+            sm_inv[64 + lane] = nz ? 1.0 / (T.lf * (double)N) : 0.0;
         }
+        tws = sm_tw; invs = sm_inv;
+        __syncthreads();
     }
 };
 
@@ -93,10 +107,11 @@ template <int N, int B> DEVINL void fft_fwd_b(cd (&v)[B], const FusedLane<N> &L)
 #pragma unroll
     for (int s = 0; s < LOG; ++s) {
         const int h = N >> (s + 1);
+        const cd w = (h > 1) ? L.tw(s) : mk(1.0, 0.0);
 #pragma unroll
         for (int q = 0; q < B; ++q) {
             cd d = mk(v[q].re + shfl_xor_flip(v[q].re, h, L.sgn[s]), v[q].im + shfl_xor_flip(v[q].im, h, L.sgn[s]));
-            if (h > 1) d = cmul(d, mk(L.T.twr[s], L.T.twi[s]));
+            if (h > 1) d = cmul(d, w);
             v[q] = d;
         }
     }
@@ -107,10 +122,11 @@ template <int N, int B> DEVINL void fft_bwd_b(cd (&v)[B], const FusedLane<N> &L)
 #pragma unroll
     for (int s = LOG - 1; s >= 0; --s) {
         const int h = N >> (s + 1);
+        const cd w = (h > 1) ? L.tw(s) : mk(1.0, 0.0);
 #pragma unroll
         for (int q = 0; q < B; ++q) {
             cd a = v[q];
-            if (h > 1) a = cmulc(a, mk(L.T.twr[s], L.T.twi[s]));
+            if (h > 1) a = cmulc(a, w);
             v[q] = mk(a.re - shfl_xor_flip(a.re, h, L.sgn[s]), a.im - shfl_xor_flip(a.im, h, L.sgn[s]));
         }
     }
@@ -149,27 +165,27 @@ DEVINL int wrap_fast(int i, int off, int n) {
     return r;
 }
 
-// separable M6 gather: 6 rows of 6 nodes, (ex,ey) pairs read as 16-byte words through the read-only path
-DEVINL void gather_fast(const MeshDev &m, const double2 *__restrict__ e, const Cell &c, double &e1, double &e2) {
+// separable M6 gather on the periodic halo copy of E: no index wrap, one base address per row and immediate offsets
+// for its 6 nodes; (ex,ey) pairs read as 16-byte words through the read-only path
+DEVINL void gather_fast(const MeshDev &m, const double2 *__restrict__ ehalo, const Cell &c, double &e1, double &e2) {
     double cx[6], cy[6];
     m6_weights_fast(c.dpx, cx);
     m6_weights_fast(c.dpy, cy);
-    int ix[6];
-#pragma unroll
-    for (int a = 0; a < 6; ++a) ix[a] = wrap_fast(c.i, a - 2, m.nx);
+    const int ldx = m.nx + 6;
+    const double2 *row = ehalo + (c.j * ldx + c.i);      // node (i-2, j-2)
     double s1 = 0.0, s2 = 0.0;
 #pragma unroll
     for (int b = 0; b < 6; ++b) {
-        const double2 *row = e + wrap_fast(c.j, b - 2, m.ny) * m.ld;
         double r1 = 0.0, r2 = 0.0;
 #pragma unroll
         for (int a = 0; a < 6; ++a) {
-            const double2 ev = __ldg(&row[ix[a]]);
+            const double2 ev = __ldg(row + a);
             r1 = fma(cx[a], ev.x, r1);
             r2 = fma(cx[a], ev.y, r2);
         }
         s1 = fma(cy[b], r1, s1);
         s2 = fma(cy[b], r2, s2);
+        row += ldx;
     }
     e1 = s1; e2 = s2;
 }
@@ -224,8 +240,9 @@ template <int N> DEVINL void pl_ql_fast(const FusedLane<N> &L, double t, double 
         pl = mk(t, 0.0);
         ql = mk(0.5 * t * t, 0.0);
     } else {
-        pl = mk(-eps * elt.im * L.inv_l, eps * (elt.re - 1.0) * L.inv_l);
-        ql = mk(eps * eps * (1.0 - elt.re) * L.inv_l2, -eps * fma(eps, elt.im, L.T.lf * t) * L.inv_l2);
+        const double il = L.inv_l(), il2 = L.inv_l2();
+        pl = mk(-eps * elt.im * il, eps * (elt.re - 1.0) * il);
+        ql = mk(eps * eps * (1.0 - elt.re) * il2, -eps * fma(eps, elt.im, L.T.lf * t) * il2);
     }
 }
 
@@ -262,7 +279,9 @@ struct FusedParams {
 template <int N>
 __global__ void __launch_bounds__(kPhaseBlock, kPhaseMinBlocks) k_phase_a(FusedParams F) {
     const PhaseParams &P = F.p;
-    FusedLane<N> L; L.init(threadIdx.x & 31);
+    __shared__ double2 sm_tw[4 * 32];
+    __shared__ double sm_inv[3 * 32];
+    FusedLane<N> L; L.init(threadIdx.x & 31, sm_tw, sm_inv);
     WarpMap<N> W;
     const double eps = P.eps, inv_eps = F.inv_eps;
     const double ct = L.T.ct, st = L.T.st;
@@ -292,7 +311,7 @@ __global__ void __launch_bounds__(kPhaseBlock, kPhaseMinBlocks) k_phase_a(FusedP
         if (k == 0) {
             c[0] = mk(z[0].re, 0.0); c[1] = mk(z[0].im, 0.0);
         } else {
-            const double s = 0.5 * L.inv_lN;
+            const double s = 0.5 * L.inv_lN();
             c[0] = mk(s * (z[0].im - wn.im), -s * (z[0].re + wn.re));
             c[1] = mk(-s * (z[0].re - wn.re), -s * (z[0].im + wn.im));
         }
@@ -316,7 +335,7 @@ __global__ void __launch_bounds__(kPhaseBlock, kPhaseMinBlocks) k_phase_a(FusedP
         {
             double xw, yw;
             const Cell cell = cell_fast(P.m, F.f, xt1, xt2, P.wrap, xw, yw);
-            gather_fast(P.m, P.emesh, cell, et1, et2);
+            gather_fast(P.m, P.ehalo, cell, et1, et2);
         }
 
         // ---- compute_f (ua_steps.F90:160-195) ----
@@ -378,7 +397,9 @@ __global__ void __launch_bounds__(kPhaseBlock, kPhaseMinBlocks) k_phase_a(FusedP
 template <int N>
 __global__ void __launch_bounds__(kPhaseBlock, kPhaseMinBlocks) k_phase_b(FusedParams F) {
     const PhaseParams &P = F.p;
-    FusedLane<N> L; L.init(threadIdx.x & 31);
+    __shared__ double2 sm_tw[4 * 32];
+    __shared__ double sm_inv[3 * 32];
+    FusedLane<N> L; L.init(threadIdx.x & 31, sm_tw, sm_inv);
     WarpMap<N> W;
     const double eps = P.eps, inv_eps = F.inv_eps;
     for (int64_t base = W.first; base < P.np; base += W.stride) {
@@ -399,7 +420,7 @@ __global__ void __launch_bounds__(kPhaseBlock, kPhaseMinBlocks) k_phase_b(FusedP
         {
             double xw, yw;
             const Cell cell = cell_fast(P.m, F.f, f6[0].re, f6[1].re, P.wrap, xw, yw);
-            gather_fast(P.m, P.emesh, cell, et1, et2);
+            gather_fast(P.m, P.ehalo, cell, et1, et2);
         }
         const double interv = (1.0 + 0.5 * sin(f6[0].re) * sin(f6[1].re) - b) * inv_eps;   // :177
         fy_time<N>(L, rb, interv, f6[2], f6[3], et1, et2, f6[4], f6[5]);

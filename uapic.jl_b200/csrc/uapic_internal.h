@@ -48,6 +48,9 @@ struct PoissonWork { double2 *rk; double2 *ek; };   // rk: (nx/2+1)*ny ; ek: 2*(
 cudaError_t launch_poisson(const LaunchCtx &c, const MeshDev &m, const PoissonWork &w, const double *rho, double *emesh,
                            double *energy);
 bool poisson_size_supported(int n);
+// periodic halo copy of the E mesh for the fused gathers: node (i,j), i in [-2,nx+3], j in [-2,ny+3], holds E(i mod nx, j mod ny)
+inline size_t ehalo_nodes(const MeshDev &m) { return (size_t)(m.nx + 6) * (size_t)(m.ny + 6); }
+cudaError_t launch_extend_emesh(const LaunchCtx &c, const MeshDev &m, const double *emesh, double2 *ehalo);
 
 // ---- fused phase kernels (session path) -----------------------------------------------------------------------
 struct PhaseParams {
@@ -60,6 +63,7 @@ struct PhaseParams {
     double2 *v;            // (2,np): read by A, written by B
     const double2 *ep;     // (2,np): particles.e, frozen after init
     const double2 *emesh;  // (2,nx+1,ny+1)
+    const double2 *ehalo;  // periodic halo copy of emesh: (nx+6) x (ny+6) nodes, node (i,j) at [(i+2) + (nx+6)*(j+2)]
     double2 *store;        // np * 8 * ntau complex: what crosses the intra-step barrier
     double2 *tb;           // (t,b) per particle
     RhoAcc rho;

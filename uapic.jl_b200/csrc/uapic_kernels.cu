@@ -477,6 +477,19 @@ __global__ void k_poisson_rows_bwd(MeshDev m, const double2 *__restrict__ ek, do
     }
 }
 
+// periodic halo copy of E: lets the fused gathers address the 6x6 stencil without any index wrap
+// (the ghost row/column of the reference layout already is the i = nx / j = ny image; this extends it to [-2, n+3])
+__global__ void __launch_bounds__(kBlock) k_extend_emesh(MeshDev m, const double2 *__restrict__ emesh, double2 *__restrict__ ehalo) {
+    const int lx = m.nx + 6, ly = m.ny + 6;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < lx * ly; q += gridDim.x * blockDim.x) {
+        const int je = q / lx, ie = q - je * lx;
+        int i = ie - 2, j = je - 2;
+        i += (i < 0) ? m.nx : 0; i -= (i >= m.nx) ? m.nx : 0;
+        j += (j < 0) ? m.ny : 0; j -= (j >= m.ny) ? m.ny : 0;
+        ehalo[q] = emesh[i + m.ld * j];
+    }
+}
+
 // src/poisson.jl:80-81 : sum over the ghosted array of e1^2+e2^2, times dx*dy (fixed summation order)
 __global__ void __launch_bounds__(kMeshBlock) k_energy(MeshDev m, const double2 *__restrict__ emesh, double *energy) {
     __shared__ double sh[kMeshBlock];
@@ -697,6 +710,14 @@ cudaError_t launch_generate(const LaunchCtx &c, const MeshDev &m, int kind, uint
                             int64_t np_global, double alpha, double kx, double *x, double *v) {
     if (np <= 0) return cudaSuccess;
     k_generate<<<grid_for(c, np, kBlock), kBlock, 0, c.stream>>>(m, kind, seed, first, np, np_global, alpha, kx, x, v);
+    count(c);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_extend_emesh(const LaunchCtx &c, const MeshDev &m, const double *emesh, double2 *ehalo) {
+    if (m.nx < 4 || m.ny < 4) return cudaErrorInvalidValue;
+    const int n = (m.nx + 6) * (m.ny + 6);
+    k_extend_emesh<<<grid_for(c, n, kBlock), kBlock, 0, c.stream>>>(m, reinterpret_cast<const double2 *>(emesh), ehalo);
     count(c);
     return cudaGetLastError();
 }
