@@ -38,6 +38,8 @@ WORKLOADS = {
     "config3": ("landau", 32, 128, 128, 12_500_000, "BASELINE config 3 shard: 4D Landau load, ntau=32, 128x128, M6, 12.5e6 particles/GPU (1e8 at 8 GPUs)"),
     "config2": ("plasma", 16, 128, 64, 1_000_000, "BASELINE config 2: bupdate case, M6, 1e6 particles, ntau=16, 128x64"),
     "config5": ("landau", 32, 256, 256, 15_625_000, "BASELINE config 5 weak point: 5e8 particle-tau samples/GPU, ntau=32, 256x256, M6"),
+    # the literal config 3 on ONE GPU: needs --storage hybrid (store-full would take 410 GB)
+    "config3-1gpu": ("landau", 32, 128, 128, 100_000_000, "BASELINE config 3 on one GPU: 4D Landau load, 1e8 particles, ntau=32, 128x128, M6 (hybrid storage)"),
 }
 
 
@@ -163,6 +165,8 @@ def main():
     ap.add_argument("--workload", default="config3", choices=sorted(WORKLOADS))
     ap.add_argument("--particles-per-gpu", type=int, default=0)
     ap.add_argument("--deposit", default="fp64", choices=["fp64", "fixed"])
+    ap.add_argument("--storage", default="auto", choices=["auto", "full", "hybrid"],
+                    help="what crosses the intra-step barrier: 128 B/particle-tau (full) or 16 B + recompute (hybrid)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="particles in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -196,8 +200,12 @@ def main():
     mesh = ub.Mesh(0, DIMX, nx, 0, DIMY, ny)
     lo, hi = ub.dist.shard_range(np_global, rank, world)
     stream = torch.cuda.current_stream().cuda_stream
+    free_b, _ = torch.cuda.mem_get_info()
+    need_full = (hi - lo) * (ntau * 128 + 64) + (1 << 30)
+    storage = args.storage if args.storage != "auto" else ("full" if need_full < free_b else "hybrid")
     s = ub.Session(mesh, ntau, EPS, DT, hi - lo, nbpart_global=np_global, device=local, stream=stream,
-                   deposit_mode=ub.DEPOSIT_FIXED_POINT if args.deposit == "fixed" else ub.DEPOSIT_FP64_ATOMIC)
+                   deposit_mode=ub.DEPOSIT_FIXED_POINT if args.deposit == "fixed" else ub.DEPOSIT_FP64_ATOMIC,
+                   storage_mode=ub.STORE_HYBRID if storage == "hybrid" else ub.STORE_FULL)
     if world > 1:
         ub.dist.attach_torch_allreduce(s)
     s.generate_particles(load, seed=20190101, first_global_index=lo)
@@ -272,19 +280,21 @@ def main():
     if rank == 0:
         hbm, hbm_src = peaks()
         n_loc = hi - lo
-        bytes_a = n_loc * ntau * 128 + n_loc * 64          # reads x,v,e (48 B/particle); writes 128 B/sample + (t,b)
-        bytes_b = n_loc * ntau * 128 + n_loc * 48          # reads 128 B/sample + (t,b); writes x,v
+        per_sample = 16 if storage == "hybrid" else 128     # bytes per particle-tau crossing the barrier (one way)
+        bytes_a = n_loc * ntau * per_sample + n_loc * 64   # reads x,v,e (48 B/particle); writes the store + (t,b)
+        bytes_b = n_loc * ntau * per_sample + n_loc * 48   # reads the store + (t,b); writes x,v
         per_a, per_b = ms_a / max(nt, 1), ms_b / max(nt, 1)
         dom = ("uapic::k_phase_b", bytes_b, per_b) if per_b >= per_a else ("uapic::k_phase_a", bytes_a, per_a)
         achieved = dom[1] / (dom[2] * 1e-3) / 1e9 if dom[2] > 0 else 0.0
-        b_alg = 256 + 112 / ntau
+        b_alg = (256 if storage == "full" else 32) + 112 / ntau
         line = {
             "metric": "particle-tau updates/sec", "value": value, "unit": "particle-tau updates/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": desc, "load": load, "ntau": ntau, "mesh": [nx, ny], "eps": EPS, "dt": DT, "scheme": "M6",
                        "particles_per_gpu": np_gpu, "particles_total": np_global, "deposit": args.deposit,
-                       "storage": "store-full (128 B per particle-tau across the intra-step barrier)",
+                       "storage": ("store-full (128 B per particle-tau across the intra-step barrier)" if storage == "full" else
+                                   "hybrid (16 B per particle-tau across the barrier, predictor recomputed in phase B)"),
                        "l2": f"inputs larger than L2: {s.device_bytes / 1e9:.1f} GB of particle state per GPU streamed every step",
                        "parallelism": f"particle shards x{world}, allreduce(rho) over NCCL" if world > 1 else "single GPU"},
             "e2e": e2e,

@@ -175,6 +175,30 @@ def test_device_loaders_and_diagnostics():
         assert x[0].min() >= 0 and x[0].max() <= DIMX
 
 
+@pytest.mark.parametrize("ntau,nx,ny,eps", [(16, 128, 64, 0.1), (32, 128, 128, 0.1), (16, 128, 64, 1e-3)])
+def test_hybrid_storage_vs_oracle_and_store_full(corc, ntau, nx, ny, eps):
+    """UAPIC_STORE_HYBRID keeps 16 B per particle-tau (E at the tau samples) across the barrier and recomputes the
+    predictor in phase B: same answer as the oracle, and as the store-full layout to round-off."""
+    npart, nstep = 6000, 4
+    om, x0, v0 = seeded_load(npart, nx, ny, seed=71)
+    mesh = ub.Mesh(0, DIMX, nx, 0, DIMY, ny)
+    w = DIMX * DIMY / npart
+    xo, vo = x0.copy(order="F"), v0.copy(order="F")
+    eno, _, _, _ = corc.run_bupdate(om, ntau, eps, DT, nstep, xo, vo, w)
+    res = {}
+    for name, mode in (("full", ub.STORE_FULL), ("hybrid", ub.STORE_HYBRID)):
+        with ub.Session(mesh, ntau, eps, DT, npart, weight=w, storage_mode=mode) as s:
+            s.upload_particles(x0, v0)
+            s.init_fields()
+            s.step(nstep)
+            s.synchronize()
+            x, v = s.download_particles()
+            res[name] = (x, v, s.energy_history(), s.device_bytes)
+    _compare(res["hybrid"][0], res["hybrid"][1], res["hybrid"][2], xo, vo, eno, eps)
+    _compare(res["hybrid"][0], res["hybrid"][1], res["hybrid"][2], res["full"][0], res["full"][1], res["full"][2], eps, tol=1e-11)
+    assert res["hybrid"][3] < res["full"][3] * 0.3          # 16 B instead of 128 B per particle-tau
+
+
 def test_session_state_errors():
     mesh = ub.Mesh(0, DIMX, 32, 0, DIMY, 16)
     with ub.Session(mesh, 16, 0.1, DT, 100) as s:

@@ -480,7 +480,7 @@ PhaseParams session_params(uapic_session *s) {
     p.m = s->m; p.eps = s->cfg.eps; p.dt = s->cfg.dt; p.weight = s->cfg.weight; p.np = s->cfg.nbpart;
     p.wrap = s->cfg.wrap; p.ntau = s->cfg.ntau;
     p.x = s->x.as<double2>(); p.v = s->v.as<double2>(); p.ep = s->ep.as<double2>();
-    p.emesh = s->emesh.as<double2>(); p.ehalo = s->ehalo.as<double2>(); p.store = s->store.as<double2>(); p.tb = s->tb.as<double2>();
+    p.emesh = s->emesh.as<double2>(); p.ehalo = s->ehalo.as<double2>(); p.store = s->store.as<double2>(); p.etstore = s->store.as<double>(); p.hybrid = s->cfg.storage_mode == UAPIC_STORE_HYBRID; p.tb = s->tb.as<double2>();
     p.rho = s->acc;
     return p;
 }
@@ -497,7 +497,7 @@ int uapic_session_create(const uapic_config_t *cfg, uapic_session_t **out) {
     if (cfg->nbpart < 0) return fail(UAPIC_EINVAL, "nbpart must be >= 0");
     if (!(cfg->eps > 0) || !(cfg->dt > 0) || !(cfg->weight > 0)) return fail(UAPIC_EINVAL, "eps, dt and weight must be positive");
     if (cfg->scheme != UAPIC_SCHEME_M6) return fail(UAPIC_EUNSUPPORTED, "only UAPIC_SCHEME_M6 is implemented in the session path");
-    if (cfg->storage_mode != UAPIC_STORE_FULL) return fail(UAPIC_EUNSUPPORTED, "only UAPIC_STORE_FULL is implemented");
+    if (cfg->storage_mode != UAPIC_STORE_FULL && cfg->storage_mode != UAPIC_STORE_HYBRID) return fail(UAPIC_EINVAL, "unknown storage_mode %d", cfg->storage_mode);
     if (cfg->wrap != UAPIC_WRAP_FORTRAN && cfg->wrap != UAPIC_WRAP_JULIA) return fail(UAPIC_EINVAL, "unknown wrap %d", cfg->wrap);
     if (!poisson_size_supported(cfg->mesh.nx) || !poisson_size_supported(cfg->mesh.ny) || cfg->mesh.nx < 4 || cfg->mesh.ny < 4)
         return fail(UAPIC_EUNSUPPORTED, "session mesh %d x %d unsupported (need 4 <= n, powers of two <= 1024 or any n <= 512)", cfg->mesh.nx, cfg->mesh.ny);
@@ -523,7 +523,8 @@ int uapic_session_create(const uapic_config_t *cfg, uapic_session_t **out) {
     if (!rc) rc = session_alloc(s, s->v, 16 * (np ? np : 1));
     if (!rc) rc = session_alloc(s, s->ep, 16 * (np ? np : 1));
     if (!rc) rc = session_alloc(s, s->tb, 16 * (np ? np : 1));
-    if (!rc) rc = session_alloc(s, s->store, 16 * 8 * N * (np ? np : 1));
+    // store-full: 128 B per particle-tau; hybrid: 16 B per particle-tau (E at the tau samples)
+    if (!rc) rc = session_alloc(s, s->store, (cfg->storage_mode == UAPIC_STORE_HYBRID ? 16 : 128) * N * (np ? np : 1));
     if (!rc) rc = session_alloc(s, s->raw, 8 * nrho);
     if (!rc) rc = session_alloc(s, s->rho, 8 * nrho);
     if (!rc) rc = session_alloc(s, s->emesh, 16 * nrho);

@@ -276,125 +276,141 @@ struct FusedParams {
 };
 
 // =================================================================================================
-template <int N>
+// The predictor of one particle (N lanes): preparation -> [gather E] -> compute_f -> ua_step1 for x and y.
+//   ua_steps.F90:49-113, interpolation_m6.F90:83-189, ua_steps.F90:160-195, :215-234
+// GATHER = true : E at the tau samples is interpolated from the mesh and returned in et1, et2 (phase A)
+// GATHER = false: et1, et2 are inputs (hybrid storage: phase B recomputes the predictor from x, v, e and the stored et)
+// out: b, t; o4 = predicted xt1, xt2, yt1, yt2 in the time domain; fhat_x, fhat_y (normalised, lane order);
+//      pos1, pos2 = predicted position at tau* = t/eps (compute_rho_m6.F90:74-87)
+template <int N, bool GATHER>
+DEVINL void predictor(const FusedLane<N> &L, const FusedParams &F, double x1, double x2, double vx, double vy, double ex, double ey,
+                      double &et1, double &et2, double &b, double &t, cd (&o4)[4], cd &fx1, cd &fx2, cd &fy1, cd &fy2,
+                      double &pos1, double &pos2) {
+    const PhaseParams &P = F.p;
+    const double eps = P.eps, inv_eps = F.inv_eps;
+    const double ct = L.T.ct, st = L.T.st;
+    const int k = L.T.k;
+
+    // ---- preparation (ua_steps.F90:49-113) ----
+    b = bfield(x1, x2);                                               // :54
+    t = P.dt * b;                                                     // :55
+    const double rb = 1.0 / b;
+    const double vxb = vx * rb, vyb = vy * rb;                        // :73-74
+    const double xt1 = x1 + eps * (st * vxb - ct * vyb) + eps * vyb;  // :78-81
+    const double xt2 = x2 + eps * (st * vyb + ct * vxb) - eps * vxb;  // :79-82
+    const double interv = (1.0 + 0.5 * sin(xt1) * sin(xt2) - b) * inv_eps;   // :87
+    const double exb = ((ct * vy - st * vx) * interv + ex) * rb;      // :89
+    const double eyb = ((-ct * vx - st * vy) * interv + ey) * rb;     // :90
+    cd z[1] = {mk(ct * exb - st * eyb, st * exb + ct * eyb)};          // r1 + i r2   :92-93
+    fft_fwd_b<N, 1>(z, L);                                            // :97-98 (both real signals at once)
+    z[0] = rmul(L.s1, z[0]);
+    const cd wn = shfl_idx<N>(z[0], L.src_neg);
+    cd c[2];   // filtered coefficients, :100-103 ; slot 0 keeps the unnormalised sums
+    if (k == 0) {
+        c[0] = mk(z[0].re, 0.0); c[1] = mk(z[0].im, 0.0);
+    } else {
+        const double s = 0.5 * L.inv_lN();
+        c[0] = mk(s * (z[0].im - wn.im), -s * (z[0].re + wn.re));
+        c[1] = mk(-s * (z[0].re - wn.re), -s * (z[0].im + wn.im));
+    }
+    const double r10sum = group_bcast0<N>(c[0].re), r20sum = group_bcast0<N>(c[1].re);
+    cd rp[2] = {rmul(L.s1, c[0]), rmul(L.s1, c[1])};
+    fft_bwd_b<N, 2>(rp, L);                                           // :105-106
+    const cd r10 = group_bcast0<N>(rp[0]), r20 = group_bcast0<N>(rp[1]);
+    const cd yt1 = mk(vx + (rp[0].re - r10.re) * eps, (rp[0].im - r10.im) * eps);   // :109
+    const cd yt2 = mk(vy + (rp[1].re - r20.re) * eps, (rp[1].im - r20.im) * eps);   // :110
+    // FFT(yt)/N without a transform: eps*c_k for k != 0, mean value for k = 0
+    cd yh1, yh2;
+    if (k == 0) {
+        yh1 = mk(vx - eps * (r10.re - r10sum), -eps * r10.im);
+        yh2 = mk(vy - eps * (r20.re - r20sum), -eps * r20.im);
+    } else {
+        yh1 = rmul(eps, c[0]); yh2 = rmul(eps, c[1]);
+    }
+
+    // ---- gather E at the tau samples (interpolation_m6.F90:83-189) ----
+    if (GATHER) {
+        double xw, yw;
+        const Cell cell = cell_fast(P.m, F.f, xt1, xt2, P.wrap, xw, yw);
+        gather_fast(P.m, P.ehalo, cell, et1, et2);
+    }
+
+    // ---- compute_f (ua_steps.F90:160-195) ----
+    fx_from_yhat<N>(L, rb, yh1, yh2, fx1, fx2);
+    cd fy[2];
+    fy_time<N>(L, rb, interv, yt1, yt2, et1, et2, fy[0], fy[1]);
+    fft_fwd_b<N, 2>(fy, L);
+    fy1 = rmul(L.sN, fy[0]); fy2 = rmul(L.sN, fy[1]);
+
+    // ---- ua_step1 for x and y (ua_steps.F90:215-234) ----
+    const cd elt = elt_minus<N>(L.T, t, eps);                         // :224
+    cd pl, ql;
+    pl_ql_fast<N>(L, t, eps, elt, pl, ql);
+    // FFT(xt)/N of the first-order profile: modes 0 and +-1 only
+    cd xh1 = mk(0.0, 0.0), xh2 = mk(0.0, 0.0);
+    {
+        const double he = 0.5 * eps;
+        if (k == 0) { xh1 = mk(x1 + eps * vyb, 0.0); xh2 = mk(x2 - eps * vxb, 0.0); }
+        if (k == (1 & (N - 1)) && N > 1 && k != 0) { xh1 = mk(xh1.re - he * vyb, xh1.im - he * vxb); xh2 = mk(xh2.re + he * vxb, xh2.im - he * vyb); }
+        if (k == N - 1 && k != 0) { xh1 = mk(xh1.re - he * vyb, xh1.im + he * vxb); xh2 = mk(xh2.re + he * vxb, xh2.im + he * vyb); }
+    }
+    // everything below is carried NEGATED ON ODD LANES (input convention of fft_bwd_b); the position sums are
+    // products of two such quantities, so they are unaffected
+    const cd elts = rmul(L.s1, elt), pls = rmul(L.s1, pl);
+    o4[0] = cfma(pls, fx1, cmul(elts, xh1));                          // :226
+    o4[1] = cfma(pls, fx2, cmul(elts, xh2));                          // :227
+    o4[2] = cfma(pls, fy1, cmul(elts, yh1));
+    o4[3] = cfma(pls, fy2, cmul(elts, yh2));
+    pos1 = group_sum<N>(dot_conj(o4[0], elts));
+    pos2 = group_sum<N>(dot_conj(o4[1], elts));
+    fft_bwd_b<N, 4>(o4, L);                                           // :231-232
+}
+
+// =================================================================================================
+// HYB = false: store-full  -- 128 B per particle-tau cross the barrier (predicted xt, yt and fhat_x, fhat_y)
+// HYB = true : hybrid      --  16 B per particle-tau (et only); phase B recomputes the predictor
+template <int N, bool HYB>
 __global__ void __launch_bounds__(kPhaseBlock, kPhaseMinBlocks) k_phase_a(FusedParams F) {
     const PhaseParams &P = F.p;
     __shared__ double2 sm_tw[4 * 32];
     __shared__ double sm_inv[3 * 32];
     FusedLane<N> L; L.init(threadIdx.x & 31, sm_tw, sm_inv);
     WarpMap<N> W;
-    const double eps = P.eps, inv_eps = F.inv_eps;
-    const double ct = L.T.ct, st = L.T.st;
-    const int k = L.T.k;
     for (int64_t base = W.first; base < P.np; base += W.stride) {
         const int64_t kraw = base + W.g;
         const bool valid = kraw < P.np;
         const int64_t ip = valid ? kraw : P.np - 1;
         const double2 xx = P.x[ip], vv = P.v[ip], ee = P.ep[ip];
-        const double x1 = xx.x, x2 = xx.y, vx = vv.x, vy = vv.y;
-
-        // ---- preparation (ua_steps.F90:49-113) ----
-        const double b = bfield(x1, x2);                                  // :54
-        const double t = P.dt * b;                                        // :55
-        const double rb = 1.0 / b;
-        const double vxb = vx * rb, vyb = vy * rb;                        // :73-74
-        const double xt1 = x1 + eps * (st * vxb - ct * vyb) + eps * vyb;  // :78-81
-        const double xt2 = x2 + eps * (st * vyb + ct * vxb) - eps * vxb;  // :79-82
-        const double interv = (1.0 + 0.5 * sin(xt1) * sin(xt2) - b) * inv_eps;   // :87
-        const double exb = ((ct * vy - st * vx) * interv + ee.x) * rb;    // :89
-        const double eyb = ((-ct * vx - st * vy) * interv + ee.y) * rb;   // :90
-        cd z[1] = {mk(ct * exb - st * eyb, st * exb + ct * eyb)};          // r1 + i r2   :92-93
-        fft_fwd_b<N, 1>(z, L);                                            // :97-98 (both real signals at once)
-        z[0] = rmul(L.s1, z[0]);
-        const cd wn = shfl_idx<N>(z[0], L.src_neg);
-        cd c[2];   // filtered coefficients, :100-103 ; slot 0 keeps the unnormalised sums
-        if (k == 0) {
-            c[0] = mk(z[0].re, 0.0); c[1] = mk(z[0].im, 0.0);
-        } else {
-            const double s = 0.5 * L.inv_lN();
-            c[0] = mk(s * (z[0].im - wn.im), -s * (z[0].re + wn.re));
-            c[1] = mk(-s * (z[0].re - wn.re), -s * (z[0].im + wn.im));
-        }
-        const double r10sum = group_bcast0<N>(c[0].re), r20sum = group_bcast0<N>(c[1].re);
-        cd rp[2] = {rmul(L.s1, c[0]), rmul(L.s1, c[1])};
-        fft_bwd_b<N, 2>(rp, L);                                           // :105-106
-        const cd r10 = group_bcast0<N>(rp[0]), r20 = group_bcast0<N>(rp[1]);
-        const cd yt1 = mk(vx + (rp[0].re - r10.re) * eps, (rp[0].im - r10.im) * eps);   // :109
-        const cd yt2 = mk(vy + (rp[1].re - r20.re) * eps, (rp[1].im - r20.im) * eps);   // :110
-        // FFT(yt)/N without a transform: eps*c_k for k != 0, mean value for k = 0
-        cd yh1, yh2;
-        if (k == 0) {
-            yh1 = mk(vx - eps * (r10.re - r10sum), -eps * r10.im);
-            yh2 = mk(vy - eps * (r20.re - r20sum), -eps * r20.im);
-        } else {
-            yh1 = rmul(eps, c[0]); yh2 = rmul(eps, c[1]);
-        }
-
-        // ---- gather E at the tau samples (interpolation_m6.F90:83-189) ----
-        double et1, et2;
-        {
-            double xw, yw;
-            const Cell cell = cell_fast(P.m, F.f, xt1, xt2, P.wrap, xw, yw);
-            gather_fast(P.m, P.ehalo, cell, et1, et2);
-        }
-
-        // ---- compute_f (ua_steps.F90:160-195) ----
-        cd fx1, fx2;
-        fx_from_yhat<N>(L, rb, yh1, yh2, fx1, fx2);
-        cd fy[2];
-        fy_time<N>(L, rb, interv, yt1, yt2, et1, et2, fy[0], fy[1]);
-        fft_fwd_b<N, 2>(fy, L);
-        fy[0] = rmul(L.sN, fy[0]); fy[1] = rmul(L.sN, fy[1]);
-
-        // ---- ua_step1 for x and y (ua_steps.F90:215-234) ----
-        const cd elt = elt_minus<N>(L.T, t, eps);                         // :224
-        cd pl, ql;
-        pl_ql_fast<N>(L, t, eps, elt, pl, ql);
-        // FFT(xt)/N of the first-order profile: modes 0 and +-1 only
-        cd xh1 = mk(0.0, 0.0), xh2 = mk(0.0, 0.0);
-        {
-            const double he = 0.5 * eps;
-            if (k == 0) { xh1 = mk(x1 + eps * vyb, 0.0); xh2 = mk(x2 - eps * vxb, 0.0); }
-            if (k == (1 & (N - 1)) && N > 1 && k != 0) { xh1 = mk(xh1.re - he * vyb, xh1.im - he * vxb); xh2 = mk(xh2.re + he * vxb, xh2.im - he * vyb); }
-            if (k == N - 1 && k != 0) { xh1 = mk(xh1.re - he * vyb, xh1.im + he * vxb); xh2 = mk(xh2.re + he * vxb, xh2.im + he * vyb); }
-        }
-        // everything below is carried NEGATED ON ODD LANES (input convention of fft_bwd_b); the position sums are
-        // products of two such quantities, so they are unaffected
-        const cd elts = rmul(L.s1, elt), pls = rmul(L.s1, pl);
-        cd o4[4];
-        o4[0] = cfma(pls, fx1, cmul(elts, xh1));                          // :226
-        o4[1] = cfma(pls, fx2, cmul(elts, xh2));                          // :227
-        o4[2] = cfma(pls, fy[0], cmul(elts, yh1));
-        o4[3] = cfma(pls, fy[1], cmul(elts, yh2));
-
-        // ---- predictor deposit: position at tau* = t/eps (compute_rho_m6.F90:74-87) ----
-        const double pos1 = group_sum<N>(dot_conj(o4[0], elts));
-        const double pos2 = group_sum<N>(dot_conj(o4[1], elts));
-
-        fft_bwd_b<N, 4>(o4, L);                                           // :231-232
+        double et1, et2, b, t, pos1, pos2;
+        cd o4[4], fx1, fx2, fy1, fy2;
+        predictor<N, true>(L, F, xx.x, xx.y, vv.x, vv.y, ee.x, ee.y, et1, et2, b, t, o4, fx1, fx2, fy1, fy2, pos1, pos2);
 
         if (valid) {
-            double2 *s = P.store + (size_t)ip * 8 * N + L.T.j;
-            s[0 * N] = make_double2(o4[0].re, o4[0].im);
-            s[1 * N] = make_double2(o4[1].re, o4[1].im);
-            s[2 * N] = make_double2(o4[2].re, o4[2].im);
-            s[3 * N] = make_double2(o4[3].re, o4[3].im);
-            s[4 * N] = make_double2(fx1.re, fx1.im);
-            s[5 * N] = make_double2(fx2.re, fx2.im);
-            s[6 * N] = make_double2(fy[0].re, fy[0].im);
-            s[7 * N] = make_double2(fy[1].re, fy[1].im);
-            if (L.T.j == 0) P.tb[ip] = make_double2(t, b);
+            if (HYB) {
+                double *e = P.etstore + (size_t)ip * 2 * N + L.T.j;
+                e[0] = et1; e[N] = et2;
+            } else {
+                double2 *s = P.store + (size_t)ip * 8 * N + L.T.j;
+                s[0 * N] = make_double2(o4[0].re, o4[0].im);
+                s[1 * N] = make_double2(o4[1].re, o4[1].im);
+                s[2 * N] = make_double2(o4[2].re, o4[2].im);
+                s[3 * N] = make_double2(o4[3].re, o4[3].im);
+                s[4 * N] = make_double2(fx1.re, fx1.im);
+                s[5 * N] = make_double2(fx2.re, fx2.im);
+                s[6 * N] = make_double2(fy1.re, fy1.im);
+                s[7 * N] = make_double2(fy2.re, fy2.im);
+                if (L.T.j == 0) P.tb[ip] = make_double2(t, b);
+            }
         }
-        {
-            double xw, yw;
-            const Cell cell = cell_fast(P.m, F.f, pos1, pos2, P.wrap, xw, yw);
-            deposit_coop<N>(P.m, P.rho, cell, P.weight, L.T.j, valid);
-        }
+        // ---- predictor deposit (compute_rho_m6.F90:89-187) ----
+        double xw, yw;
+        const Cell cell = cell_fast(P.m, F.f, pos1, pos2, P.wrap, xw, yw);
+        deposit_coop<N>(P.m, P.rho, cell, P.weight, L.T.j, valid);
     }
 }
 
 // =================================================================================================
-template <int N>
+template <int N, bool HYB>
 __global__ void __launch_bounds__(kPhaseBlock, kPhaseMinBlocks) k_phase_b(FusedParams F) {
     const PhaseParams &P = F.p;
     __shared__ double2 sm_tw[4 * 32];
@@ -406,14 +422,26 @@ __global__ void __launch_bounds__(kPhaseBlock, kPhaseMinBlocks) k_phase_b(FusedP
         const int64_t kraw = base + W.g;
         const bool valid = kraw < P.np;
         const int64_t ip = valid ? kraw : P.np - 1;
-        const double2 *s = P.store + (size_t)ip * 8 * N + L.T.j;
-        const double2 tb = P.tb[ip];
-        const double t = tb.x, b = tb.y, rb = 1.0 / b;
-        cd f6[6];
+        double t, b;
+        cd f6[6], fx1, fx2, fy1, fy2;
+        if (HYB) {
+            const double2 xx = P.x[ip], vv = P.v[ip], ee = P.ep[ip];
+            const double *e = P.etstore + (size_t)ip * 2 * N + L.T.j;
+            double et1 = e[0], et2 = e[N], p1, p2;
+            cd o4[4];
+            predictor<N, false>(L, F, xx.x, xx.y, vv.x, vv.y, ee.x, ee.y, et1, et2, b, t, o4, fx1, fx2, fy1, fy2, p1, p2);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) f6[q] = mk(s[q * N].x, s[q * N].y);          // predicted xt1, xt2, yt1, yt2
-        const cd fx1 = mk(s[4 * N].x, s[4 * N].y), fx2 = mk(s[5 * N].x, s[5 * N].y);
-        const cd fy1 = mk(s[6 * N].x, s[6 * N].y), fy2 = mk(s[7 * N].x, s[7 * N].y);
+            for (int q = 0; q < 4; ++q) f6[q] = o4[q];
+        } else {
+            const double2 *s = P.store + (size_t)ip * 8 * N + L.T.j;
+            const double2 tb = P.tb[ip];
+            t = tb.x; b = tb.y;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) f6[q] = mk(s[q * N].x, s[q * N].y);          // predicted xt1, xt2, yt1, yt2
+            fx1 = mk(s[4 * N].x, s[4 * N].y); fx2 = mk(s[5 * N].x, s[5 * N].y);
+            fy1 = mk(s[6 * N].x, s[6 * N].y); fy2 = mk(s[7 * N].x, s[7 * N].y);
+        }
+        const double rb = 1.0 / b;
 
         // ---- gather E_new at the predicted samples, g in the time domain (ua_steps.F90:160-185) ----
         double et1, et2;
@@ -493,7 +521,8 @@ cudaError_t launch_phase_a(const LaunchCtx &c, const PhaseParams &p) {
     if (p.np <= 0) return cudaSuccess;
     if (p.m.nx < 4 || p.m.ny < 4) return cudaErrorInvalidValue;
     const FusedParams F = make_fused(p);
-    UAPIC_DISPATCH_N(p.ntau, (k_phase_a<N><<<phase_grid(c, p.np, N), kPhaseBlock, 0, c.stream>>>(F)));
+    if (p.hybrid) { UAPIC_DISPATCH_N(p.ntau, (k_phase_a<N, true><<<phase_grid(c, p.np, N), kPhaseBlock, 0, c.stream>>>(F))); }
+    else { UAPIC_DISPATCH_N(p.ntau, (k_phase_a<N, false><<<phase_grid(c, p.np, N), kPhaseBlock, 0, c.stream>>>(F))); }
     if (c.launches) *c.launches += 1;
     return cudaGetLastError();
 }
@@ -502,7 +531,8 @@ cudaError_t launch_phase_b(const LaunchCtx &c, const PhaseParams &p) {
     if (p.np <= 0) return cudaSuccess;
     if (p.m.nx < 4 || p.m.ny < 4) return cudaErrorInvalidValue;
     const FusedParams F = make_fused(p);
-    UAPIC_DISPATCH_N(p.ntau, (k_phase_b<N><<<phase_grid(c, p.np, N), kPhaseBlock, 0, c.stream>>>(F)));
+    if (p.hybrid) { UAPIC_DISPATCH_N(p.ntau, (k_phase_b<N, true><<<phase_grid(c, p.np, N), kPhaseBlock, 0, c.stream>>>(F))); }
+    else { UAPIC_DISPATCH_N(p.ntau, (k_phase_b<N, false><<<phase_grid(c, p.np, N), kPhaseBlock, 0, c.stream>>>(F))); }
     if (c.launches) *c.launches += 1;
     return cudaGetLastError();
 }

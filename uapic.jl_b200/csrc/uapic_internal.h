@@ -64,7 +64,9 @@ struct PhaseParams {
     const double2 *ep;     // (2,np): particles.e, frozen after init
     const double2 *emesh;  // (2,nx+1,ny+1)
     const double2 *ehalo;  // periodic halo copy of emesh: (nx+6) x (ny+6) nodes, node (i,j) at [(i+2) + (nx+6)*(j+2)]
-    double2 *store;        // np * 8 * ntau complex: what crosses the intra-step barrier
+    double2 *store;        // store-full: np * 8 * ntau complex, what crosses the intra-step barrier
+    double *etstore;       // hybrid: np * 2 * ntau doubles (E at the tau samples of the predictor)
+    int hybrid;
     double2 *tb;           // (t,b) per particle
     RhoAcc rho;
 };
