@@ -1,14 +1,14 @@
 #!/usr/bin/env python
 """bench.py -- throughput of the UA-PIC time step (BASELINE.json metric: particle-tau updates per second).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload config3|config2|config5] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload config3|config3-shard|config2|config5] [--impl b200|reference]
 
 One process per GPU (the driver launches N>1 through torch.distributed.run).  A "step" is one full UA step
 (fortran/bupdate.F90:97-123: predictor + corrector, two deposits, two Poisson solves) over every particle-tau
-sample of the workload.  Default workload = the per-GPU shard of BASELINE config 3 (4D Landau load, ntau = 32,
-128 x 128 mesh, M6): 12.5e6 particles per GPU, so that 8 GPUs run exactly the 1e8-particle case the metric is
-quoted on (weak scaling).  1e8 particles do not fit one GPU in the store-full layout (410 GB of barrier-crossing
-state), hence the shard at N = 1.
+sample of the workload.  Default workload = BASELINE config 3, the case the metric is quoted on: 4D Landau load,
+1e8 particles, ntau = 32, 128 x 128 mesh, M6 -- the SAME 1e8-particle problem at every N (strong scaling).
+--storage auto keeps 128 B per particle-tau across the intra-step barrier when the shard fits HBM (N >= 4) and
+switches to the hybrid layout (16 B per particle-tau, predictor recomputed in phase B) when it does not (N = 1, 2).
 
 Prints ONE JSON line (rank 0).  `value` times K steps with all state resident in HBM; `e2e` times the same step
 through the host-facing API with the particles living in pinned HOST memory (x, v, e copied up, x, v and the energy
@@ -34,12 +34,14 @@ DT = np.pi / 16          # bupdate.F90:66
 EPS = 0.1                # bupdate.F90:18
 
 WORKLOADS = {
-    # name: (load, ntau, nx, ny, particles per GPU, description)
-    "config3": ("landau", 32, 128, 128, 12_500_000, "BASELINE config 3 shard: 4D Landau load, ntau=32, 128x128, M6, 12.5e6 particles/GPU (1e8 at 8 GPUs)"),
-    "config2": ("plasma", 16, 128, 64, 1_000_000, "BASELINE config 2: bupdate case, M6, 1e6 particles, ntau=16, 128x64"),
-    "config5": ("landau", 32, 256, 256, 15_625_000, "BASELINE config 5 weak point: 5e8 particle-tau samples/GPU, ntau=32, 256x256, M6"),
-    # the literal config 3 on ONE GPU: needs --storage hybrid (store-full would take 410 GB)
-    "config3-1gpu": ("landau", 32, 128, 128, 100_000_000, "BASELINE config 3 on one GPU: 4D Landau load, 1e8 particles, ntau=32, 128x128, M6 (hybrid storage)"),
+    # name: (load, ntau, nx, ny, particles, "total" (strong scaling) | "per_gpu" (weak scaling), description)
+    "config3": ("landau", 32, 128, 128, 100_000_000, "total",
+                "BASELINE config 3: 4D Landau load, 1e8 particles, ntau=32, 128x128 mesh, M6, strong scaling over the GPUs"),
+    "config3-shard": ("landau", 32, 128, 128, 12_500_000, "per_gpu",
+                      "per-GPU shard of BASELINE config 3 (12.5e6 particles/GPU = 1e8 at 8 GPUs), weak scaling"),
+    "config2": ("plasma", 16, 128, 64, 1_000_000, "total", "BASELINE config 2: bupdate case, M6, 1e6 particles, ntau=16, 128x64"),
+    "config5": ("landau", 32, 256, 256, 15_625_000, "per_gpu",
+                "BASELINE config 5 weak point: 5e8 particle-tau samples/GPU, ntau=32, 256x256, M6"),
 }
 
 
@@ -104,7 +106,7 @@ class ClockSampler:
 def cpu_oracle_rate(workload, steps, warmup, sample_particles, threads=None, faithful=True):
     """particle-tau updates/s of the CPU oracle (port of the Fortran reference) on a bounded sample of the workload"""
     import oracle
-    load, ntau, nx, ny, _, _ = WORKLOADS[workload]
+    load, ntau, nx, ny = WORKLOADS[workload][:4]
     orc = oracle.corc()
     nthreads = threads or orc.max_threads()
     orc.set_threads(nthreads)
@@ -140,13 +142,13 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    load, ntau, nx, ny, np_gpu, desc = WORKLOADS[args.workload]
+    load, ntau, nx, ny, _, mode, desc = WORKLOADS[args.workload]
     sample = args.cpu_sample or 200_000
     rate, ms, threads = cpu_oracle_rate(args.workload, args.steps, args.warmup, sample)
     line = {
         "impl": "reference", "metric": "particle-tau updates/sec", "value": rate, "unit": "particle-tau updates/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "scaling": "strong" if mode == "total" else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": desc, "ntau": ntau, "mesh": [nx, ny], "eps": EPS, "scheme": "M6",
                    "note": "CPU port timed on a bounded sample; cost is linear in the particle count"},
         "cpu_baseline": {"value": rate, "unit": "particle-tau updates/s", "cores": threads, "kind": "port",
@@ -192,11 +194,12 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    load, ntau, nx, ny, np_gpu, desc = WORKLOADS[args.workload]
+    load, ntau, nx, ny, np_cfg, mode, desc = WORKLOADS[args.workload]
     if args.particles_per_gpu:
-        np_gpu = args.particles_per_gpu
-        desc += f" [particles/GPU overridden to {np_gpu}]"
-    np_global = np_gpu * world
+        mode, np_cfg = "per_gpu", args.particles_per_gpu
+        desc += f" [overridden: {np_cfg} particles per GPU, weak scaling]"
+    np_global = np_cfg * world if mode == "per_gpu" else np_cfg
+    np_gpu = np_global // world
     mesh = ub.Mesh(0, DIMX, nx, 0, DIMY, ny)
     lo, hi = ub.dist.shard_range(np_global, rank, world)
     stream = torch.cuda.current_stream().cuda_stream
@@ -289,7 +292,8 @@ def main():
         b_alg = (256 if storage == "full" else 32) + 112 / ntau
         line = {
             "metric": "particle-tau updates/sec", "value": value, "unit": "particle-tau updates/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "strong" if mode == "total" else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": desc, "load": load, "ntau": ntau, "mesh": [nx, ny], "eps": EPS, "dt": DT, "scheme": "M6",
                        "particles_per_gpu": np_gpu, "particles_total": np_global, "deposit": args.deposit,
