@@ -51,6 +51,10 @@ extern "C" {
 /* what crosses the intra-step barrier */
 #define UAPIC_STORE_FULL   0    /* 128 B per particle-tau kept in HBM between predictor and corrector */
 #define UAPIC_STORE_HYBRID 1    /* 16 B per particle-tau (E at the tau samples); predictor recomputed */
+/* one-pass modes (ntau = 8, 16, 32): the corrector deposit does not depend on the predictor field, so both deposits of a
+   step come out of ONE kernel and one field barrier per step remains; compute_v needs no tau-FFT */
+#define UAPIC_STORE_ONEPASS      2   /* 72 B per particle-tau: Re xt_pred, yt_pred, W_n, interv */
+#define UAPIC_STORE_ONEPASS_LEAN 3   /* 48 B per particle-tau: Re xt_pred, yt_pred; W_n and interv recomputed */
 
 typedef struct uapic_mesh {
     double  xmin, xmax, ymin, ymax;   /* src/meshfields.jl:5-12, fortran/meshfields.F90:7-14 */

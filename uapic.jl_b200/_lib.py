@@ -16,7 +16,7 @@ OK = 0
 WRAP_FORTRAN, WRAP_JULIA = 0, 1
 DEPOSIT_FP64_ATOMIC, DEPOSIT_FIXED_POINT = 0, 1
 SCHEME_M6, SCHEME_CIC = 0, 1
-STORE_FULL, STORE_HYBRID = 0, 1
+STORE_FULL, STORE_HYBRID, STORE_ONEPASS, STORE_ONEPASS_LEAN = 0, 1, 2, 3
 
 ERROR_NAMES = {-1: "UAPIC_EINVAL", -2: "UAPIC_ENODEVICE", -3: "UAPIC_ECUDA", -4: "UAPIC_ENOMEM", -5: "UAPIC_ESTATE",
                -6: "UAPIC_EUNSUPPORTED"}

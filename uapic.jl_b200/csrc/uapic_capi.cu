@@ -422,7 +422,10 @@ struct uapic_session {
     int64_t launches = 0;
     int64_t np_global = 0;
     DevBuf x, v, ep, store, tb, raw, rho, emesh, ehalo, rk, ek, energy, sumv;
+    DevBuf rec, emesh_p, ehalo_p;     // one-pass modes: per-particle record, predictor field
     RhoAcc acc{};
+    RhoAcc acc_c{};                    // one-pass modes: corrector deposit mesh (second half of raw)
+    bool onepass = false;
     int64_t n_energy = 0, cap_energy = 0;
     uapic_allreduce_fn reduce = nullptr;
     void *reduce_ctx = nullptr;
@@ -459,20 +462,41 @@ int session_clear_raw(uapic_session *s) {
     return UAPIC_OK;
 }
 
-// raw deposits -> (sum over ranks) -> neutralised rho -> E, energy appended      compute_rho_m6.F90:191-200 + poisson_2d.f90:85-111
-int session_field_solve(uapic_session *s) {
+// sum the raw deposit mesh(es) over the ranks (the only exchange of the scheme)
+int session_reduce(uapic_session *s, int nmesh) {
     if (s->reduce) {
-        const int64_t n = (int64_t)s->m.ld * (s->m.ny + 1);
+        const int64_t n = (int64_t)s->m.ld * (s->m.ny + 1) * nmesh;
         int rc = s->reduce(s->reduce_ctx, s->raw.p, n, s->acc.i64 ? 1 : 0, (void *)s->lc.stream);
         if (rc) return fail(UAPIC_ECUDA, "allreduce callback failed with code %d", rc);
     }
-    CU(launch_rho_epilogue(s->lc, s->m, s->acc, s->rho.as<double>(), nullptr));
+    return UAPIC_OK;
+}
+
+// summed raw deposits -> neutralised rho -> E (+ halo copy), energy appended      compute_rho_m6.F90:191-200 + poisson_2d.f90:85-111
+int session_solve(uapic_session *s, const RhoAcc &acc, DevBuf &emesh, DevBuf &ehalo) {
+    CU(launch_rho_epilogue(s->lc, s->m, acc, s->rho.as<double>(), nullptr));
     if (s->n_energy >= s->cap_energy) return fail(UAPIC_ESTATE, "energy history full (%lld entries)", (long long)s->cap_energy);
     PoissonWork pw{s->rk.as<double2>(), s->ek.as<double2>()};
-    CU(launch_poisson(s->lc, s->m, pw, s->rho.as<double>(), s->emesh.as<double>(), s->energy.as<double>() + s->n_energy));
-    CU(launch_extend_emesh(s->lc, s->m, s->emesh.as<double>(), s->ehalo.as<double2>()));
+    CU(launch_poisson(s->lc, s->m, pw, s->rho.as<double>(), emesh.as<double>(), s->energy.as<double>() + s->n_energy));
+    CU(launch_extend_emesh(s->lc, s->m, emesh.as<double>(), ehalo.as<double2>()));
     s->n_energy++;
     return UAPIC_OK;
+}
+
+int session_field_solve(uapic_session *s) {
+    TRY(session_reduce(s, 1));
+    return session_solve(s, s->acc, s->emesh, s->ehalo);
+}
+
+OnepassParams session_onepass_params(uapic_session *s) {
+    OnepassParams p;
+    p.m = s->m; p.eps = s->cfg.eps; p.dt = s->cfg.dt; p.weight = s->cfg.weight; p.np = s->cfg.nbpart;
+    p.wrap = s->cfg.wrap; p.ntau = s->cfg.ntau; p.full = s->cfg.storage_mode == UAPIC_STORE_ONEPASS;
+    p.x = s->x.as<double2>(); p.v = s->v.as<double2>(); p.ep = s->ep.as<double2>();
+    p.ehalo = s->ehalo.as<double2>();
+    p.store = s->store.as<char>(); p.rec = s->rec.as<double>();
+    p.rho_p = s->acc; p.rho_c = s->acc_c;
+    return p;
 }
 
 PhaseParams session_params(uapic_session *s) {
@@ -497,7 +521,9 @@ int uapic_session_create(const uapic_config_t *cfg, uapic_session_t **out) {
     if (cfg->nbpart < 0) return fail(UAPIC_EINVAL, "nbpart must be >= 0");
     if (!(cfg->eps > 0) || !(cfg->dt > 0) || !(cfg->weight > 0)) return fail(UAPIC_EINVAL, "eps, dt and weight must be positive");
     if (cfg->scheme != UAPIC_SCHEME_M6) return fail(UAPIC_EUNSUPPORTED, "only UAPIC_SCHEME_M6 is implemented in the session path");
-    if (cfg->storage_mode != UAPIC_STORE_FULL && cfg->storage_mode != UAPIC_STORE_HYBRID) return fail(UAPIC_EINVAL, "unknown storage_mode %d", cfg->storage_mode);
+    const bool onepass = cfg->storage_mode == UAPIC_STORE_ONEPASS || cfg->storage_mode == UAPIC_STORE_ONEPASS_LEAN;
+    if (cfg->storage_mode != UAPIC_STORE_FULL && cfg->storage_mode != UAPIC_STORE_HYBRID && !onepass) return fail(UAPIC_EINVAL, "unknown storage_mode %d", cfg->storage_mode);
+    if (onepass && !onepass_ntau_supported(cfg->ntau)) return fail(UAPIC_EUNSUPPORTED, "the one-pass storage modes need ntau = 8, 16 or 32 (got %d)", cfg->ntau);
     if (cfg->wrap != UAPIC_WRAP_FORTRAN && cfg->wrap != UAPIC_WRAP_JULIA) return fail(UAPIC_EINVAL, "unknown wrap %d", cfg->wrap);
     if (!poisson_size_supported(cfg->mesh.nx) || !poisson_size_supported(cfg->mesh.ny) || cfg->mesh.nx < 4 || cfg->mesh.ny < 4)
         return fail(UAPIC_EUNSUPPORTED, "session mesh %d x %d unsupported (need 4 <= n, powers of two <= 1024 or any n <= 512)", cfg->mesh.nx, cfg->mesh.ny);
@@ -523,9 +549,16 @@ int uapic_session_create(const uapic_config_t *cfg, uapic_session_t **out) {
     if (!rc) rc = session_alloc(s, s->v, 16 * (np ? np : 1));
     if (!rc) rc = session_alloc(s, s->ep, 16 * (np ? np : 1));
     if (!rc) rc = session_alloc(s, s->tb, 16 * (np ? np : 1));
-    // store-full: 128 B per particle-tau; hybrid: 16 B per particle-tau (E at the tau samples)
-    if (!rc) rc = session_alloc(s, s->store, (cfg->storage_mode == UAPIC_STORE_HYBRID ? 16 : 128) * N * (np ? np : 1));
-    if (!rc) rc = session_alloc(s, s->raw, 8 * nrho);
+    // store-full: 128 B per particle-tau; hybrid: 16 B (E at the tau samples); one-pass: 72 B / 48 B (lean)
+    s->onepass = onepass;
+    const size_t per_tau = onepass ? (cfg->storage_mode == UAPIC_STORE_ONEPASS ? 72 : 48) : (cfg->storage_mode == UAPIC_STORE_HYBRID ? 16 : 128);
+    if (!rc) rc = session_alloc(s, s->store, per_tau * N * (np ? np : 1));
+    if (!rc) rc = session_alloc(s, s->raw, 8 * nrho * (onepass ? 2 : 1));
+    if (onepass) {
+        if (!rc) rc = session_alloc(s, s->rec, 64 * (np ? np : 1));
+        if (!rc) rc = session_alloc(s, s->emesh_p, 16 * nrho);
+        if (!rc) rc = session_alloc(s, s->ehalo_p, 16 * ehalo_nodes(s->m));
+    }
     if (!rc) rc = session_alloc(s, s->rho, 8 * nrho);
     if (!rc) rc = session_alloc(s, s->emesh, 16 * nrho);
     if (!rc) rc = session_alloc(s, s->ehalo, 16 * ehalo_nodes(s->m));
@@ -536,8 +569,10 @@ int uapic_session_create(const uapic_config_t *cfg, uapic_session_t **out) {
     if (rc) { delete s; return rc; }
     if (cfg->deposit_mode == UAPIC_DEPOSIT_FIXED_POINT) {
         s->acc.f64 = nullptr; s->acc.i64 = s->raw.as<unsigned long long>(); s->acc.scale = fixed_point_scale(total_mass);
+        s->acc_c = s->acc; s->acc_c.i64 += nrho;
     } else if (cfg->deposit_mode == UAPIC_DEPOSIT_FP64_ATOMIC) {
         s->acc.f64 = s->raw.as<double>(); s->acc.i64 = nullptr; s->acc.scale = 1.0;
+        s->acc_c = s->acc; s->acc_c.f64 += nrho;
     } else {
         delete s;
         return fail(UAPIC_EINVAL, "unknown deposit_mode %d", cfg->deposit_mode);
@@ -647,6 +682,7 @@ int uapic_session_step(uapic_session_t *s, int nsteps) {
     if (nsteps < 0) return fail(UAPIC_EINVAL, "nsteps must be >= 0");
     TRY(session_bind(s));
     const PhaseParams p = session_params(s);
+    OnepassParams op = s->onepass ? session_onepass_params(s) : OnepassParams{};
     for (int it = 0; it < nsteps; ++it) {
         cudaEvent_t e4[4] = {nullptr, nullptr, nullptr, nullptr};
         if (s->timing) {
@@ -654,6 +690,21 @@ int uapic_session_step(uapic_session_t *s, int nsteps) {
             for (int q = 0; q < 4; ++q) { CU(cudaEventCreate(&e4[q])); s->ev.push_back(e4[q]); }
         }
         TRY(session_clear_raw(s));
+        if (s->onepass) {
+            // one field barrier per step: both deposits come out of the first kernel (uapic_onepass.cu)
+            if (s->timing) CU(cudaEventRecord(e4[0], s->lc.stream));
+            op.ehalo = s->ehalo.as<double2>();
+            CU(launch_onepass_a(s->lc, op));                               // bupdate.F90:97-106, :112-117 (x part)
+            if (s->timing) CU(cudaEventRecord(e4[1], s->lc.stream));
+            TRY(session_reduce(s, 2));
+            TRY(session_solve(s, s->acc, s->emesh_p, s->ehalo_p));         // :108  predictor field
+            TRY(session_solve(s, s->acc_c, s->emesh, s->ehalo));           // :119  field of the next step
+            if (s->timing) CU(cudaEventRecord(e4[2], s->lc.stream));
+            op.ehalo = s->ehalo_p.as<double2>();
+            CU(launch_onepass_b(s->lc, op));                               // :110-115 (y part), :123
+            if (s->timing) CU(cudaEventRecord(e4[3], s->lc.stream));
+            continue;
+        }
         if (s->timing) CU(cudaEventRecord(e4[0], s->lc.stream));
         CU(launch_phase_a(s->lc, p));          // bupdate.F90:97-106
         if (s->timing) CU(cudaEventRecord(e4[1], s->lc.stream));

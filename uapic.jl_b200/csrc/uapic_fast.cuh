@@ -1,0 +1,73 @@
+// uapic_fast.cuh -- reciprocal-based mesh helpers shared by the fused phase kernels (uapic_fused.cu) and the
+// one-pass kernels (uapic_onepass.cu): periodic cell lookup, wrap-free halo gather, branch-free M6 weights.
+#pragma once
+
+#include "uapic_device.cuh"
+
+namespace uapic {
+
+// ---- mesh access with reciprocals -------------------------------------------------------------------------
+struct MeshFast {
+    double inv_dx, inv_dy, inv_nx, inv_ny, inv_dimx, inv_dimy;
+};
+
+DEVINL Cell cell_fast(const MeshDev &m, const MeshFast &f, double x, double y, int wrap, double &xw, double &yw) {
+    double px, py;
+    if (wrap == kWrapJulia) {
+        const double xn = modulo_fast(x - m.xmin, m.dimx, f.inv_dimx);
+        const double yn = modulo_fast(y - m.ymin, m.dimy, f.inv_dimy);
+        px = xn * f.inv_dx; py = yn * f.inv_dy;
+        xw = xn + m.xmin; yw = yn + m.ymin;
+    } else {
+        px = modulo_fast(x * f.inv_dx, (double)m.nx, f.inv_nx);
+        py = modulo_fast(y * f.inv_dy, (double)m.ny, f.inv_ny);
+        xw = x; yw = y;
+    }
+    Cell c;
+    c.i = __double2int_rd(px); c.dpx = px - (double)c.i;
+    c.j = __double2int_rd(py); c.dpy = py - (double)c.j;
+    return c;
+}
+
+// i in [0,n], off in [-2,3], n >= 4: one conditional add and one conditional subtract replace the integer modulo.
+// The centre keeps the reference's unwrapped index (compute_rho_m6.F90:102-116).
+DEVINL int wrap_fast(int i, int off, int n) {
+    if (off == 0) return i;
+    int r = i + off;
+    r += (r < 0) ? n : 0;
+    r -= (r >= n) ? n : 0;
+    return r;
+}
+
+// separable M6 gather on the periodic halo copy of E: no index wrap, one base address per row and immediate offsets
+// for its 6 nodes; (ex,ey) pairs read as 16-byte words through the read-only path
+DEVINL void gather_fast(const MeshDev &m, const double2 *__restrict__ ehalo, const Cell &c, double &e1, double &e2) {
+    double cx[6], cy[6];
+    m6_weights_fast(c.dpx, cx);
+    m6_weights_fast(c.dpy, cy);
+    const int ldx = m.nx + 6;
+    const double2 *row = ehalo + (c.j * ldx + c.i);      // node (i-2, j-2)
+    double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+    for (int b = 0; b < 6; ++b) {
+        double r1 = 0.0, r2 = 0.0;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+            const double2 ev = __ldg(row + a);
+            r1 = fma(cx[a], ev.x, r1);
+            r2 = fma(cx[a], ev.y, r2);
+        }
+        s1 = fma(cy[b], r1, s1);
+        s2 = fma(cy[b], r2, s2);
+        row += ldx;
+    }
+    e1 = s1; e2 = s2;
+}
+
+// f_m6 without branches (q >= 0): the three pieces of compute_rho_m6.F90:33-41 are the same sum of truncated powers
+DEVINL double f_m6_branchless(double q) {
+    const double a = fmax(3.0 - q, 0.0), b = fmax(2.0 - q, 0.0), c = fmax(1.0 - q, 0.0);
+    return fma(15.0, pow5(c), fma(-6.0, pow5(b), pow5(a))) * (1.0 / 120.0);
+}
+
+}  // namespace uapic

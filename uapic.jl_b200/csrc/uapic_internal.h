@@ -73,6 +73,27 @@ struct PhaseParams {
 cudaError_t launch_phase_a(const LaunchCtx &c, const PhaseParams &p);
 cudaError_t launch_phase_b(const LaunchCtx &c, const PhaseParams &p);
 
+// ---- one-pass kernels (session path, one field barrier per step; uapic_onepass.cu) ------------------------------
+struct OnepassParams {
+    MeshDev m;
+    double eps, dt, weight;
+    int64_t np;
+    int wrap;
+    int ntau;              // 8, 16 or 32
+    int full;              // 1: 72 B per particle-tau (W_n and interv stored); 0: 48 B (phase B recomputes them)
+    double2 *x;            // (2,np): read and rewritten (corrector position) by A
+    double2 *v;            // (2,np): read by A, written by B
+    const double2 *ep;     // (2,np): particles.e, frozen after init
+    const double2 *ehalo;  // periodic halo copy of the field to gather: E_n for A, E_pred for B
+    char *store;           // np * onepass_store_bytes_per_particle(ntau, full)
+    double *rec;           // np * 8 doubles: t, b, 1/b, bracket sums (2), cos(t/eps), sin(t/eps), unused
+    RhoAcc rho_p, rho_c;   // raw accumulation meshes of the predictor and the corrector deposit (A only)
+};
+bool onepass_ntau_supported(int ntau);
+size_t onepass_store_bytes_per_particle(int ntau, int full);
+cudaError_t launch_onepass_a(const LaunchCtx &c, const OnepassParams &p);
+cudaError_t launch_onepass_b(const LaunchCtx &c, const OnepassParams &p);
+
 // ---- loaders / diagnostics --------------------------------------------------------------------------------------
 cudaError_t launch_generate(const LaunchCtx &c, const MeshDev &m, int kind, uint64_t seed, int64_t first, int64_t np,
                             int64_t np_global, double alpha, double kx, double *x, double *v);

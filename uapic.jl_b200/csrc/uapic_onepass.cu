@@ -1,0 +1,646 @@
+// uapic_onepass.cu -- "one-pass" kernels of the session path, sm_100a: ONE field barrier per UA step.
+//
+// Two exact identities of the reference's formulas (tests/onepass_algebra_np.py states and checks them in numpy):
+//   1. gx of the second compute_f is R(-tau) yt_pred / b (ua_steps.F90:174-175): independent of the predictor field.
+//      The corrected x coefficients elt*xf + pl*fx + ql*(gx-fx)/t (ua_steps.F90:260), the corrector deposit position
+//      (compute_rho_m6.F90:74-87) and hence rho_{n+1} are known before the predictor Poisson solve.
+//   2. only the tau* evaluation sum_k Yc_k exp(+i l_k t/eps) of the corrected y coefficients is used
+//      (ua_steps.F90:293-303) and it is linear in gy:
+//        sum_k (Yp_k + qt_k (Gy_k - Fy_k)) conj(elt_k) = [sum_k (Yp_k - qt_k Fy_k) conj(elt_k)] + sum_n gy(tau_n) W_n,
+//        qt = ql/t,  W_n = (1/N) sum_k qt_k conj(elt_k) exp(-i k tau_n).
+//
+//   k_onepass_a = preparation + gather(E_n) + compute_f + ua_step1 + BOTH deposit positions + both deposits
+//                 (ua_steps.F90:15-236, :252-265 for x, interpolation_m6.F90:40-191, compute_rho_m6.F90:47-189)
+//   k_onepass_b = gather(E_pred) + time-domain gy + compute_v           (ua_steps.F90:160-185, :274-307)
+//
+// What crosses the barrier, per particle-tau: Re xt_pred (2 doubles), yt_pred (2 complex) and, in the FULL layout, W_n
+// (1 complex) and interv (1 double): 72 B (FULL) or 48 B (LEAN: phase B recomputes W and interv) instead of 128 B.
+// Per particle: an 8-double record (t, b, 1/b, the two bracket sums, cos(t/eps), sin(t/eps)).
+//
+// Work mapping of phase A: a particle is spread over G = N/8 adjacent lanes, EIGHT tau samples per lane.
+//   time domain   : lane g, register s  <->  sample n = g + G*s
+//   Fourier domain: lane g, register k1 <->  mode   k = 8*kappa(g) + k1,   kappa = bit reversal of g in log2(G) bits
+// A length-N transform is an in-register 8-point FFT, a twiddle, and a G-point FFT across lanes whose twiddles are
+// +-1, +-i (no multiplications): 14.5 fp64 instructions and 2 shuffles per sample instead of 26 and 20 for the
+// one-sample-per-lane butterfly network of uapic_fused.cu; everything per particle (b, 1/b, sincos(t/eps)) is amortised
+// over 8 samples; exp(-i l t/eps) comes from a recurrence over the lane's 8 consecutive modes.
+// The M6 gathers run in the "lane = tau sample" layout (positions and fields are exchanged through shared memory), where
+// one load instruction touches the orbit of a single particle.
+#include "uapic_internal.h"
+#include "uapic_fast.cuh"
+
+namespace uapic {
+
+namespace {
+
+#ifndef UAPIC_OP_MINB_A
+#define UAPIC_OP_MINB_A 2
+#endif
+#ifndef UAPIC_OP_MINB_B
+#define UAPIC_OP_MINB_B 4
+#endif
+constexpr int kOpBlock = 128;                  // 4 warps per CTA
+constexpr int kOpWarps = kOpBlock / 32;
+constexpr int kRow = 36;                       // padded row (double2 units) of the per-warp exchange area: conflict-free
+constexpr int kTab = 96;                       // 3 tables of 32 double2
+constexpr int kWarpSmA = 8 * kRow + 4 * 32 + 16 * 32;   // exchange rows + interv stash + yhat stash (double2 units)
+constexpr int kWarpSmB = 8 * kRow;
+
+constexpr double kRsqrt2 = 0.70710678118654752440;
+
+// ---- 8-point FFT in registers, natural order in and out; SGN = -1 forward (exp(-i..)), +1 backward ---------------
+template <int SGN> DEVINL cd mul_i(cd a) { return SGN > 0 ? mk(-a.im, a.re) : mk(a.im, -a.re); }            // a * (SGN i)
+template <int SGN> DEVINL cd mul_w8_1(cd a) {                                                              // a * exp(SGN i pi/4)
+    return SGN > 0 ? mk((a.re - a.im) * kRsqrt2, (a.im + a.re) * kRsqrt2) : mk((a.re + a.im) * kRsqrt2, (a.im - a.re) * kRsqrt2);
+}
+template <int SGN> DEVINL cd mul_w8_3(cd a) {                                                              // a * exp(SGN 3 i pi/4)
+    return SGN > 0 ? mk((-a.re - a.im) * kRsqrt2, (a.re - a.im) * kRsqrt2) : mk((a.im - a.re) * kRsqrt2, (-a.im - a.re) * kRsqrt2);
+}
+template <int SGN> DEVINL void fft8(cd (&a)[8]) {
+    const cd u0 = cadd(a[0], a[4]), u1 = cadd(a[1], a[5]), u2 = cadd(a[2], a[6]), u3 = cadd(a[3], a[7]);
+    const cd v0 = csub(a[0], a[4]), v1 = mul_w8_1<SGN>(csub(a[1], a[5])), v2 = mul_i<SGN>(csub(a[2], a[6])),
+             v3 = mul_w8_3<SGN>(csub(a[3], a[7]));
+    const cd p0 = cadd(u0, u2), p1 = cadd(u1, u3), q0 = csub(u0, u2), q1 = mul_i<SGN>(csub(u1, u3));
+    a[0] = cadd(p0, p1); a[4] = csub(p0, p1); a[2] = cadd(q0, q1); a[6] = csub(q0, q1);
+    const cd r0 = cadd(v0, v2), r1 = cadd(v1, v3), s0 = csub(v0, v2), s1 = mul_i<SGN>(csub(v1, v3));
+    a[1] = cadd(r0, r1); a[5] = csub(r0, r1); a[3] = cadd(s0, s1); a[7] = csub(s0, s1);
+}
+
+// ---- per-lane constants -----------------------------------------------------------------------------------------
+template <int G> struct OpLane {
+    static constexpr int N = 8 * G;
+    int lane, g, kap;
+    double sg1, sg2;            // -1 on the upper lane of an xor-1 / xor-2 pair
+    bool rot;                   // G == 4: lane 3 carries the +-i twiddle of the 4-point cross-lane FFT
+    int src_m1, src_p1;         // lane (inside the group) holding Fourier block kappa-1 / kappa+1
+    int src_neg, src_neg0;      // ... block G-1-kappa / (G-kappa) mod G  (conjugate partners)
+    double l0;                  // l of the lane's first mode
+    const double2 *cs;          // [N]    (cos tau_n, sin tau_n)                         ua_type.F90:60-62
+    const double2 *tw;          // [G][8] exp(-2 pi i g k1 / N)
+    const double2 *il;          // [N]    (1/l_k, 1/l_k^2), zero for k = 0               ua_type.F90:51-56
+
+    DEVINL static int kappa_of(int g) { return G == 4 ? (((g & 1) << 1) | (g >> 1)) : g; }
+    DEVINL static double lmode(int k) { return (double)(k < N / 2 ? k : k - N); }
+
+    // tab: 96 double2 of shared memory; every thread of the CTA must call; ends with __syncthreads
+    DEVINL void init(int lane_, double2 *tab) {
+        lane = lane_;
+        g = lane & (G - 1);
+        kap = kappa_of(g);
+        sg1 = (g & 1) ? -1.0 : 1.0;
+        sg2 = (g & 2) ? -1.0 : 1.0;
+        rot = (G == 4) && g == 3;
+        src_m1 = kappa_of((kap + G - 1) & (G - 1));
+        src_p1 = kappa_of((kap + 1) & (G - 1));
+        src_neg = kappa_of(G - 1 - kap);
+        src_neg0 = kappa_of((G - kap) & (G - 1));
+        l0 = lmode(8 * kap);
+        cs = tab; tw = tab + 32; il = tab + 64;
+        const int i = threadIdx.x;
+        if (i < N) {
+            double s, c;
+            sincospi(2.0 * (double)i / (double)N, &s, &c);
+            tab[i] = make_double2(c, s);
+            const int gg = i >> 3, k1 = i & 7;
+            sincospi(-2.0 * (double)(gg * k1) / (double)N, &s, &c);
+            tab[32 + i] = make_double2(c, s);
+            const double l = lmode(i);
+            tab[64 + i] = (i == 0) ? make_double2(0.0, 0.0) : make_double2(1.0 / l, 1.0 / (l * l));
+        }
+        __syncthreads();
+    }
+    DEVINL double lf(int k1) const { return G == 1 ? lmode(k1) : l0 + (double)k1; }
+};
+
+template <int G> DEVINL double shfl_grp(double v, int src) { return G == 1 ? v : __shfl_sync(kFull, v, src, G); }
+template <int G> DEVINL cd shfl_grp(cd v, int src) { return mk(shfl_grp<G>(v.re, src), shfl_grp<G>(v.im, src)); }
+template <int G> DEVINL double grp_sum(double v) {
+#pragma unroll
+    for (int h = G / 2; h >= 1; h >>= 1) v += __shfl_xor_sync(kFull, v, h);
+    return v;
+}
+
+// butterfly across lanes: a <- partner + sg * own  (lower lane: own + partner ; upper lane: partner - own)
+DEVINL void xbfly(cd (&a)[8], int mask, double sg) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const double pr = __shfl_xor_sync(kFull, a[i].re, mask), pi = __shfl_xor_sync(kFull, a[i].im, mask);
+        a[i] = mk(fma(sg, a[i].re, pr), fma(sg, a[i].im, pi));
+    }
+}
+
+// forward length-N transform, unnormalised: time layout in, Fourier layout out
+template <int G> DEVINL void fwdN(cd (&a)[8], const OpLane<G> &L) {
+    fft8<-1>(a);
+    if (G > 1) {
+#pragma unroll
+        for (int k1 = 1; k1 < 8; ++k1) { const double2 w = L.tw[8 * L.g + k1]; a[k1] = cmul(a[k1], mk(w.x, w.y)); }
+    }
+    if (G == 4) {
+        xbfly(a, 2, L.sg2);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[i] = L.rot ? mk(a[i].im, -a[i].re) : a[i];     // lane 3: times -i
+    }
+    if (G >= 2) xbfly(a, 1, L.sg1);
+}
+
+// backward length-N transform, unnormalised: Fourier layout in, time layout out
+template <int G> DEVINL void bwdN(cd (&a)[8], const OpLane<G> &L) {
+    if (G >= 2) xbfly(a, 1, L.sg1);
+    if (G == 4) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[i] = L.rot ? mk(-a[i].im, a[i].re) : a[i];     // lane 3: times +i
+        xbfly(a, 2, L.sg2);
+    }
+    if (G > 1) {
+#pragma unroll
+        for (int k1 = 1; k1 < 8; ++k1) { const double2 w = L.tw[8 * L.g + k1]; a[k1] = cmulc(a[k1], mk(w.x, w.y)); }
+    }
+    fft8<+1>(a);
+}
+
+// exp(-i l_k t/eps) for the lane's 8 modes: one sincos for the first mode, a recurrence with e1 = exp(-i t/eps) for the
+// others (the reference evaluates every mode directly, ua_steps.F90:64,224,258; the recurrence error, a few ulp, is
+// below the rounding of the phase l*t/eps itself)
+template <int G> DEVINL void elt_modes(const OpLane<G> &L, double t, double eps, cd e1, cd (&elt)[8]) {
+    if (G == 1) {
+        elt[0] = mk(1.0, 0.0);
+        elt[1] = e1;
+        elt[2] = cmul(elt[1], e1);
+        elt[3] = cmul(elt[2], e1);
+        const cd e4 = cmul(elt[3], e1);
+        elt[4] = mk(e4.re, -e4.im);                    // l = -4
+        elt[5] = mk(elt[3].re, -elt[3].im);
+        elt[6] = mk(elt[2].re, -elt[2].im);
+        elt[7] = mk(elt[1].re, -elt[1].im);
+    } else {
+        double s, c;
+        sincos(-(L.l0 * t) / eps, &s, &c);
+        elt[0] = mk(c, s);
+#pragma unroll
+        for (int k1 = 1; k1 < 8; ++k1) elt[k1] = cmul(elt[k1 - 1], e1);
+    }
+}
+
+// pl, ql/t of ua_steps.F90:60-66 for mode (lane, k1); il = (1/l, 1/l^2)
+template <int G>
+DEVINL void pl_qt(const OpLane<G> &L, int k1, double t, double rt, double eps, cd elt, cd &pl, cd &qt) {
+    const double2 il = L.il[8 * L.kap + k1];
+    const double l = L.lf(k1);
+    pl = mk(-eps * elt.im * il.x, eps * (elt.re - 1.0) * il.x);
+    qt = mk(eps * eps * (1.0 - elt.re) * il.y * rt, -eps * fma(eps, elt.im, l * t) * il.y * rt);
+    if (k1 == 0 && L.kap == 0) { pl = mk(t, 0.0); qt = mk(0.5 * t, 0.0); }
+}
+
+// F[R(-tau) y / b]: F[cos(tau) y]_k = (Y_{k-1}+Y_{k+1})/2, F[sin(tau) y]_k = -i (Y_{k-1}-Y_{k+1})/2   (ua_steps.F90:174-175)
+DEVINL void fx_modes(double hb, cd p1, cd m1, cd p2, cd m2, cd &fx1, cd &fx2) {
+    const cd a1 = cadd(p1, m1), d1 = csub(p1, m1), a2 = cadd(p2, m2), d2 = csub(p2, m2);
+    fx1 = mk(hb * (a1.re + d2.im), hb * (a1.im - d2.re));
+    fx2 = mk(hb * (a2.re - d1.im), hb * (a2.im + d1.re));
+}
+
+// time-domain fy of ua_steps.F90:177-183
+DEVINL void fy_time(double ct, double st, double rb, double interv, cd yt1, cd yt2, double et1, double et2, cd &fy1, cd &fy2) {
+    const cd t1 = mk(fma(ct * yt2.re - st * yt1.re, interv, et1), (ct * yt2.im - st * yt1.im) * interv);
+    const cd t2 = mk(fma(-(ct * yt1.re + st * yt2.re), interv, et2), -(ct * yt1.im + st * yt2.im) * interv);
+    fy1 = mk((ct * t1.re - st * t2.re) * rb, (ct * t1.im - st * t2.im) * rb);
+    fy2 = mk((st * t1.re + ct * t2.re) * rb, (st * t1.im + ct * t2.im) * rb);
+}
+
+DEVINL double re_mulc(cd a, cd b) { return fma(a.re, b.re, a.im * b.im); }    // Re(a * conj(b))
+DEVINL double re_mul(cd a, cd b) { return fma(a.re, b.re, -a.im * b.im); }    // Re(a * b)
+
+// three M6 weights of one half of the stencil: u = 1-dp for offsets -2,-1,0 ; u = dp for offsets 3,2,1 (in this order)
+DEVINL void m6_half_weights(double u, double (&w)[3]) {
+    const double a = pow5(u), b = pow5(1.0 + u), c = pow5(2.0 + u);
+    const double k = 1.0 / 120.0;
+    w[0] = a * k;
+    w[1] = fma(-6.0, a, b) * k;
+    w[2] = fma(15.0, a, fma(-6.0, b, c)) * k;
+}
+
+// deposit of one particle by its G lanes (compute_rho_m6.F90:89-187): the 36 live taps are split 3x3 (G = 4), 3x6 (G = 2)
+template <int G>
+DEVINL void deposit_split(const MeshDev &m, const RhoAcc &r, const Cell &c, double weight, int g, bool valid) {
+    constexpr int NXP = (G >= 2) ? 3 : 6, NYP = (G == 4) ? 3 : 6;
+    double wx[6], wy[6];
+    int ox[6], oy[6];
+    if (G >= 2) {
+        const bool hi = g & 1;
+        double w3[3];
+        m6_half_weights(hi ? c.dpx : 1.0 - c.dpx, w3);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { wx[i] = w3[i]; ox[i] = hi ? 3 - i : i - 2; }
+    } else {
+        m6_weights_fast(c.dpx, wx);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) ox[i] = i - 2;
+    }
+    if (G == 4) {
+        const bool hi = g & 2;
+        double w3[3];
+        m6_half_weights(hi ? c.dpy : 1.0 - c.dpy, w3);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { wy[i] = w3[i]; oy[i] = hi ? 3 - i : i - 2; }
+    } else {
+        m6_weights_fast(c.dpy, wy);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) oy[i] = i - 2;
+    }
+    if (!valid) return;
+#pragma unroll
+    for (int j = 0; j < NYP; ++j) {
+        const int jy = wrap_fast(c.j, oy[j], m.ny) * m.ld;
+        const double wyw = wy[j] * weight;
+#pragma unroll
+        for (int i = 0; i < NXP; ++i) rho_add(r, wrap_fast(c.i, ox[i], m.nx) + jy, wx[i] * wyw);
+    }
+}
+
+struct OpDev {
+    OnepassParams p;
+    MeshFast f;
+    double inv_eps;
+};
+
+// byte offsets inside a particle's block of the store (N = ntau): xtr | yt1 | yt2 | W | interv
+template <int N, bool FULL> struct StoreMap {
+    static constexpr size_t stride = (FULL ? 72 : 48) * (size_t)N;
+    DEVINL static double2 *xtr(char *base) { return reinterpret_cast<double2 *>(base); }
+    DEVINL static double2 *yt1(char *base) { return reinterpret_cast<double2 *>(base) + N; }
+    DEVINL static double2 *yt2(char *base) { return reinterpret_cast<double2 *>(base) + 2 * N; }
+    DEVINL static double2 *wn(char *base) { return reinterpret_cast<double2 *>(base) + 3 * N; }
+    DEVINL static double *iv(char *base) { return reinterpret_cast<double *>(base + 64 * (size_t)N); }
+};
+
+// =================================================================================================
+template <int G, bool FULL>
+__global__ void __launch_bounds__(kOpBlock, UAPIC_OP_MINB_A) k_onepass_a(OpDev D) {
+    constexpr int N = 8 * G, PW = 32 / G, PPI = 32 / N;     // particles per warp tile / per gather iteration
+    using SM = StoreMap<N, FULL>;
+    const OnepassParams &P = D.p;
+    extern __shared__ double2 smem[];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double2 *gx = smem + kTab + wib * kWarpSmA;    // [8][kRow]  positions -> E at the samples
+    double2 *ivs = gx + 8 * kRow;                  // [4][32]    interv pairs
+    double2 *yhs = ivs + 4 * 32;                   // [16][32]   yhat1[k1] at slot k1, yhat2[k1] at slot 8+k1
+    OpLane<G> L; L.init(lane, smem);
+    const int g = L.g, pin = lane / G, gbase = lane - g;
+    const double eps = P.eps, inv_eps = D.inv_eps, invN = 1.0 / (double)N;
+    const int64_t ntiles = (P.np + PW - 1) / PW;
+    const int64_t nwarps = (int64_t)gridDim.x * kOpWarps;
+
+    for (int64_t tile = (int64_t)blockIdx.x * kOpWarps + wib; tile < ntiles; tile += nwarps) {
+        const int64_t kraw = tile * PW + pin;
+        const bool valid = kraw < P.np;
+        const int64_t ip = valid ? kraw : P.np - 1;
+        const double2 xx = P.x[ip], vv = P.v[ip], ee = P.ep[ip];
+        const double x1 = xx.x, x2 = xx.y, vx = vv.x, vy = vv.y;
+
+        // ---- preparation (ua_steps.F90:49-113) ----
+        const double b = bfield(x1, x2);                                     // :54
+        const double t = P.dt * b;                                           // :55
+        const double rb = 1.0 / b, rt = 1.0 / t;
+        const double vxb = vx * rb, vyb = vy * rb;                           // :73-74
+        double xt1[8], xt2[8];
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+            const double2 c = L.cs[g + G * s];
+            xt1[s] = x1 + eps * (c.y * vxb - c.x * vyb) + eps * vyb;         // :78-81
+            xt2[s] = x2 + eps * (c.y * vyb + c.x * vxb) - eps * vxb;         // :79-82
+            gx[s * kRow + lane] = make_double2(xt1[s], xt2[s]);
+        }
+        __syncwarp();
+        // ---- gather E_n at the samples, lane = sample (interpolation_m6.F90:83-189) ----
+#pragma unroll 2
+        for (int j = 0; j < 8; ++j) {
+            const int n = lane & (N - 1), pp = j * PPI + lane / N;
+            const int idx = (n / G) * kRow + pp * G + (n & (G - 1));
+            const double2 pos = gx[idx];
+            double xw, yw, e1, e2;
+            const Cell cell = cell_fast(P.m, D.f, pos.x, pos.y, P.wrap, xw, yw);
+            gather_fast(P.m, P.ehalo, cell, e1, e2);
+            gx[idx] = make_double2(e1, e2);
+        }
+        __syncwarp();
+
+        cd z[8];
+        {
+            double iv[8];
+#pragma unroll
+            for (int s = 0; s < 8; ++s) {
+                const double2 c = L.cs[g + G * s];
+                iv[s] = (1.0 + 0.5 * sin(xt1[s]) * sin(xt2[s]) - b) * inv_eps;              // :87
+                const double exb = ((c.x * vy - c.y * vx) * iv[s] + ee.x) * rb;             // :89
+                const double eyb = ((-c.x * vx - c.y * vy) * iv[s] + ee.y) * rb;            // :90
+                z[s] = mk(c.x * exb - c.y * eyb, c.y * exb + c.x * eyb);                    // r1 + i r2   :92-93
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) ivs[q * 32 + lane] = make_double2(iv[2 * q], iv[2 * q + 1]);
+        }
+        fwdN<G>(z, L);                                                       // :97-98, both real signals at once
+        // split the two spectra, filter (:100-103; the k = 0 coefficient cancels in :109-110 and is dropped)
+        {
+            cd zp[8];
+            zp[0] = shfl_grp<G>(z[0], L.src_neg0);
+#pragma unroll
+            for (int k1 = 1; k1 < 8; ++k1) zp[k1] = shfl_grp<G>(z[8 - k1], L.src_neg);
+            cd c1[8], c2[8], cs1 = mk(0.0, 0.0), cs2 = mk(0.0, 0.0);
+#pragma unroll
+            for (int k1 = 0; k1 < 8; ++k1) {
+                const double s = 0.5 * invN * L.il[8 * L.kap + k1].x;
+                c1[k1] = mk(s * (z[k1].im - zp[k1].im), -s * (z[k1].re + zp[k1].re));
+                c2[k1] = mk(-s * (z[k1].re - zp[k1].re), -s * (z[k1].im + zp[k1].im));
+                cs1 = cadd(cs1, c1[k1]); cs2 = cadd(cs2, c2[k1]);
+            }
+            cs1 = mk(grp_sum<G>(cs1.re), grp_sum<G>(cs1.im));                // value of the filtered signal at tau = 0
+            cs2 = mk(grp_sum<G>(cs2.re), grp_sum<G>(cs2.im));
+            // FFT(yt)/N: eps*c_k, and the mean value for k = 0   (:109-110)
+#pragma unroll
+            for (int k1 = 0; k1 < 8; ++k1) {
+                cd y1 = rmul(eps, c1[k1]), y2 = rmul(eps, c2[k1]);
+                if (k1 == 0 && L.kap == 0) { y1 = mk(vx - eps * cs1.re, -eps * cs1.im); y2 = mk(vy - eps * cs2.re, -eps * cs2.im); }
+                yhs[k1 * 32 + lane] = make_double2(y1.re, y1.im);
+                yhs[(8 + k1) * 32 + lane] = make_double2(y2.re, y2.im);
+            }
+        }
+        __syncwarp();
+
+        // ---- exp(-i l t/eps), pl, ql/t, w = ql/t * conj(elt) for the lane's modes ----
+        cd e1;
+        { double s, c; sincos(-t / eps, &s, &c); e1 = mk(c, s); }
+        cd elt[8];
+        elt_modes<G>(L, t, eps, e1, elt);
+
+        // ---- x: fhat_x from yhat (a +-1 shift in Fourier space), ua_step1 (:226-227), position sums ----
+        double posp1 = 0.0, posp2 = 0.0, swf1 = 0.0, swf2 = 0.0;
+        cd X1[8], X2[8];
+        {
+            const double hb = 0.5 * rb, he = 0.5 * eps;
+            const double2 *y1s = yhs + lane, *y2s = yhs + 8 * 32 + lane;
+            // sliding window over the modes k-1, k, k+1 (neighbouring blocks live in other lanes' slots)
+            double2 a1 = yhs[7 * 32 + gbase + L.src_m1], a2 = yhs[15 * 32 + gbase + L.src_m1];
+            double2 b1 = y1s[0], b2 = y2s[0];
+#pragma unroll
+            for (int k1 = 0; k1 < 8; ++k1) {
+                const double2 n1 = (k1 < 7) ? y1s[(k1 + 1) * 32] : yhs[gbase + L.src_p1];
+                const double2 n2 = (k1 < 7) ? y2s[(k1 + 1) * 32] : yhs[8 * 32 + gbase + L.src_p1];
+                cd fx1, fx2;
+                fx_modes(hb, mk(a1.x, a1.y), mk(n1.x, n1.y), mk(a2.x, a2.y), mk(n2.x, n2.y), fx1, fx2);
+                cd pl, qt;
+                pl_qt<G>(L, k1, t, rt, eps, elt[k1], pl, qt);
+                const cd w = cmulc(qt, elt[k1]);
+                // FFT(xt)/N of the first-order profile: modes 0, +-1 only
+                cd xh1 = mk(0.0, 0.0), xh2 = mk(0.0, 0.0);
+                if (k1 == 0 && L.kap == 0) { xh1 = mk(x1 + eps * vyb, 0.0); xh2 = mk(x2 - eps * vxb, 0.0); }
+                if (k1 == 1 && L.kap == 0) { xh1 = mk(-he * vyb, -he * vxb); xh2 = mk(he * vxb, -he * vyb); }
+                if (k1 == 7 && L.kap == G - 1) { xh1 = mk(-he * vyb, he * vxb); xh2 = mk(he * vxb, he * vyb); }
+                if (k1 == 0 || k1 == 1 || k1 == 7) {
+                    X1[k1] = cfma(pl, fx1, cmul(elt[k1], xh1));                  // :226
+                    X2[k1] = cfma(pl, fx2, cmul(elt[k1], xh2));                  // :227
+                } else {
+                    X1[k1] = cmul(pl, fx1);
+                    X2[k1] = cmul(pl, fx2);
+                }
+                posp1 += re_mulc(X1[k1], elt[k1]);                               // compute_rho_m6.F90:74-84
+                posp2 += re_mulc(X2[k1], elt[k1]);
+                swf1 += re_mul(w, fx1);
+                swf2 += re_mul(w, fx2);
+                a1 = b1; a2 = b2; b1 = n1; b2 = n2;
+            }
+        }
+        bwdN<G>(X1, L);                                                      // :231
+        bwdN<G>(X2, L);
+        char *sbase = P.store + (size_t)ip * SM::stride;
+        if (valid) {
+#pragma unroll
+            for (int s = 0; s < 8; ++s) SM::xtr(sbase)[g + G * s] = make_double2(X1[s].re, X2[s].re);
+            if (FULL) {
+#pragma unroll
+                for (int s = 0; s < 8; ++s)
+                    SM::iv(sbase)[g + G * s] = (1.0 + 0.5 * sin(X1[s].re) * sin(X2[s].re) - b) * inv_eps;   // :177 of the 2nd compute_f
+            }
+        }
+
+        // ---- y: yt = B(yhat) (:105-110), fy in the time domain (:177-183), FFT, ua_step1 (:226), bracket sums ----
+        cd y1[8], y2[8];
+#pragma unroll
+        for (int k1 = 0; k1 < 8; ++k1) {
+            const double2 a = yhs[k1 * 32 + lane], c = yhs[(8 + k1) * 32 + lane];
+            y1[k1] = mk(a.x, a.y); y2[k1] = mk(c.x, c.y);
+        }
+        bwdN<G>(y1, L);
+        bwdN<G>(y2, L);
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+            const double2 c = L.cs[g + G * s], et = gx[s * kRow + lane];
+            const double2 ivp = ivs[(s >> 1) * 32 + lane];
+            fy_time(c.x, c.y, rb, (s & 1) ? ivp.y : ivp.x, y1[s], y2[s], et.x, et.y, y1[s], y2[s]);
+        }
+        fwdN<G>(y1, L);                                                      // :189-190
+        fwdN<G>(y2, L);
+        double qa1 = 0.0, qa2 = 0.0;
+        cd wv[8];
+#pragma unroll
+        for (int k1 = 0; k1 < 8; ++k1) {
+            const cd fy1 = rmul(invN, y1[k1]), fy2 = rmul(invN, y2[k1]);     // :194-195
+            const double2 h1 = yhs[k1 * 32 + lane], h2 = yhs[(8 + k1) * 32 + lane];
+            cd pl, qt;
+            pl_qt<G>(L, k1, t, rt, eps, elt[k1], pl, qt);
+            wv[k1] = cmulc(qt, elt[k1]);
+            const cd yp1 = cfma(pl, fy1, cmul(elt[k1], mk(h1.x, h1.y)));     // :226 for y
+            const cd yp2 = cfma(pl, fy2, cmul(elt[k1], mk(h2.x, h2.y)));
+            qa1 += re_mulc(yp1, elt[k1]) - re_mul(wv[k1], fy1);              // Re[(Yp - qt Fy) conj(elt)]
+            qa2 += re_mulc(yp2, elt[k1]) - re_mul(wv[k1], fy2);
+            y1[k1] = yp1; y2[k1] = yp2;
+        }
+        // corrector position (:260 + compute_rho_m6.F90:74-84): needs ghat_x = shift of the predicted yhat only
+        double swg1 = 0.0, swg2 = 0.0;
+        {
+            const double hb = 0.5 * rb;
+            const cd m1 = shfl_grp<G>(y1[7], L.src_m1), m2 = shfl_grp<G>(y2[7], L.src_m1);
+            const cd p1 = shfl_grp<G>(y1[0], L.src_p1), p2 = shfl_grp<G>(y2[0], L.src_p1);
+#pragma unroll
+            for (int k1 = 0; k1 < 8; ++k1) {
+                cd gx1, gx2;
+                fx_modes(hb, k1 == 0 ? m1 : y1[k1 - 1], k1 == 7 ? p1 : y1[k1 + 1], k1 == 0 ? m2 : y2[k1 - 1], k1 == 7 ? p2 : y2[k1 + 1],
+                         gx1, gx2);
+                swg1 += re_mul(wv[k1], gx1);
+                swg2 += re_mul(wv[k1], gx2);
+            }
+        }
+        bwdN<G>(y1, L);                                                      // :232
+        bwdN<G>(y2, L);
+        if (valid) {
+#pragma unroll
+            for (int s = 0; s < 8; ++s) {
+                SM::yt1(sbase)[g + G * s] = make_double2(y1[s].re, y1[s].im);
+                SM::yt2(sbase)[g + G * s] = make_double2(y2[s].re, y2[s].im);
+            }
+        }
+        if (FULL) {
+            // W_n = (1/N) sum_k w_k exp(-i k tau_n) = conj( B(conj(w)) ) / N
+#pragma unroll
+            for (int k1 = 0; k1 < 8; ++k1) wv[k1] = mk(invN * wv[k1].re, -invN * wv[k1].im);
+            bwdN<G>(wv, L);
+            if (valid) {
+#pragma unroll
+                for (int s = 0; s < 8; ++s) SM::wn(sbase)[g + G * s] = make_double2(wv[s].re, -wv[s].im);
+            }
+        }
+
+        // ---- both deposit positions, deposits, per-particle record ----
+        posp1 = grp_sum<G>(posp1); posp2 = grp_sum<G>(posp2);
+        const double posc1 = posp1 + grp_sum<G>(swg1 - swf1), posc2 = posp2 + grp_sum<G>(swg2 - swf2);
+        qa1 = grp_sum<G>(qa1); qa2 = grp_sum<G>(qa2);
+        double xw, yw;
+        const Cell cp = cell_fast(P.m, D.f, posp1, posp2, P.wrap, xw, yw);
+        deposit_split<G>(P.m, P.rho_p, cp, P.weight, g, valid);              // compute_rho_m6.F90:89-187 (predictor)
+        const Cell cc = cell_fast(P.m, D.f, posc1, posc2, P.wrap, xw, yw);
+        deposit_split<G>(P.m, P.rho_c, cc, P.weight, g, valid);              // (corrector)
+        if (valid && g == 0) {
+            P.x[ip] = make_double2(xw, yw);                                  // compute_rho_m6.F90:86-87
+            double2 *rec = reinterpret_cast<double2 *>(P.rec + 8 * ip);
+            rec[0] = make_double2(t, b);
+            rec[1] = make_double2(rb, qa1);
+            rec[2] = make_double2(qa2, e1.re);                               // cos(t/eps)
+            rec[3] = make_double2(-e1.im, 0.0);                              // sin(t/eps)
+        }
+        __syncwarp();
+    }
+}
+
+// =================================================================================================
+template <int G, bool FULL>
+__global__ void __launch_bounds__(kOpBlock, UAPIC_OP_MINB_B) k_onepass_b(OpDev D) {
+    constexpr int N = 8 * G, PW = 32 / G, PPI = 32 / N;
+    using SM = StoreMap<N, FULL>;
+    const OnepassParams &P = D.p;
+    extern __shared__ double2 smem[];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double2 *wx = smem + kTab + wib * kWarpSmB;    // [8][kRow]  W_n of the tile (LEAN only)
+    OpLane<G> L; L.init(lane, smem);
+    const int g = L.g, pin = lane / G;
+    const double eps = P.eps, inv_eps = D.inv_eps, invN = 1.0 / (double)N;
+    const int n = lane & (N - 1);
+    const double2 csn = L.cs[n];
+    const int64_t ntiles = (P.np + PW - 1) / PW;
+    const int64_t nwarps = (int64_t)gridDim.x * kOpWarps;
+
+    for (int64_t tile = (int64_t)blockIdx.x * kOpWarps + wib; tile < ntiles; tile += nwarps) {
+        if (!FULL) {
+            // W_n of the tile's particles in the phase-A layout, handed to the sample lanes through shared memory
+            const int64_t kraw = tile * PW + pin;
+            const int64_t ip = kraw < P.np ? kraw : P.np - 1;
+            const double2 *rec = reinterpret_cast<const double2 *>(P.rec + 8 * ip);
+            const double t = rec[0].x, rt = 1.0 / t;
+            const cd e1 = mk(rec[2].y, -rec[3].x);
+            cd elt[8], wv[8];
+            elt_modes<G>(L, t, eps, e1, elt);
+#pragma unroll
+            for (int k1 = 0; k1 < 8; ++k1) {
+                cd pl, qt;
+                pl_qt<G>(L, k1, t, rt, eps, elt[k1], pl, qt);
+                const cd w = cmulc(qt, elt[k1]);
+                wv[k1] = mk(invN * w.re, -invN * w.im);
+            }
+            bwdN<G>(wv, L);
+            __syncwarp();
+#pragma unroll
+            for (int s = 0; s < 8; ++s) wx[s * kRow + lane] = make_double2(wv[s].re, -wv[s].im);
+            __syncwarp();
+        }
+#pragma unroll 2
+        for (int j = 0; j < 8; ++j) {
+            const int pp = j * PPI + lane / N;
+            const int64_t kraw = tile * PW + pp;
+            const bool valid = kraw < P.np;
+            const int64_t ip = valid ? kraw : P.np - 1;
+            const double2 *rec = reinterpret_cast<const double2 *>(P.rec + 8 * ip);
+            const double2 r0 = rec[0], r1 = rec[1], r2 = rec[2], r3 = rec[3];
+            const double b = r0.y, rb = r1.x, qa1 = r1.y, qa2 = r2.x, cs = r2.y, sn = r3.x;
+            char *sbase = P.store + (size_t)ip * SM::stride;
+            const double2 xs = SM::xtr(sbase)[n], ya = SM::yt1(sbase)[n], yb = SM::yt2(sbase)[n];
+            double2 wn;
+            double iv;
+            if (FULL) {
+                wn = SM::wn(sbase)[n];
+                iv = SM::iv(sbase)[n];
+            } else {
+                wn = wx[(n / G) * kRow + pp * G + (n & (G - 1))];
+                iv = (1.0 + 0.5 * sin(xs.x) * sin(xs.y) - b) * inv_eps;      // ua_steps.F90:177
+            }
+            // ---- gather E_pred at the predicted samples (interpolation_m6.F90:83-189) ----
+            double xw, yw, e1, e2;
+            const Cell cell = cell_fast(P.m, D.f, xs.x, xs.y, P.wrap, xw, yw);
+            gather_fast(P.m, P.ehalo, cell, e1, e2);
+            cd gy1, gy2;
+            fy_time(csn.x, csn.y, rb, iv, mk(ya.x, ya.y), mk(yb.x, yb.y), e1, e2, gy1, gy2);     // :177-183
+            // Re sum_n gy(tau_n) W_n
+            const double px = qa1 + group_sum<N>(fma(gy1.re, wn.x, -gy1.im * wn.y));
+            const double py = qa2 + group_sum<N>(fma(gy2.re, wn.x, -gy2.im * wn.y));
+            if (valid && n == 0) P.v[ip] = make_double2(cs * px + sn * py, cs * py - sn * px);     // :302-303
+        }
+        (void)g;
+    }
+}
+
+inline int op_grid(const LaunchCtx &c, int64_t np, int ntau, int minb) {
+    const int pw = 32 / (ntau / 8);
+    int64_t need = ((np + pw - 1) / pw + kOpWarps - 1) / kOpWarps;
+    const int64_t cap = (int64_t)c.sm_count * minb;
+    if (need < 1) need = 1;
+    return (int)(need < cap ? need : cap);
+}
+
+OpDev make_opdev(const OnepassParams &p) {
+    OpDev D;
+    D.p = p;
+    D.f.inv_dx = 1.0 / p.m.dx; D.f.inv_dy = 1.0 / p.m.dy;
+    D.f.inv_nx = 1.0 / (double)p.m.nx; D.f.inv_ny = 1.0 / (double)p.m.ny;
+    D.f.inv_dimx = 1.0 / p.m.dimx; D.f.inv_dimy = 1.0 / p.m.dimy;
+    D.inv_eps = 1.0 / p.eps;
+    return D;
+}
+
+template <typename K> cudaError_t op_launch(K kernel, const LaunchCtx &c, const OpDev &D, int grid, size_t smem) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kernel<<<grid, kOpBlock, smem, c.stream>>>(D);
+    if (c.launches) *c.launches += 1;
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+bool onepass_ntau_supported(int ntau) { return ntau == 8 || ntau == 16 || ntau == 32; }
+size_t onepass_store_bytes_per_particle(int ntau, int full) { return (size_t)(full ? 72 : 48) * (size_t)ntau; }
+
+#define UAPIC_OP_DISPATCH(KERNEL, MINB, SMEM)                                                              \
+    switch (p.ntau) {                                                                                      \
+        case 8:  return p.full ? op_launch(KERNEL<1, true>, c, D, op_grid(c, p.np, 8, MINB), SMEM)         \
+                               : op_launch(KERNEL<1, false>, c, D, op_grid(c, p.np, 8, MINB), SMEM);       \
+        case 16: return p.full ? op_launch(KERNEL<2, true>, c, D, op_grid(c, p.np, 16, MINB), SMEM)        \
+                               : op_launch(KERNEL<2, false>, c, D, op_grid(c, p.np, 16, MINB), SMEM);      \
+        case 32: return p.full ? op_launch(KERNEL<4, true>, c, D, op_grid(c, p.np, 32, MINB), SMEM)        \
+                               : op_launch(KERNEL<4, false>, c, D, op_grid(c, p.np, 32, MINB), SMEM);      \
+        default: return cudaErrorInvalidValue;                                                             \
+    }
+
+cudaError_t launch_onepass_a(const LaunchCtx &c, const OnepassParams &p) {
+    if (p.np <= 0) return cudaSuccess;
+    if (p.m.nx < 4 || p.m.ny < 4) return cudaErrorInvalidValue;
+    const OpDev D = make_opdev(p);
+    const size_t smem = sizeof(double2) * (size_t)(kTab + kOpWarps * kWarpSmA);
+    UAPIC_OP_DISPATCH(k_onepass_a, UAPIC_OP_MINB_A, smem)
+}
+
+cudaError_t launch_onepass_b(const LaunchCtx &c, const OnepassParams &p) {
+    if (p.np <= 0) return cudaSuccess;
+    if (p.m.nx < 4 || p.m.ny < 4) return cudaErrorInvalidValue;
+    const OpDev D = make_opdev(p);
+    const size_t smem = sizeof(double2) * (size_t)(kTab + kOpWarps * kWarpSmB);
+    UAPIC_OP_DISPATCH(k_onepass_b, UAPIC_OP_MINB_B, smem)
+}
+
+}  // namespace uapic

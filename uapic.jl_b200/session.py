@@ -166,10 +166,11 @@ class Session:
 
 
 def run_bupdate(mesh: Mesh, ntau: int, eps: float, dt: float, nstep: int, x: np.ndarray, v: np.ndarray, w: float | None = None,
-                wrap=_lib.WRAP_FORTRAN, deposit_mode=_lib.DEPOSIT_FP64_ATOMIC, device: int = 0):
+                wrap=_lib.WRAP_FORTRAN, deposit_mode=_lib.DEPOSIT_FP64_ATOMIC, device: int = 0, storage_mode=_lib.STORE_FULL):
     """the whole program fortran/bupdate.F90:89-128 on one GPU: returns (x, v, energy[1+2*nstep], e_mesh)"""
     nbpart = x.shape[1]
-    with Session(mesh, ntau, eps, dt, nbpart, weight=w, wrap=wrap, deposit_mode=deposit_mode, device=device) as s:
+    with Session(mesh, ntau, eps, dt, nbpart, weight=w, wrap=wrap, deposit_mode=deposit_mode, device=device,
+                 storage_mode=storage_mode) as s:
         s.upload_particles(np.asfortranarray(x), np.asfortranarray(v))
         s.init_fields()
         s.step(nstep)
