@@ -172,6 +172,11 @@ int uapic_session_upload_particles(uapic_session_t *s, const double *x, const do
 /* particles.e (2,nbpart), the field at the particles frozen after init (bupdate.F90:93): lets a caller that keeps
    the particles on the host hand the full per-step input (x, v, e) back to a session */
 int uapic_session_upload_particle_e(uapic_session_t *s, const double *ep);
+/* spatial reordering of the particle arrays by coarse mesh bin (2^bin_cells_log2 cells per side) every `interval` steps;
+   0 switches it off.  It only changes which particles a warp works on together (L1 hit rate of the M6 gathers): uploads
+   and downloads are always in the caller's particle order.  Default: every step with 8 x 8-cell bins for the one-pass
+   storage modes, off for the others.  Not in the reference (particles there are processed in array order). */
+int uapic_session_set_sort(uapic_session_t *s, int interval, int bin_cells_log2);
 /* per-kernel device timing: when enabled, CUDA events bracket the two fused phase kernels of every step;
    phase_times returns the accumulated milliseconds and the number of steps they cover, then resets them */
 int uapic_session_enable_timing(uapic_session_t *s, int enable);

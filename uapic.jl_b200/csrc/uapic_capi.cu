@@ -90,6 +90,7 @@ struct DevBuf {
         return cudaMalloc(&p, n);
     }
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+    void swap(DevBuf &o) { std::swap(p, o.p); std::swap(bytes, o.bytes); }
 };
 
 // scratch context for the synchronous stage API (device 0 of the current context, default stream)
@@ -426,6 +427,11 @@ struct uapic_session {
     RhoAcc acc{};
     RhoAcc acc_c{};                    // one-pass modes: corrector deposit mesh (second half of raw)
     bool onepass = false;
+    // spatial reordering (uapic_sort.cu): alternate buffers, slot -> original index, scratch; allocated at the first sort
+    DevBuf x2, v2, ep2, perm, perm2, binid, hist;
+    bool permuted = false;             // device arrays are in sorted order, perm is valid
+    int sort_interval = 0, sort_shift = 3;
+    int64_t steps_done = 0;
     int64_t n_energy = 0, cap_energy = 0;
     uapic_allreduce_fn reduce = nullptr;
     void *reduce_ctx = nullptr;
@@ -499,6 +505,41 @@ OnepassParams session_onepass_params(uapic_session *s) {
     return p;
 }
 
+// reorder x, v, ep by coarse mesh bin; callers never see the order (downloads undo it)
+int session_sort(uapic_session *s) {
+    const size_t np = (size_t)s->cfg.nbpart;
+    if (np == 0) return UAPIC_OK;
+    if (!s->x2.p) {
+        int rc = UAPIC_OK;
+        if (!rc) rc = session_alloc(s, s->x2, 16 * np);
+        if (!rc) rc = session_alloc(s, s->v2, 16 * np);
+        if (!rc) rc = session_alloc(s, s->ep2, 16 * np);
+        if (!rc) rc = session_alloc(s, s->perm, 4 * np);
+        if (!rc) rc = session_alloc(s, s->perm2, 4 * np);
+        if (!rc) rc = session_alloc(s, s->binid, 2 * np);
+        if (!rc) rc = session_alloc(s, s->hist, 4 * 4096);
+        if (rc) return rc;
+    }
+    CU(launch_sort_particles(s->lc, s->m, s->sort_shift, s->cfg.nbpart, s->x.as<double2>(), s->v.as<double2>(), s->ep.as<double2>(),
+                             s->permuted ? s->perm.as<uint32_t>() : nullptr, s->x2.as<double2>(), s->v2.as<double2>(),
+                             s->ep2.as<double2>(), s->perm2.as<uint32_t>(), s->binid.as<uint16_t>(), s->hist.as<unsigned>()));
+    s->x.swap(s->x2); s->v.swap(s->v2); s->ep.swap(s->ep2); s->perm.swap(s->perm2);
+    s->permuted = true;
+    return UAPIC_OK;
+}
+
+// device array in slot order -> host array in the caller's particle order
+int session_download_pairs(uapic_session *s, DevBuf &src, DevBuf &tmp, double *host) {
+    const size_t n = 16 * (size_t)s->cfg.nbpart;
+    if (s->permuted) {
+        CU(launch_unpermute(s->lc, s->cfg.nbpart, s->perm.as<uint32_t>(), src.as<double2>(), tmp.as<double2>()));
+        CU(cudaMemcpyAsync(host, tmp.p, n, cudaMemcpyDeviceToHost, s->lc.stream));
+    } else {
+        CU(cudaMemcpyAsync(host, src.p, n, cudaMemcpyDeviceToHost, s->lc.stream));
+    }
+    return UAPIC_OK;
+}
+
 PhaseParams session_params(uapic_session *s) {
     PhaseParams p;
     p.m = s->m; p.eps = s->cfg.eps; p.dt = s->cfg.dt; p.weight = s->cfg.weight; p.np = s->cfg.nbpart;
@@ -548,9 +589,13 @@ int uapic_session_create(const uapic_config_t *cfg, uapic_session_t **out) {
     if (!rc) rc = session_alloc(s, s->x, 16 * (np ? np : 1));
     if (!rc) rc = session_alloc(s, s->v, 16 * (np ? np : 1));
     if (!rc) rc = session_alloc(s, s->ep, 16 * (np ? np : 1));
-    if (!rc) rc = session_alloc(s, s->tb, 16 * (np ? np : 1));
     // store-full: 128 B per particle-tau; hybrid: 16 B (E at the tau samples); one-pass: 72 B / 48 B (lean)
     s->onepass = onepass;
+    // the one-pass kernels are bound by the L1 data pipe of the M6 gathers: keep the particles ordered by 8 x 8-cell bins
+    s->sort_interval = onepass ? 1 : 0;
+    s->sort_shift = 3;
+    while (sort_bins(s->m, s->sort_shift) > 4096) s->sort_shift++;
+    if (!rc && !onepass) rc = session_alloc(s, s->tb, 16 * (np ? np : 1));
     const size_t per_tau = onepass ? (cfg->storage_mode == UAPIC_STORE_ONEPASS ? 72 : 48) : (cfg->storage_mode == UAPIC_STORE_HYBRID ? 16 : 128);
     if (!rc) rc = session_alloc(s, s->store, per_tau * N * (np ? np : 1));
     if (!rc) rc = session_alloc(s, s->raw, 8 * nrho * (onepass ? 2 : 1));
@@ -604,6 +649,12 @@ int uapic_session_upload_particles(uapic_session_t *s, const double *x, const do
     CU(cudaMemcpyAsync(s->x.p, x, n, cudaMemcpyHostToDevice, s->lc.stream));
     CU(cudaMemcpyAsync(s->v.p, v, n, cudaMemcpyHostToDevice, s->lc.stream));
     CU(cudaStreamSynchronize(s->lc.stream));
+    if (s->permuted) {
+        // x and v are back in the caller's order: bring particles.e along, then forget the permutation
+        CU(launch_unpermute(s->lc, s->cfg.nbpart, s->perm.as<uint32_t>(), s->ep.as<double2>(), s->ep2.as<double2>()));
+        s->ep.swap(s->ep2);
+        s->permuted = false;
+    }
     s->have_particles = true;
     return UAPIC_OK;
 }
@@ -611,8 +662,24 @@ int uapic_session_upload_particles(uapic_session_t *s, const double *x, const do
 int uapic_session_upload_particle_e(uapic_session_t *s, const double *ep) {
     if (!s || !ep) return fail(UAPIC_EINVAL, "uapic_session_upload_particle_e: null pointer");
     TRY(session_bind(s));
+    if (s->permuted) {
+        // the device arrays are in sorted order: undo it for x and v so that everything is in the caller's order again
+        CU(launch_unpermute(s->lc, s->cfg.nbpart, s->perm.as<uint32_t>(), s->x.as<double2>(), s->x2.as<double2>()));
+        CU(launch_unpermute(s->lc, s->cfg.nbpart, s->perm.as<uint32_t>(), s->v.as<double2>(), s->v2.as<double2>()));
+        s->x.swap(s->x2); s->v.swap(s->v2);
+        s->permuted = false;
+    }
     CU(cudaMemcpyAsync(s->ep.p, ep, 16 * (size_t)s->cfg.nbpart, cudaMemcpyHostToDevice, s->lc.stream));
     CU(cudaStreamSynchronize(s->lc.stream));
+    return UAPIC_OK;
+}
+
+int uapic_session_set_sort(uapic_session_t *s, int interval, int bin_cells_log2) {
+    if (!s) return fail(UAPIC_EINVAL, "session is null");
+    if (interval < 0 || bin_cells_log2 < 0 || bin_cells_log2 > 12) return fail(UAPIC_EINVAL, "uapic_session_set_sort: bad argument");
+    if (sort_bins(s->m, bin_cells_log2) > 4096) return fail(UAPIC_EUNSUPPORTED, "more than 4096 sort bins: use larger bins");
+    if (s->cfg.nbpart >= ((int64_t)1 << 32)) return fail(UAPIC_EUNSUPPORTED, "sorting needs nbpart < 2^32 per session");
+    s->sort_interval = interval; s->sort_shift = bin_cells_log2;
     return UAPIC_OK;
 }
 
@@ -659,6 +726,7 @@ int uapic_session_generate_particles(uapic_session_t *s, int kind, uint64_t seed
     TRY(session_bind(s));
     CU(launch_generate(s->lc, s->m, kind, seed, first_global_index, s->cfg.nbpart, s->np_global, alpha, kx, s->x.as<double>(),
                        s->v.as<double>()));
+    s->permuted = false;
     s->have_particles = true;
     return UAPIC_OK;
 }
@@ -681,9 +749,11 @@ int uapic_session_step(uapic_session_t *s, int nsteps) {
     if (!s->fields_ready) return fail(UAPIC_ESTATE, "call uapic_session_init_fields before uapic_session_step");
     if (nsteps < 0) return fail(UAPIC_EINVAL, "nsteps must be >= 0");
     TRY(session_bind(s));
-    const PhaseParams p = session_params(s);
-    OnepassParams op = s->onepass ? session_onepass_params(s) : OnepassParams{};
     for (int it = 0; it < nsteps; ++it) {
+        if (s->sort_interval > 0 && s->steps_done % s->sort_interval == 0) TRY(session_sort(s));
+        s->steps_done++;
+        const PhaseParams p = session_params(s);
+        OnepassParams op = s->onepass ? session_onepass_params(s) : OnepassParams{};
         cudaEvent_t e4[4] = {nullptr, nullptr, nullptr, nullptr};
         if (s->timing) {
             if (s->ev.size() >= 4096) TRY(drain_timing(s));
@@ -728,9 +798,8 @@ int uapic_session_synchronize(uapic_session_t *s) {
 int uapic_session_download_particles(uapic_session_t *s, double *x, double *v) {
     if (!s) return fail(UAPIC_EINVAL, "session is null");
     TRY(session_bind(s));
-    const size_t n = 16 * (size_t)s->cfg.nbpart;
-    if (x) CU(cudaMemcpyAsync(x, s->x.p, n, cudaMemcpyDeviceToHost, s->lc.stream));
-    if (v) CU(cudaMemcpyAsync(v, s->v.p, n, cudaMemcpyDeviceToHost, s->lc.stream));
+    if (x) TRY(session_download_pairs(s, s->x, s->x2, x));
+    if (v) TRY(session_download_pairs(s, s->v, s->v2, v));
     CU(cudaStreamSynchronize(s->lc.stream));
     return UAPIC_OK;
 }
@@ -738,7 +807,7 @@ int uapic_session_download_particles(uapic_session_t *s, double *x, double *v) {
 int uapic_session_download_particle_e(uapic_session_t *s, double *ep) {
     if (!s || !ep) return fail(UAPIC_EINVAL, "null pointer");
     TRY(session_bind(s));
-    CU(cudaMemcpyAsync(ep, s->ep.p, 16 * (size_t)s->cfg.nbpart, cudaMemcpyDeviceToHost, s->lc.stream));
+    TRY(session_download_pairs(s, s->ep, s->ep2, ep));
     CU(cudaStreamSynchronize(s->lc.stream));
     return UAPIC_OK;
 }

@@ -94,6 +94,13 @@ size_t onepass_store_bytes_per_particle(int ntau, int full);
 cudaError_t launch_onepass_a(const LaunchCtx &c, const OnepassParams &p);
 cudaError_t launch_onepass_b(const LaunchCtx &c, const OnepassParams &p);
 
+// ---- spatial reordering of the particle arrays (uapic_sort.cu) ----------------------------------------------------
+int sort_bins(const MeshDev &m, int bin_cells_log2);
+cudaError_t launch_sort_particles(const LaunchCtx &c, const MeshDev &m, int bin_cells_log2, int64_t np, const double2 *x,
+                                  const double2 *v, const double2 *ep, const uint32_t *perm, double2 *x2, double2 *v2,
+                                  double2 *ep2, uint32_t *perm2, uint16_t *binid, unsigned *hist);
+cudaError_t launch_unpermute(const LaunchCtx &c, int64_t np, const uint32_t *perm, const double2 *a, double2 *out);
+
 // ---- loaders / diagnostics --------------------------------------------------------------------------------------
 cudaError_t launch_generate(const LaunchCtx &c, const MeshDev &m, int kind, uint64_t seed, int64_t first, int64_t np,
                             int64_t np_global, double alpha, double kx, double *x, double *v);

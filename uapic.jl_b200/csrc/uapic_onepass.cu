@@ -39,7 +39,19 @@ namespace {
 #ifndef UAPIC_OP_MINB_B
 #define UAPIC_OP_MINB_B 4
 #endif
+#ifndef UAPIC_OP_LOCKSTEP
+#define UAPIC_OP_LOCKSTEP 1
+#endif
+#if UAPIC_OP_LOCKSTEP
+#define OP_STEP() __syncthreads()
+#else
+#define OP_STEP() __syncwarp()
+#endif
+#ifndef UAPIC_OP_GATHER_UNROLL
+#define UAPIC_OP_GATHER_UNROLL 1
+#endif
 constexpr int kOpBlock = 128;                  // 4 warps per CTA
+constexpr int kGatherUnroll = UAPIC_OP_GATHER_UNROLL;
 constexpr int kOpWarps = kOpBlock / 32;
 constexpr int kRow = 36;                       // padded row (double2 units) of the per-warp exchange area: conflict-free
 constexpr int kTab = 96;                       // 3 tables of 32 double2
@@ -290,7 +302,11 @@ __global__ void __launch_bounds__(kOpBlock, UAPIC_OP_MINB_A) k_onepass_a(OpDev D
     const int64_t ntiles = (P.np + PW - 1) / PW;
     const int64_t nwarps = (int64_t)gridDim.x * kOpWarps;
 
-    for (int64_t tile = (int64_t)blockIdx.x * kOpWarps + wib; tile < ntiles; tile += nwarps) {
+    // the trip count is uniform over the CTA (a warp past the end works on a clamped copy of the last particle with its
+    // stores and deposits switched off) so that the warps of a CTA can be kept in step: they then share instruction
+    // fetches of this long straight-line kernel (UAPIC_OP_LOCKSTEP)
+    for (int64_t tbase = (int64_t)blockIdx.x * kOpWarps; tbase < ntiles; tbase += nwarps) {
+        const int64_t tile = tbase + wib;
         const int64_t kraw = tile * PW + pin;
         const bool valid = kraw < P.np;
         const int64_t ip = valid ? kraw : P.np - 1;
@@ -310,9 +326,9 @@ __global__ void __launch_bounds__(kOpBlock, UAPIC_OP_MINB_A) k_onepass_a(OpDev D
             xt2[s] = x2 + eps * (c.y * vyb + c.x * vxb) - eps * vxb;         // :79-82
             gx[s * kRow + lane] = make_double2(xt1[s], xt2[s]);
         }
-        __syncwarp();
+        OP_STEP();
         // ---- gather E_n at the samples, lane = sample (interpolation_m6.F90:83-189) ----
-#pragma unroll 2
+#pragma unroll (kGatherUnroll)
         for (int j = 0; j < 8; ++j) {
             const int n = lane & (N - 1), pp = j * PPI + lane / N;
             const int idx = (n / G) * kRow + pp * G + (n & (G - 1));
@@ -322,7 +338,7 @@ __global__ void __launch_bounds__(kOpBlock, UAPIC_OP_MINB_A) k_onepass_a(OpDev D
             gather_fast(P.m, P.ehalo, cell, e1, e2);
             gx[idx] = make_double2(e1, e2);
         }
-        __syncwarp();
+        OP_STEP();
 
         cd z[8];
         {
@@ -364,7 +380,7 @@ __global__ void __launch_bounds__(kOpBlock, UAPIC_OP_MINB_A) k_onepass_a(OpDev D
                 yhs[(8 + k1) * 32 + lane] = make_double2(y2.re, y2.im);
             }
         }
-        __syncwarp();
+        OP_STEP();
 
         // ---- exp(-i l t/eps), pl, ql/t, w = ql/t * conj(elt) for the lane's modes ----
         cd e1;
@@ -423,6 +439,7 @@ __global__ void __launch_bounds__(kOpBlock, UAPIC_OP_MINB_A) k_onepass_a(OpDev D
         }
 
         // ---- y: yt = B(yhat) (:105-110), fy in the time domain (:177-183), FFT, ua_step1 (:226), bracket sums ----
+        OP_STEP();
         cd y1[8], y2[8];
 #pragma unroll
         for (int k1 = 0; k1 < 8; ++k1) {
@@ -437,6 +454,7 @@ __global__ void __launch_bounds__(kOpBlock, UAPIC_OP_MINB_A) k_onepass_a(OpDev D
             const double2 ivp = ivs[(s >> 1) * 32 + lane];
             fy_time(c.x, c.y, rb, (s & 1) ? ivp.y : ivp.x, y1[s], y2[s], et.x, et.y, y1[s], y2[s]);
         }
+        OP_STEP();
         fwdN<G>(y1, L);                                                      // :189-190
         fwdN<G>(y2, L);
         double qa1 = 0.0, qa2 = 0.0;
@@ -469,6 +487,7 @@ __global__ void __launch_bounds__(kOpBlock, UAPIC_OP_MINB_A) k_onepass_a(OpDev D
                 swg2 += re_mul(wv[k1], gx2);
             }
         }
+        OP_STEP();
         bwdN<G>(y1, L);                                                      // :232
         bwdN<G>(y2, L);
         if (valid) {
@@ -506,7 +525,7 @@ __global__ void __launch_bounds__(kOpBlock, UAPIC_OP_MINB_A) k_onepass_a(OpDev D
             rec[2] = make_double2(qa2, e1.re);                               // cos(t/eps)
             rec[3] = make_double2(-e1.im, 0.0);                              // sin(t/eps)
         }
-        __syncwarp();
+        OP_STEP();
     }
 }
 

@@ -74,6 +74,10 @@ class Session:
     def upload_particle_e_ptr(self, ep_ptr: int):
         check(lib().uapic_session_upload_particle_e(self._h, C.cast(ep_ptr, _dp)))
 
+    def set_sort(self, interval: int, bin_cells_log2: int = 3):
+        """reorder the particle arrays by coarse mesh bin every `interval` steps (0 = never); invisible to the caller"""
+        check(lib().uapic_session_set_sort(self._h, C.c_int(interval), C.c_int(bin_cells_log2)))
+
     def enable_timing(self, enable: bool = True):
         check(lib().uapic_session_enable_timing(self._h, C.c_int(int(enable))))
 
