@@ -1,0 +1,247 @@
+"""GPU parity tests of the one-pass kernels (UAPIC_STORE_ONEPASS / UAPIC_STORE_ONEPASS_LEAN, uapic_onepass.cu) and of
+the particle reordering (uapic_sort.cu) against the CPU oracle, the golden vectors and the two-barrier kernels.
+
+Tolerances as in test_gpu_session.py: 1e-10 relative on x, v and the energy history at eps = 0.1, velocity tolerance
+scaled by 0.1/eps below; bit-exact where the arithmetic is order independent (fixed-point deposits)."""
+import glob
+import os
+import threading
+
+import numpy as np
+import pytest
+
+import uapic_b200 as ub
+
+from conftest import GOLDEN, periodic_diff, seeded_load
+
+pytestmark = pytest.mark.gpu
+
+DT = np.pi / 16
+DIMX, DIMY = 4 * np.pi, 2 * np.pi
+MODES = {"onepass": ub.STORE_ONEPASS, "lean": ub.STORE_ONEPASS_LEAN}
+
+
+def _compare(xg, vg, eng, xo, vo, eno, eps, tol=1e-10):
+    tolv = tol * max(1.0, 0.1 / eps)
+    assert periodic_diff(xg[0], xo[0], DIMX).max() < tol * DIMX
+    assert periodic_diff(xg[1], xo[1], DIMY).max() < tol * DIMY
+    assert np.abs(vg - vo).max() < tolv * np.abs(vo).max()
+    assert eng.shape == eno.shape
+    assert np.abs(eng - eno).max() / np.abs(eno).max() < tol
+
+
+def _run(mesh, ntau, eps, nstep, x0, v0, w, mode, sort=None, **kw):
+    with ub.Session(mesh, ntau, eps, DT, x0.shape[1], weight=w, storage_mode=mode, **kw) as s:
+        if sort is not None:
+            s.set_sort(*sort)
+        s.upload_particles(np.asfortranarray(x0), np.asfortranarray(v0))
+        s.init_fields()
+        s.step(nstep)
+        s.synchronize()
+        x, v = s.download_particles()
+        e, rho = s.download_fields()
+        return x, v, s.energy_history(), e, rho, s.device_bytes
+
+
+@pytest.mark.parametrize("mode", sorted(MODES))
+@pytest.mark.parametrize("ntau,nx,ny,npart,nstep,eps", [
+    (16, 128, 64, 20000, 8, 0.1),       # config 1 (as shipped) at reduced particle count, all 8 steps
+    (32, 128, 128, 6000, 4, 0.1),       # config 3 shape
+    (8, 64, 32, 5003, 4, 0.1),          # one lane per particle; ragged last tile
+    (16, 128, 64, 6001, 4, 1e-2),       # ragged last tile
+    (16, 128, 64, 6000, 4, 1e-3),
+    (32, 256, 256, 3000, 2, 0.1),       # config 5 mesh
+    (32, 20, 12, 777, 3, 0.1),          # non power-of-two mesh, fewer particles than one CTA sweep
+])
+def test_onepass_session_vs_oracle(corc, mode, ntau, nx, ny, npart, nstep, eps):
+    om, x0, v0 = seeded_load(npart, nx, ny, seed=5)
+    mesh = ub.Mesh(0, DIMX, nx, 0, DIMY, ny)
+    w = DIMX * DIMY / npart
+    xo, vo = x0.copy(order="F"), v0.copy(order="F")
+    eno, _, _, emesh_o = corc.run_bupdate(om, ntau, eps, DT, nstep, xo, vo, w)
+    xg, vg, eng, emesh_g, _, _ = _run(mesh, ntau, eps, nstep, x0, v0, w, MODES[mode])
+    _compare(xg, vg, eng, xo, vo, eno, eps)
+    assert np.abs(emesh_g - emesh_o).max() < 1e-10 * np.abs(emesh_o).max()
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "bupdate_*.npz"))))
+def test_onepass_against_golden(path):
+    g = np.load(path)
+    nx, ny, ntau, nstep = int(g["nx"]), int(g["ny"]), int(g["ntau"]), int(g["nstep"])
+    eps, dt, w = float(g["eps"]), float(g["dt"]), float(g["w"])
+    assert abs(dt - DT) < 1e-15
+    mesh = ub.Mesh(0, DIMX, nx, 0, DIMY, ny)
+    xg, vg, eng, _, _, _ = _run(mesh, ntau, eps, nstep, g["x0"], g["v0"], w, ub.STORE_ONEPASS_LEAN)
+    _compare(xg, vg, eng, g["x"], g["v"], g["energy"], eps)
+
+
+def test_onepass_julia_wrap_vs_oracle(corc):
+    import oracle
+    npart, ntau, eps, nstep = 5000, 16, 0.1, 3
+    om, x0, v0 = seeded_load(npart, seed=9)
+    mesh = ub.Mesh(0, DIMX, 128, 0, DIMY, 64)
+    w = DIMX * DIMY / npart
+    xo, vo = x0.copy(order="F"), v0.copy(order="F")
+    eno, _, _, _ = corc.run_bupdate(om, ntau, eps, DT, nstep, xo, vo, w, wrap=oracle.WRAP_JULIA)
+    xg, vg, eng, _, _, _ = _run(mesh, ntau, eps, nstep, x0, v0, w, ub.STORE_ONEPASS_LEAN, wrap=ub.WRAP_JULIA)
+    _compare(xg, vg, eng, xo, vo, eno, eps)
+    assert xg[0].min() >= 0 and xg[0].max() < DIMX and xg[1].min() >= 0 and xg[1].max() < DIMY   # stored wrapped
+
+
+def test_onepass_layouts_agree_and_shrink_the_store():
+    """72 B, 48 B and the two-barrier 128 B layouts: same answer to round-off, decreasing HBM footprint"""
+    npart, ntau, eps, nstep = 6000, 32, 0.1, 3
+    _, x0, v0 = seeded_load(npart, 128, 128, seed=71)
+    mesh = ub.Mesh(0, DIMX, 128, 0, DIMY, 128)
+    w = DIMX * DIMY / npart
+    full = _run(mesh, ntau, eps, nstep, x0, v0, w, ub.STORE_FULL)
+    one = _run(mesh, ntau, eps, nstep, x0, v0, w, ub.STORE_ONEPASS, sort=(0, 3))
+    lean = _run(mesh, ntau, eps, nstep, x0, v0, w, ub.STORE_ONEPASS_LEAN, sort=(0, 3))
+    _compare(one[0], one[1], one[2], full[0], full[1], full[2], eps, tol=1e-11)
+    _compare(lean[0], lean[1], lean[2], one[0], one[1], one[2], eps, tol=1e-12)
+    assert lean[5] < one[5] < full[5]
+    assert lean[5] < npart * ntau * 48 * 1.2 + (8 << 20)
+
+
+def test_onepass_fixed_point_is_bit_reproducible_and_order_independent():
+    """fixed-point deposits make rho exactly order independent: run to run, and with the particle reordering on or off
+    (any interval, any bin size), every particle and every energy value must come out bit-identical -- which also proves
+    that downloads undo the permutation"""
+    npart, ntau, eps, nstep = 9000, 16, 0.1, 4
+    _, x0, v0 = seeded_load(npart, seed=21)
+    mesh = ub.Mesh(0, DIMX, 128, 0, DIMY, 64)
+    w = DIMX * DIMY / npart
+    kw = dict(deposit_mode=ub.DEPOSIT_FIXED_POINT)
+    ref = _run(mesh, ntau, eps, nstep, x0, v0, w, ub.STORE_ONEPASS_LEAN, sort=(0, 3), **kw)
+    for sort in [(0, 3), (1, 3), (1, 1), (2, 2), (3, 5)]:
+        r = _run(mesh, ntau, eps, nstep, x0, v0, w, ub.STORE_ONEPASS_LEAN, sort=sort, **kw)
+        for a, b in zip(ref[:5], r[:5]):
+            assert np.array_equal(a, b), sort
+    r72 = _run(mesh, ntau, eps, nstep, x0, v0, w, ub.STORE_ONEPASS, **kw)
+    assert np.array_equal(ref[2], r72[2]) or np.abs(ref[2] - r72[2]).max() < 1e-13 * np.abs(ref[2]).max()
+
+
+def test_reordering_is_invisible_to_uploads_and_downloads():
+    """step -> download x, v, e -> upload x, v, e -> step (the end-to-end pattern of bench.py) must equal stepping straight
+    through, bit for bit in fixed-point mode, although the device arrays were permuted in between"""
+    npart, ntau, eps = 7001, 32, 0.1
+    _, x0, v0 = seeded_load(npart, 128, 128, seed=13)
+    mesh = ub.Mesh(0, DIMX, 128, 0, DIMY, 128)
+    w = DIMX * DIMY / npart
+    kw = dict(weight=w, storage_mode=ub.STORE_ONEPASS_LEAN, deposit_mode=ub.DEPOSIT_FIXED_POINT)
+    with ub.Session(mesh, ntau, eps, DT, npart, **kw) as s:
+        s.upload_particles(x0, v0); s.init_fields(); s.step(4); s.synchronize()
+        xa, va = s.download_particles(); ea = s.download_particle_e(); na = s.energy_history()
+    with ub.Session(mesh, ntau, eps, DT, npart, **kw) as s:
+        s.upload_particles(x0, v0); s.init_fields(); s.step(2); s.synchronize()
+        x, v = s.download_particles(); e = s.download_particle_e()
+        s.upload_particle_e(e)                      # e first: the session must realign x and v by itself
+        s.step(1)
+        x, v = s.download_particles(); e = s.download_particle_e()
+        s.upload_particles(x, v); s.upload_particle_e(e)
+        s.step(1); s.synchronize()
+        xb, vb = s.download_particles(); eb = s.download_particle_e(); nb = s.energy_history()
+    assert np.array_equal(xa, xb) and np.array_equal(va, vb) and np.array_equal(ea, eb) and np.array_equal(na, nb)
+    # particles.e is frozen after init (bupdate.F90:93): it must still be the initial interpolation, in the caller's order
+    with ub.Session(mesh, ntau, eps, DT, npart, **kw) as s:
+        s.upload_particles(x0, v0); s.init_fields(); s.synchronize()
+        e0 = s.download_particle_e()
+    assert np.array_equal(e0, ea)
+
+
+def test_onepass_sharded_fixed_point_equals_unsharded():
+    """two half-size shards whose int64 raw meshes (predictor AND corrector, one call) are summed through the allreduce hook
+    must reproduce the unsharded run bit for bit"""
+    import torch
+
+    npart, ntau, eps, nstep = 6000, 32, 0.1, 2
+    _, x0, v0 = seeded_load(npart, 128, 128, seed=33)
+    mesh = ub.Mesh(0, DIMX, 128, 0, DIMY, 128)
+    w = DIMX * DIMY / npart
+    ref = _run(mesh, ntau, eps, nstep, x0, v0, w, ub.STORE_ONEPASS_LEAN, deposit_mode=ub.DEPOSIT_FIXED_POINT)
+    world = 2
+    barrier = threading.Barrier(world)
+    slots, results, errors, counts = [None] * world, [None] * world, [], set()
+
+    def worker(rank):
+        try:
+            lo, hi = ub.dist.shard_range(npart, rank, world)
+            s = ub.Session(mesh, ntau, eps, DT, hi - lo, weight=w, nbpart_global=npart, deposit_mode=ub.DEPOSIT_FIXED_POINT,
+                           storage_mode=ub.STORE_ONEPASS_LEAN)
+
+            def reduce(ptr, count, dtype, stream):
+                assert dtype == 1
+                counts.add(count)
+                torch.cuda.synchronize()
+                view = torch.as_tensor(ub.dist._CudaView(ptr, count, "<i8"), device="cuda")
+                slots[rank] = view
+                barrier.wait()
+                total = slots[0] + slots[1]
+                torch.cuda.synchronize()
+                barrier.wait()
+                view.copy_(total)
+                torch.cuda.synchronize()
+                barrier.wait()
+                return 0
+
+            s.set_allreduce(reduce)
+            s.upload_particles(np.asfortranarray(x0[:, lo:hi]), np.asfortranarray(v0[:, lo:hi]))
+            s.init_fields()
+            s.step(nstep)
+            s.synchronize()
+            x, v = s.download_particles()
+            e, _ = s.download_fields()
+            results[rank] = (x, v, s.energy_history(), e)
+            s.close()
+        except Exception as exc:  # pragma: no cover
+            errors.append(exc)
+            barrier.abort()
+
+    threads = [threading.Thread(target=worker, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    n = 129 * 129
+    assert counts == {n, 2 * n}                    # init: one mesh; every step: both meshes in ONE exchange
+    x = np.concatenate([results[0][0], results[1][0]], axis=1)
+    v = np.concatenate([results[0][1], results[1][1]], axis=1)
+    assert np.array_equal(x, ref[0]) and np.array_equal(v, ref[1])
+    assert np.array_equal(results[0][2], ref[2]) and np.array_equal(results[1][2], ref[2])
+    assert np.array_equal(results[0][3], ref[3])
+
+
+def test_onepass_needs_ntau_8_16_32_and_reports_it():
+    mesh = ub.Mesh(0, DIMX, 32, 0, DIMY, 16)
+    with pytest.raises(ub.UapicError, match="UAPIC_EUNSUPPORTED"):
+        ub.Session(mesh, 4, 0.1, DT, 100, storage_mode=ub.STORE_ONEPASS)
+    with ub.Session(mesh, 8, 0.1, DT, 100, storage_mode=ub.STORE_ONEPASS_LEAN) as s:
+        with pytest.raises(ub.UapicError):
+            s.set_sort(1, 40)
+        with pytest.raises(ub.UapicError):
+            s.step(1)                      # fields not initialised
+
+
+def test_onepass_config3_invariants_at_scale():
+    """size-independent properties at a config-3-shaped load too large for the oracle (2e6 particles, device generated):
+    total charge is neutralised to round-off, the energy history is finite and smooth, sum(v) matches the downloaded
+    velocities, and the 48 B layout reproduces the 128 B two-barrier kernels to 1e-10"""
+    npart, ntau, eps, nstep = 2_000_000, 32, 0.1, 3
+    mesh = ub.Mesh(0, DIMX, 128, 0, DIMY, 128)
+    out = {}
+    for name, mode in (("full", ub.STORE_FULL), ("lean", ub.STORE_ONEPASS_LEAN)):
+        with ub.Session(mesh, ntau, eps, DT, npart, storage_mode=mode) as s:
+            s.generate_particles("landau", seed=11)
+            s.init_fields()
+            s.step(nstep)
+            s.synchronize()
+            x, v = s.download_particles()
+            e, rho = s.download_fields()
+            out[name] = (x, v, s.energy_history(), e, rho, s.sum_v())
+    x, v, en, e, rho, sv = out["lean"]
+    dx, dy = DIMX / 128, DIMY / 128
+    assert abs(rho[:128, :128].sum() * dx * dy) < 1e-9
+    assert np.isfinite(en).all() and en.shape == (1 + 2 * nstep,) and en.min() > 0
+    assert np.allclose(sv, v.sum(axis=1), rtol=1e-9, atol=1e-6)
+    _compare(x, v, en, out["full"][0], out["full"][1], out["full"][2], eps)
