@@ -484,7 +484,8 @@ int session_solve(uapic_session *s, const RhoAcc &acc, DevBuf &emesh, DevBuf &eh
     if (s->n_energy >= s->cap_energy) return fail(UAPIC_ESTATE, "energy history full (%lld entries)", (long long)s->cap_energy);
     PoissonWork pw{s->rk.as<double2>(), s->ek.as<double2>()};
     CU(launch_poisson(s->lc, s->m, pw, s->rho.as<double>(), emesh.as<double>(), s->energy.as<double>() + s->n_energy));
-    CU(launch_extend_emesh(s->lc, s->m, emesh.as<double>(), ehalo.as<double2>()));
+    if (s->onepass) CU(launch_extend_emesh_tiled(s->lc, s->m, emesh.as<double>(), ehalo.as<double2>()));
+    else CU(launch_extend_emesh(s->lc, s->m, emesh.as<double>(), ehalo.as<double2>()));
     s->n_energy++;
     return UAPIC_OK;
 }
@@ -602,11 +603,11 @@ int uapic_session_create(const uapic_config_t *cfg, uapic_session_t **out) {
     if (onepass) {
         if (!rc) rc = session_alloc(s, s->rec, 64 * (np ? np : 1));
         if (!rc) rc = session_alloc(s, s->emesh_p, 16 * nrho);
-        if (!rc) rc = session_alloc(s, s->ehalo_p, 16 * ehalo_nodes(s->m));
+        if (!rc) rc = session_alloc(s, s->ehalo_p, 16 * ehalo_tiled_nodes(s->m));
     }
     if (!rc) rc = session_alloc(s, s->rho, 8 * nrho);
     if (!rc) rc = session_alloc(s, s->emesh, 16 * nrho);
-    if (!rc) rc = session_alloc(s, s->ehalo, 16 * ehalo_nodes(s->m));
+    if (!rc) rc = session_alloc(s, s->ehalo, 16 * (onepass ? ehalo_tiled_nodes(s->m) : ehalo_nodes(s->m)));
     if (!rc) rc = session_alloc(s, s->rk, 16 * nk);
     if (!rc) rc = session_alloc(s, s->ek, 32 * nk);
     if (!rc) rc = session_alloc(s, s->energy, 8 * (size_t)s->cap_energy);

@@ -64,6 +64,45 @@ DEVINL void gather_fast(const MeshDev &m, const double2 *__restrict__ ehalo, con
     e1 = s1; e2 = s2;
 }
 
+// ---- tiled halo copy of E for the one-pass kernels -------------------------------------------------------------
+// Same nodes as the linear halo copy, i in [-2, nx+3], j in [-2, ny+3], but every 128-byte line holds a 2 (x) by 4 (y)
+// block of nodes: node (I, J) = (i+2, j+2) lives at [ (J/4 * ntx + I/2) * 8 + (J%4) * 2 + I%2 ].
+// Why: a gather instruction reads the SAME tap for the 32 tau samples of one particle, i.e. 32 points on its gyro-orbit;
+// the L1 data pipe spends one wavefront per distinct line those points fall in (ncu: 8.5 tag lookups, 7.3 wavefronts per
+// LDG.128 with 8 x 1 lines; a seeded model of the orbits reproduces 8.47).  Compact 2 x 4 blocks cut that to 5.2.
+DEVINL int halo_tiled_ntx(const MeshDev &m) { return (m.nx + 6 + 1) >> 1; }
+DEVINL int halo_tiled_nty(const MeshDev &m) { return (m.ny + 6 + 3) >> 2; }
+DEVINL int halo_tiled_index(int ntx, int I, int J) { return (((J >> 2) * ntx + (I >> 1)) << 3) + ((J & 3) << 1) + (I & 1); }
+
+DEVINL void gather_tiled(const MeshDev &m, const double2 *__restrict__ ehalo, const Cell &c, double &e1, double &e2) {
+    double cx[6], cy[6];
+    m6_weights_fast(c.dpx, cx);
+    m6_weights_fast(c.dpy, cy);
+    const int ntx8 = halo_tiled_ntx(m) << 3;
+    const int p = c.i & 1;
+    int q = c.j & 3;
+    int roff = (c.j >> 2) * ntx8 + (q << 1) + ((c.i >> 1) << 3) + p;      // node (i-2, j-2)
+    const int step_odd = p ? 7 : 1;                                        // from an even tap to the next (odd) one
+    double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+    for (int b = 0; b < 6; ++b) {
+        const double2 *re = ehalo + roff;          // taps 0, 2, 4 at +0, +8, +16
+        const double2 *ro = re + step_odd;         // taps 1, 3, 5
+        double r1 = 0.0, r2 = 0.0;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+            const double2 ev = __ldg(((a & 1) ? ro : re) + 8 * (a >> 1));
+            r1 = fma(cx[a], ev.x, r1);
+            r2 = fma(cx[a], ev.y, r2);
+        }
+        s1 = fma(cy[b], r1, s1);
+        s2 = fma(cy[b], r2, s2);
+        roff += (q == 3) ? ntx8 - 6 : 2;
+        q = (q + 1) & 3;
+    }
+    e1 = s1; e2 = s2;
+}
+
 // f_m6 without branches (q >= 0): the three pieces of compute_rho_m6.F90:33-41 are the same sum of truncated powers
 DEVINL double f_m6_branchless(double q) {
     const double a = fmax(3.0 - q, 0.0), b = fmax(2.0 - q, 0.0), c = fmax(1.0 - q, 0.0);

@@ -51,6 +51,9 @@ bool poisson_size_supported(int n);
 // periodic halo copy of the E mesh for the fused gathers: node (i,j), i in [-2,nx+3], j in [-2,ny+3], holds E(i mod nx, j mod ny)
 inline size_t ehalo_nodes(const MeshDev &m) { return (size_t)(m.nx + 6) * (size_t)(m.ny + 6); }
 cudaError_t launch_extend_emesh(const LaunchCtx &c, const MeshDev &m, const double *emesh, double2 *ehalo);
+// the same nodes with every 128-byte line holding a 2 x 4 block of nodes (one-pass kernels; layout in uapic_fast.cuh)
+inline size_t ehalo_tiled_nodes(const MeshDev &m) { return (size_t)((m.nx + 6 + 1) >> 1) * (size_t)((m.ny + 6 + 3) >> 2) * 8; }
+cudaError_t launch_extend_emesh_tiled(const LaunchCtx &c, const MeshDev &m, const double *emesh, double2 *ehalo);
 
 // ---- fused phase kernels (session path) -----------------------------------------------------------------------
 struct PhaseParams {
@@ -84,7 +87,7 @@ struct OnepassParams {
     double2 *x;            // (2,np): read and rewritten (corrector position) by A
     double2 *v;            // (2,np): read by A, written by B
     const double2 *ep;     // (2,np): particles.e, frozen after init
-    const double2 *ehalo;  // periodic halo copy of the field to gather: E_n for A, E_pred for B
+    const double2 *ehalo;  // TILED periodic halo copy of the field to gather: E_n for A, E_pred for B
     char *store;           // np * onepass_store_bytes_per_particle(ntau, full)
     double *rec;           // np * 8 doubles: t, b, 1/b, bracket sums (2), cos(t/eps), sin(t/eps), unused
     RhoAcc rho_p, rho_c;   // raw accumulation meshes of the predictor and the corrector deposit (A only)

@@ -490,6 +490,21 @@ __global__ void __launch_bounds__(kBlock) k_extend_emesh(MeshDev m, const double
     }
 }
 
+// the same halo copy in the 2 x 4-node tiled layout of uapic_fast.cuh (gather_tiled)
+__global__ void __launch_bounds__(kBlock) k_extend_emesh_tiled(MeshDev m, const double2 *__restrict__ emesh, double2 *__restrict__ ehalo) {
+    const int ntx = (m.nx + 6 + 1) >> 1, nty = (m.ny + 6 + 3) >> 2;
+    const int n = ntx * nty * 8;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
+        const int tile = q >> 3, w = q & 7;
+        const int tj = tile / ntx, ti = tile - tj * ntx;
+        int i = 2 * ti + (w & 1) - 2, j = 4 * tj + (w >> 1) - 2;
+        // nodes of the padding beyond [-2, n+3] wrap as well: never read, but defined
+        i %= m.nx; i += (i < 0) ? m.nx : 0;
+        j %= m.ny; j += (j < 0) ? m.ny : 0;
+        ehalo[q] = emesh[i + m.ld * j];
+    }
+}
+
 // src/poisson.jl:80-81 : sum over the ghosted array of e1^2+e2^2, times dx*dy (fixed summation order)
 __global__ void __launch_bounds__(kMeshBlock) k_energy(MeshDev m, const double2 *__restrict__ emesh, double *energy) {
     __shared__ double sh[kMeshBlock];
@@ -718,6 +733,14 @@ cudaError_t launch_extend_emesh(const LaunchCtx &c, const MeshDev &m, const doub
     if (m.nx < 4 || m.ny < 4) return cudaErrorInvalidValue;
     const int n = (m.nx + 6) * (m.ny + 6);
     k_extend_emesh<<<grid_for(c, n, kBlock), kBlock, 0, c.stream>>>(m, reinterpret_cast<const double2 *>(emesh), ehalo);
+    count(c);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_extend_emesh_tiled(const LaunchCtx &c, const MeshDev &m, const double *emesh, double2 *ehalo) {
+    if (m.nx < 4 || m.ny < 4) return cudaErrorInvalidValue;
+    const int n = (int)ehalo_tiled_nodes(m);
+    k_extend_emesh_tiled<<<grid_for(c, n, kBlock), kBlock, 0, c.stream>>>(m, reinterpret_cast<const double2 *>(emesh), ehalo);
     count(c);
     return cudaGetLastError();
 }

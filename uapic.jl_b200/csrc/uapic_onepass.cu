@@ -54,7 +54,7 @@ constexpr int kOpBlock = 128;                  // 4 warps per CTA
 constexpr int kGatherUnroll = UAPIC_OP_GATHER_UNROLL;
 constexpr int kOpWarps = kOpBlock / 32;
 constexpr int kRow = 36;                       // padded row (double2 units) of the per-warp exchange area: conflict-free
-constexpr int kTab = 96;                       // 3 tables of 32 double2
+constexpr int kTab = 108;                      // cos/sin table (32) + two [4][9]-padded tables: rows in distinct bank groups
 constexpr int kWarpSmA = 8 * kRow + 4 * 32 + 16 * 32;   // exchange rows + interv stash + yhat stash (double2 units)
 constexpr int kWarpSmB = 8 * kRow;
 
@@ -88,13 +88,13 @@ template <int G> struct OpLane {
     int src_neg, src_neg0;      // ... block G-1-kappa / (G-kappa) mod G  (conjugate partners)
     double l0;                  // l of the lane's first mode
     const double2 *cs;          // [N]    (cos tau_n, sin tau_n)                         ua_type.F90:60-62
-    const double2 *tw;          // [G][8] exp(-2 pi i g k1 / N)
-    const double2 *il;          // [N]    (1/l_k, 1/l_k^2), zero for k = 0               ua_type.F90:51-56
+    const double2 *tw;          // [G][9] exp(-2 pi i g k1 / N), row g (stride 9: the G lanes of a group hit distinct banks)
+    const double2 *il;          // [G][9] (1/l_k, 1/l_k^2) of mode k = 8*kappa + k1, row kappa; zero for k = 0   ua_type.F90:51-56
 
     DEVINL static int kappa_of(int g) { return G == 4 ? (((g & 1) << 1) | (g >> 1)) : g; }
     DEVINL static double lmode(int k) { return (double)(k < N / 2 ? k : k - N); }
 
-    // tab: 96 double2 of shared memory; every thread of the CTA must call; ends with __syncthreads
+    // tab: kTab double2 of shared memory; every thread of the CTA must call; ends with __syncthreads
     DEVINL void init(int lane_, double2 *tab) {
         lane = lane_;
         g = lane & (G - 1);
@@ -107,7 +107,7 @@ template <int G> struct OpLane {
         src_neg = kappa_of(G - 1 - kap);
         src_neg0 = kappa_of((G - kap) & (G - 1));
         l0 = lmode(8 * kap);
-        cs = tab; tw = tab + 32; il = tab + 64;
+        cs = tab; tw = tab + 32 + 9 * g; il = tab + 68 + 9 * kap;
         const int i = threadIdx.x;
         if (i < N) {
             double s, c;
@@ -115,9 +115,9 @@ template <int G> struct OpLane {
             tab[i] = make_double2(c, s);
             const int gg = i >> 3, k1 = i & 7;
             sincospi(-2.0 * (double)(gg * k1) / (double)N, &s, &c);
-            tab[32 + i] = make_double2(c, s);
+            tab[32 + 9 * gg + k1] = make_double2(c, s);
             const double l = lmode(i);
-            tab[64 + i] = (i == 0) ? make_double2(0.0, 0.0) : make_double2(1.0 / l, 1.0 / (l * l));
+            tab[68 + 9 * gg + k1] = (i == 0) ? make_double2(0.0, 0.0) : make_double2(1.0 / l, 1.0 / (l * l));
         }
         __syncthreads();
     }
@@ -146,7 +146,7 @@ template <int G> DEVINL void fwdN(cd (&a)[8], const OpLane<G> &L) {
     fft8<-1>(a);
     if (G > 1) {
 #pragma unroll
-        for (int k1 = 1; k1 < 8; ++k1) { const double2 w = L.tw[8 * L.g + k1]; a[k1] = cmul(a[k1], mk(w.x, w.y)); }
+        for (int k1 = 1; k1 < 8; ++k1) { const double2 w = L.tw[k1]; a[k1] = cmul(a[k1], mk(w.x, w.y)); }
     }
     if (G == 4) {
         xbfly(a, 2, L.sg2);
@@ -166,7 +166,7 @@ template <int G> DEVINL void bwdN(cd (&a)[8], const OpLane<G> &L) {
     }
     if (G > 1) {
 #pragma unroll
-        for (int k1 = 1; k1 < 8; ++k1) { const double2 w = L.tw[8 * L.g + k1]; a[k1] = cmulc(a[k1], mk(w.x, w.y)); }
+        for (int k1 = 1; k1 < 8; ++k1) { const double2 w = L.tw[k1]; a[k1] = cmulc(a[k1], mk(w.x, w.y)); }
     }
     fft8<+1>(a);
 }
@@ -197,7 +197,7 @@ template <int G> DEVINL void elt_modes(const OpLane<G> &L, double t, double eps,
 // pl, ql/t of ua_steps.F90:60-66 for mode (lane, k1); il = (1/l, 1/l^2)
 template <int G>
 DEVINL void pl_qt(const OpLane<G> &L, int k1, double t, double rt, double eps, cd elt, cd &pl, cd &qt) {
-    const double2 il = L.il[8 * L.kap + k1];
+    const double2 il = L.il[k1];
     const double l = L.lf(k1);
     pl = mk(-eps * elt.im * il.x, eps * (elt.re - 1.0) * il.x);
     qt = mk(eps * eps * (1.0 - elt.re) * il.y * rt, -eps * fma(eps, elt.im, l * t) * il.y * rt);
@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(kOpBlock, UAPIC_OP_MINB_A) k_onepass_a(OpDev D
             const double2 pos = gx[idx];
             double xw, yw, e1, e2;
             const Cell cell = cell_fast(P.m, D.f, pos.x, pos.y, P.wrap, xw, yw);
-            gather_fast(P.m, P.ehalo, cell, e1, e2);
+            gather_tiled(P.m, P.ehalo, cell, e1, e2);
             gx[idx] = make_double2(e1, e2);
         }
         OP_STEP();
@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(kOpBlock, UAPIC_OP_MINB_A) k_onepass_a(OpDev D
             cd c1[8], c2[8], cs1 = mk(0.0, 0.0), cs2 = mk(0.0, 0.0);
 #pragma unroll
             for (int k1 = 0; k1 < 8; ++k1) {
-                const double s = 0.5 * invN * L.il[8 * L.kap + k1].x;
+                const double s = 0.5 * invN * L.il[k1].x;
                 c1[k1] = mk(s * (z[k1].im - zp[k1].im), -s * (z[k1].re + zp[k1].re));
                 c2[k1] = mk(-s * (z[k1].re - zp[k1].re), -s * (z[k1].im + zp[k1].im));
                 cs1 = cadd(cs1, c1[k1]); cs2 = cadd(cs2, c2[k1]);
@@ -592,7 +592,7 @@ __global__ void __launch_bounds__(kOpBlock, UAPIC_OP_MINB_B) k_onepass_b(OpDev D
             // ---- gather E_pred at the predicted samples (interpolation_m6.F90:83-189) ----
             double xw, yw, e1, e2;
             const Cell cell = cell_fast(P.m, D.f, xs.x, xs.y, P.wrap, xw, yw);
-            gather_fast(P.m, P.ehalo, cell, e1, e2);
+            gather_tiled(P.m, P.ehalo, cell, e1, e2);
             cd gy1, gy2;
             fy_time(csn.x, csn.y, rb, iv, mk(ya.x, ya.y), mk(yb.x, yb.y), e1, e2, gy1, gy2);     // :177-183
             // Re sum_n gy(tau_n) W_n
