@@ -34,10 +34,10 @@ namespace uapic {
 namespace {
 
 #ifndef UAPIC_OP_MINB_A
-#define UAPIC_OP_MINB_A 2
+#define UAPIC_OP_MINB_A 2     // 2 x 6 warps at 168 registers: measured best (8 warps at 255: -7 %; 12 x 1: -6 %)
 #endif
 #ifndef UAPIC_OP_MINB_B
-#define UAPIC_OP_MINB_B 4
+#define UAPIC_OP_MINB_B 2
 #endif
 #ifndef UAPIC_OP_LOCKSTEP
 #define UAPIC_OP_LOCKSTEP 1
@@ -50,9 +50,14 @@ namespace {
 #ifndef UAPIC_OP_GATHER_UNROLL
 #define UAPIC_OP_GATHER_UNROLL 1
 #endif
-constexpr int kOpBlock = 128;                  // 4 warps per CTA
+#ifndef UAPIC_OP_BLOCK_A
+#define UAPIC_OP_BLOCK_A 192
+#endif
+#ifndef UAPIC_OP_BLOCK_B
+#define UAPIC_OP_BLOCK_B 256
+#endif
+constexpr int kOpBlockA = UAPIC_OP_BLOCK_A, kOpBlockB = UAPIC_OP_BLOCK_B;      // threads per CTA of the two kernels
 constexpr int kGatherUnroll = UAPIC_OP_GATHER_UNROLL;
-constexpr int kOpWarps = kOpBlock / 32;
 constexpr int kRow = 36;                       // padded row (double2 units) of the per-warp exchange area: conflict-free
 constexpr int kTab = 108;                      // cos/sin table (32) + two [4][9]-padded tables: rows in distinct bank groups
 constexpr int kWarpSmA = 8 * kRow + 4 * 32 + 16 * 32;   // exchange rows + interv stash + yhat stash (double2 units)
@@ -287,8 +292,9 @@ template <int N, bool FULL> struct StoreMap {
 
 // =================================================================================================
 template <int G, bool FULL>
-__global__ void __launch_bounds__(kOpBlock, UAPIC_OP_MINB_A) k_onepass_a(OpDev D) {
+__global__ void __launch_bounds__(kOpBlockA, UAPIC_OP_MINB_A) k_onepass_a(OpDev D) {
     constexpr int N = 8 * G, PW = 32 / G, PPI = 32 / N;     // particles per warp tile / per gather iteration
+    constexpr int kOpWarps = kOpBlockA / 32;
     using SM = StoreMap<N, FULL>;
     const OnepassParams &P = D.p;
     extern __shared__ double2 smem[];
@@ -531,8 +537,9 @@ __global__ void __launch_bounds__(kOpBlock, UAPIC_OP_MINB_A) k_onepass_a(OpDev D
 
 // =================================================================================================
 template <int G, bool FULL>
-__global__ void __launch_bounds__(kOpBlock, UAPIC_OP_MINB_B) k_onepass_b(OpDev D) {
+__global__ void __launch_bounds__(kOpBlockB, UAPIC_OP_MINB_B) k_onepass_b(OpDev D) {
     constexpr int N = 8 * G, PW = 32 / G, PPI = 32 / N;
+    constexpr int kOpWarps = kOpBlockB / 32;
     using SM = StoreMap<N, FULL>;
     const OnepassParams &P = D.p;
     extern __shared__ double2 smem[];
@@ -604,9 +611,9 @@ __global__ void __launch_bounds__(kOpBlock, UAPIC_OP_MINB_B) k_onepass_b(OpDev D
     }
 }
 
-inline int op_grid(const LaunchCtx &c, int64_t np, int ntau, int minb) {
-    const int pw = 32 / (ntau / 8);
-    int64_t need = ((np + pw - 1) / pw + kOpWarps - 1) / kOpWarps;
+inline int op_grid(const LaunchCtx &c, int64_t np, int ntau, int minb, int block) {
+    const int pw = 32 / (ntau / 8), warps = block / 32;
+    int64_t need = ((np + pw - 1) / pw + warps - 1) / warps;
     const int64_t cap = (int64_t)c.sm_count * minb;
     if (need < 1) need = 1;
     return (int)(need < cap ? need : cap);
@@ -622,10 +629,10 @@ OpDev make_opdev(const OnepassParams &p) {
     return D;
 }
 
-template <typename K> cudaError_t op_launch(K kernel, const LaunchCtx &c, const OpDev &D, int grid, size_t smem) {
+template <typename K> cudaError_t op_launch(K kernel, const LaunchCtx &c, const OpDev &D, int grid, int block, size_t smem) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kernel<<<grid, kOpBlock, smem, c.stream>>>(D);
+    kernel<<<grid, block, smem, c.stream>>>(D);
     if (c.launches) *c.launches += 1;
     return cudaGetLastError();
 }
@@ -635,31 +642,31 @@ template <typename K> cudaError_t op_launch(K kernel, const LaunchCtx &c, const 
 bool onepass_ntau_supported(int ntau) { return ntau == 8 || ntau == 16 || ntau == 32; }
 size_t onepass_store_bytes_per_particle(int ntau, int full) { return (size_t)(full ? 72 : 48) * (size_t)ntau; }
 
-#define UAPIC_OP_DISPATCH(KERNEL, MINB, SMEM)                                                              \
-    switch (p.ntau) {                                                                                      \
-        case 8:  return p.full ? op_launch(KERNEL<1, true>, c, D, op_grid(c, p.np, 8, MINB), SMEM)         \
-                               : op_launch(KERNEL<1, false>, c, D, op_grid(c, p.np, 8, MINB), SMEM);       \
-        case 16: return p.full ? op_launch(KERNEL<2, true>, c, D, op_grid(c, p.np, 16, MINB), SMEM)        \
-                               : op_launch(KERNEL<2, false>, c, D, op_grid(c, p.np, 16, MINB), SMEM);      \
-        case 32: return p.full ? op_launch(KERNEL<4, true>, c, D, op_grid(c, p.np, 32, MINB), SMEM)        \
-                               : op_launch(KERNEL<4, false>, c, D, op_grid(c, p.np, 32, MINB), SMEM);      \
-        default: return cudaErrorInvalidValue;                                                             \
+#define UAPIC_OP_DISPATCH(KERNEL, MINB, BLOCK, SMEM)                                                               \
+    switch (p.ntau) {                                                                                              \
+        case 8:  return p.full ? op_launch(KERNEL<1, true>, c, D, op_grid(c, p.np, 8, MINB, BLOCK), BLOCK, SMEM)   \
+                               : op_launch(KERNEL<1, false>, c, D, op_grid(c, p.np, 8, MINB, BLOCK), BLOCK, SMEM); \
+        case 16: return p.full ? op_launch(KERNEL<2, true>, c, D, op_grid(c, p.np, 16, MINB, BLOCK), BLOCK, SMEM)  \
+                               : op_launch(KERNEL<2, false>, c, D, op_grid(c, p.np, 16, MINB, BLOCK), BLOCK, SMEM);\
+        case 32: return p.full ? op_launch(KERNEL<4, true>, c, D, op_grid(c, p.np, 32, MINB, BLOCK), BLOCK, SMEM)  \
+                               : op_launch(KERNEL<4, false>, c, D, op_grid(c, p.np, 32, MINB, BLOCK), BLOCK, SMEM);\
+        default: return cudaErrorInvalidValue;                                                                     \
     }
 
 cudaError_t launch_onepass_a(const LaunchCtx &c, const OnepassParams &p) {
     if (p.np <= 0) return cudaSuccess;
     if (p.m.nx < 4 || p.m.ny < 4) return cudaErrorInvalidValue;
     const OpDev D = make_opdev(p);
-    const size_t smem = sizeof(double2) * (size_t)(kTab + kOpWarps * kWarpSmA);
-    UAPIC_OP_DISPATCH(k_onepass_a, UAPIC_OP_MINB_A, smem)
+    const size_t smem = sizeof(double2) * (size_t)(kTab + (kOpBlockA / 32) * kWarpSmA);
+    UAPIC_OP_DISPATCH(k_onepass_a, UAPIC_OP_MINB_A, kOpBlockA, smem)
 }
 
 cudaError_t launch_onepass_b(const LaunchCtx &c, const OnepassParams &p) {
     if (p.np <= 0) return cudaSuccess;
     if (p.m.nx < 4 || p.m.ny < 4) return cudaErrorInvalidValue;
     const OpDev D = make_opdev(p);
-    const size_t smem = sizeof(double2) * (size_t)(kTab + kOpWarps * kWarpSmB);
-    UAPIC_OP_DISPATCH(k_onepass_b, UAPIC_OP_MINB_B, smem)
+    const size_t smem = sizeof(double2) * (size_t)(kTab + (kOpBlockB / 32) * kWarpSmB);
+    UAPIC_OP_DISPATCH(k_onepass_b, UAPIC_OP_MINB_B, kOpBlockB, smem)
 }
 
 }  // namespace uapic
