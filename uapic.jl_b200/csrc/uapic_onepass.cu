@@ -60,7 +60,7 @@ constexpr int kOpBlockA = UAPIC_OP_BLOCK_A, kOpBlockB = UAPIC_OP_BLOCK_B;      /
 constexpr int kGatherUnroll = UAPIC_OP_GATHER_UNROLL;
 constexpr int kRow = 36;                       // padded row (double2 units) of the per-warp exchange area: conflict-free
 constexpr int kTab = 108;                      // cos/sin table (32) + two [4][9]-padded tables: rows in distinct bank groups
-constexpr int kWarpSmA = 8 * kRow + 4 * 32 + 16 * 32;   // exchange rows + interv stash + yhat stash (double2 units)
+constexpr int kWarpSmA = 8 * kRow + 4 * kRow + 16 * 32;  // exchange rows + sin-product rows + yhat stash (double2 units)
 constexpr int kWarpSmB = 8 * kRow;
 
 constexpr double kRsqrt2 = 0.70710678118654752440;
@@ -300,8 +300,8 @@ __global__ void __launch_bounds__(kOpBlockA, UAPIC_OP_MINB_A) k_onepass_a(OpDev 
     extern __shared__ double2 smem[];
     const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double2 *gx = smem + kTab + wib * kWarpSmA;    // [8][kRow]  positions -> E at the samples
-    double2 *ivs = gx + 8 * kRow;                  // [4][32]    interv pairs
-    double2 *yhs = ivs + 4 * 32;                   // [16][32]   yhat1[k1] at slot k1, yhat2[k1] at slot 8+k1
+    double *sps = reinterpret_cast<double *>(gx + 8 * kRow);   // [8][kRow] doubles: sin(xt1) sin(xt2) at the samples (row stride 36: conflict-free both ways)
+    double2 *yhs = gx + 12 * kRow;                 // [16][32]   yhat1[k1] at slot k1, yhat2[k1] at slot 8+k1
     OpLane<G> L; L.init(lane, smem);
     const int g = L.g, pin = lane / G, gbase = lane - g;
     const double eps = P.eps, inv_eps = D.inv_eps, invN = 1.0 / (double)N;
@@ -324,41 +324,37 @@ __global__ void __launch_bounds__(kOpBlockA, UAPIC_OP_MINB_A) k_onepass_a(OpDev 
         const double t = P.dt * b;                                           // :55
         const double rb = 1.0 / b, rt = 1.0 / t;
         const double vxb = vx * rb, vyb = vy * rb;                           // :73-74
-        double xt1[8], xt2[8];
 #pragma unroll
         for (int s = 0; s < 8; ++s) {
             const double2 c = L.cs[g + G * s];
-            xt1[s] = x1 + eps * (c.y * vxb - c.x * vyb) + eps * vyb;         // :78-81
-            xt2[s] = x2 + eps * (c.y * vyb + c.x * vxb) - eps * vxb;         // :79-82
-            gx[s * kRow + lane] = make_double2(xt1[s], xt2[s]);
+            const double xt1 = x1 + eps * (c.y * vxb - c.x * vyb) + eps * vyb;   // :78-81
+            const double xt2 = x2 + eps * (c.y * vyb + c.x * vxb) - eps * vxb;   // :79-82
+            gx[s * kRow + lane] = make_double2(xt1, xt2);
         }
         OP_STEP();
-        // ---- gather E_n at the samples, lane = sample (interpolation_m6.F90:83-189) ----
+        // ---- gather E_n at the samples, lane = sample (interpolation_m6.F90:83-189); the sines of :87 ride along so that
+        //      the 16 sin() of a lane sit in this rolled loop instead of the unrolled code below ----
 #pragma unroll (kGatherUnroll)
         for (int j = 0; j < 8; ++j) {
             const int n = lane & (N - 1), pp = j * PPI + lane / N;
-            const int idx = (n / G) * kRow + pp * G + (n & (G - 1));
-            const double2 pos = gx[idx];
+            const int col = pp * G + (n & (G - 1)), row = n / G;
+            const double2 pos = gx[row * kRow + col];
             double xw, yw, e1, e2;
             const Cell cell = cell_fast(P.m, D.f, pos.x, pos.y, P.wrap, xw, yw);
             gather_tiled(P.m, P.ehalo, cell, e1, e2);
-            gx[idx] = make_double2(e1, e2);
+            gx[row * kRow + col] = make_double2(e1, e2);
+            sps[row * kRow + col] = sin(pos.x) * sin(pos.y);
         }
         OP_STEP();
 
         cd z[8];
-        {
-            double iv[8];
 #pragma unroll
-            for (int s = 0; s < 8; ++s) {
-                const double2 c = L.cs[g + G * s];
-                iv[s] = (1.0 + 0.5 * sin(xt1[s]) * sin(xt2[s]) - b) * inv_eps;              // :87
-                const double exb = ((c.x * vy - c.y * vx) * iv[s] + ee.x) * rb;             // :89
-                const double eyb = ((-c.x * vx - c.y * vy) * iv[s] + ee.y) * rb;            // :90
-                z[s] = mk(c.x * exb - c.y * eyb, c.y * exb + c.x * eyb);                    // r1 + i r2   :92-93
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) ivs[q * 32 + lane] = make_double2(iv[2 * q], iv[2 * q + 1]);
+        for (int s = 0; s < 8; ++s) {
+            const double2 c = L.cs[g + G * s];
+            const double iv = (1.0 + 0.5 * sps[s * kRow + lane] - b) * inv_eps;       // :87
+            const double exb = ((c.x * vy - c.y * vx) * iv + ee.x) * rb;                    // :89
+            const double eyb = ((-c.x * vx - c.y * vy) * iv + ee.y) * rb;                   // :90
+            z[s] = mk(c.x * exb - c.y * eyb, c.y * exb + c.x * eyb);                        // r1 + i r2   :92-93
         }
         fwdN<G>(z, L);                                                       // :97-98, both real signals at once
         // split the two spectra, filter (:100-103; the k = 0 coefficient cancels in :109-110 and is dropped)
@@ -457,8 +453,8 @@ __global__ void __launch_bounds__(kOpBlockA, UAPIC_OP_MINB_A) k_onepass_a(OpDev 
 #pragma unroll
         for (int s = 0; s < 8; ++s) {
             const double2 c = L.cs[g + G * s], et = gx[s * kRow + lane];
-            const double2 ivp = ivs[(s >> 1) * 32 + lane];
-            fy_time(c.x, c.y, rb, (s & 1) ? ivp.y : ivp.x, y1[s], y2[s], et.x, et.y, y1[s], y2[s]);
+            const double iv = (1.0 + 0.5 * sps[s * kRow + lane] - b) * inv_eps;       // :177, same as :87
+            fy_time(c.x, c.y, rb, iv, y1[s], y2[s], et.x, et.y, y1[s], y2[s]);
         }
         OP_STEP();
         fwdN<G>(y1, L);                                                      // :189-190
