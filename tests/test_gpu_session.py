@@ -19,6 +19,17 @@ from conftest import GOLDEN, periodic_diff, seeded_load
 
 pytestmark = pytest.mark.gpu
 
+
+@pytest.fixture(autouse=True, scope="module")
+def _two_barrier_kernels_by_default():
+    """this module targets the two-barrier kernels (uapic_fused.cu); the one-pass kernels, which a Session picks by default
+    for ntau = 8, 16, 32, have their own module (test_gpu_onepass.py)"""
+    import uapic_b200.session as sess
+    old = sess.DEFAULT_STORAGE
+    sess.DEFAULT_STORAGE = ub.STORE_FULL
+    yield
+    sess.DEFAULT_STORAGE = old
+
 DT = np.pi / 16
 DIMX, DIMY = 4 * np.pi, 2 * np.pi
 

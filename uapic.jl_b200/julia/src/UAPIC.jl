@@ -26,6 +26,10 @@ const WRAP_FORTRAN = Cint(0)
 const WRAP_JULIA   = Cint(1)
 const DEPOSIT_FP64_ATOMIC = Cint(0)
 const DEPOSIT_FIXED_POINT = Cint(1)
+const STORE_FULL         = Cint(0)   # two field barriers per step, 128 B per particle-tau between them
+const STORE_HYBRID       = Cint(1)   # ... 16 B, predictor recomputed
+const STORE_ONEPASS      = Cint(2)   # one field barrier per step, 72 B per particle-tau across it
+const STORE_ONEPASS_LEAN = Cint(3)   # ... 48 B
 
 struct UAPICError <: Exception
     code :: Cint
@@ -352,9 +356,12 @@ mutable struct Session
     handle :: Ptr{Cvoid}
     mesh   :: Mesh
     nbpart :: Int64
+    # storage_mode: STORE_ONEPASS_LEAN (one field barrier per step, 48 B per particle-tau across it) for ntau = 8, 16, 32,
+    # STORE_FULL (the literal two-barrier sequence, 128 B) otherwise; see include/uapic_b200.h
     function Session(mesh::Mesh, ntau, ε, dt, nbpart; weight = (mesh.xmax - mesh.xmin) * (mesh.ymax - mesh.ymin) / nbpart,
-                     nbpart_global = nbpart, wrap = WRAP_JULIA, deposit_mode = DEPOSIT_FP64_ATOMIC, device = 0)
-        cfg = CConfig(CMesh(mesh), ntau, wrap, deposit_mode, 0, 0, device, ε, dt, nbpart, weight, weight * nbpart_global, C_NULL)
+                     nbpart_global = nbpart, wrap = WRAP_JULIA, deposit_mode = DEPOSIT_FP64_ATOMIC, device = 0,
+                     storage_mode = ntau in (8, 16, 32) ? STORE_ONEPASS_LEAN : STORE_FULL)
+        cfg = CConfig(CMesh(mesh), ntau, wrap, deposit_mode, 0, storage_mode, device, ε, dt, nbpart, weight, weight * nbpart_global, C_NULL)
         h = Ref{Ptr{Cvoid}}(C_NULL)
         check(ccall((:uapic_session_create, libuapic), Cint, (Ref{CConfig}, Ref{Ptr{Cvoid}}), cfg, h))
         s = new(h[], mesh, nbpart)
@@ -363,6 +370,10 @@ mutable struct Session
     end
 end
 
+# reorder the device copies of the particle arrays by coarse mesh bin every `interval` steps (0 = never); uploads and
+# downloads stay in the caller's particle order
+set_sort!(s::Session, interval, bin_cells_log2 = 3) =
+    check(ccall((:uapic_session_set_sort, libuapic), Cint, (Ptr{Cvoid}, Cint, Cint), s.handle, interval, bin_cells_log2))
 upload_particles!(s::Session, p::Particles) =
     check(ccall((:uapic_session_upload_particles, libuapic), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}), s.handle, p.x, p.v))
 init_fields!(s::Session) = check(ccall((:uapic_session_init_fields, libuapic), Cint, (Ptr{Cvoid},), s.handle))

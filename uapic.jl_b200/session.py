@@ -17,10 +17,25 @@ from .api import Mesh
 _dp = C.POINTER(C.c_double)
 
 
+# storage_mode=None picks the fastest kernels for the given ntau: the one-pass kernels in their lean layout (48 B per
+# particle-tau across the one field barrier of a step) for ntau = 8, 16, 32, the two-barrier kernels otherwise.
+# Tests that target the two-barrier kernels set this to _lib.STORE_FULL.
+DEFAULT_STORAGE = None
+
+
+def default_storage(ntau: int) -> int:
+    if DEFAULT_STORAGE is not None:
+        return DEFAULT_STORAGE
+    return _lib.STORE_ONEPASS_LEAN if int(ntau) in (8, 16, 32) else _lib.STORE_FULL
+
+
 class Session:
     def __init__(self, mesh: Mesh, ntau: int, eps: float, dt: float, nbpart: int, weight: float | None = None,
                  nbpart_global: int | None = None, wrap=_lib.WRAP_FORTRAN, deposit_mode=_lib.DEPOSIT_FP64_ATOMIC,
-                 scheme=_lib.SCHEME_M6, storage_mode=_lib.STORE_FULL, device: int = 0, stream: int | None = None):
+                 scheme=_lib.SCHEME_M6, storage_mode: int | None = None, device: int = 0, stream: int | None = None):
+        if storage_mode is None:
+            storage_mode = default_storage(ntau)
+        self.storage_mode = storage_mode
         self.mesh, self.ntau, self.eps, self.dt = mesh, int(ntau), float(eps), float(dt)
         self.nbpart = int(nbpart)
         self.nbpart_global = int(nbpart_global if nbpart_global is not None else nbpart)
@@ -170,7 +185,7 @@ class Session:
 
 
 def run_bupdate(mesh: Mesh, ntau: int, eps: float, dt: float, nstep: int, x: np.ndarray, v: np.ndarray, w: float | None = None,
-                wrap=_lib.WRAP_FORTRAN, deposit_mode=_lib.DEPOSIT_FP64_ATOMIC, device: int = 0, storage_mode=_lib.STORE_FULL):
+                wrap=_lib.WRAP_FORTRAN, deposit_mode=_lib.DEPOSIT_FP64_ATOMIC, device: int = 0, storage_mode: int | None = None):
     """the whole program fortran/bupdate.F90:89-128 on one GPU: returns (x, v, energy[1+2*nstep], e_mesh)"""
     nbpart = x.shape[1]
     with Session(mesh, ntau, eps, dt, nbpart, weight=w, wrap=wrap, deposit_mode=deposit_mode, device=device,
