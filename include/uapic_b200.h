@@ -190,6 +190,14 @@ int uapic_session_generate_particles(uapic_session_t *s, int kind, uint64_t seed
 int uapic_session_init_fields(uapic_session_t *s);
 /* nsteps iterations of the loop body bupdate.F90:97-123 (dead third interpolation skipped) */
 int uapic_session_step(uapic_session_t *s, int nsteps);
+/* One UA step with the particles living in HOST memory: x_in, v_in (2,nbpart) and e_in (2,nbpart; NULL keeps the
+   particles.e held on the device) are copied up, one step runs, x_out and v_out (2,nbpart) are copied down -- the same
+   result as upload_particles + upload_particle_e + step(1) + download_particles, but pipelined: the particle range is cut
+   into chunks whose copies overlap the kernels of the neighbouring chunks.  Use pinned host buffers (pageable memory works
+   but serialises).  Returns when x_out and v_out are complete.  Caller side: what a Julia program that keeps `particles`
+   on the host calls once per iteration of the loop test/bupdate.jl:69-114. */
+int uapic_session_step_host(uapic_session_t *s, const double *x_in, const double *v_in, const double *e_in, double *x_out,
+                            double *v_out);
 /* block until everything queued on the session's stream has finished */
 int uapic_session_synchronize(uapic_session_t *s);
 

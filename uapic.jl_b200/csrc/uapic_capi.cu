@@ -1,5 +1,6 @@
 // uapic_capi.cu -- the C ABI declared in include/uapic_b200.h: host-side glue only (allocation, H2D/D2H,
 // launch ordering).  No compute happens on the host and there is no CPU fallback.
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -432,6 +433,9 @@ struct uapic_session {
     bool permuted = false;             // device arrays are in sorted order, perm is valid
     int sort_interval = 0, sort_shift = 3;
     int64_t steps_done = 0;
+    // uapic_session_step_host: copy streams and per-chunk events (created at first use)
+    cudaStream_t up_stream = nullptr, down_stream = nullptr;
+    std::vector<cudaEvent_t> chunk_ev;
     int64_t n_energy = 0, cap_energy = 0;
     uapic_allreduce_fn reduce = nullptr;
     void *reduce_ctx = nullptr;
@@ -442,7 +446,12 @@ struct uapic_session {
     std::vector<cudaEvent_t> ev;     // 4 per step: A0 A1 B0 B1
     double ms_a = 0, ms_b = 0;
     int64_t timed_steps = 0;
-    ~uapic_session() { for (cudaEvent_t e : ev) cudaEventDestroy(e); }
+    ~uapic_session() {
+        for (cudaEvent_t e : ev) cudaEventDestroy(e);
+        for (cudaEvent_t e : chunk_ev) cudaEventDestroy(e);
+        if (up_stream) cudaStreamDestroy(up_stream);
+        if (down_stream) cudaStreamDestroy(down_stream);
+    }
 };
 
 namespace {
@@ -507,20 +516,24 @@ OnepassParams session_onepass_params(uapic_session *s) {
 }
 
 // reorder x, v, ep by coarse mesh bin; callers never see the order (downloads undo it)
+int session_alloc_sort_buffers(uapic_session *s) {
+    const size_t np = (size_t)s->cfg.nbpart;
+    if (s->x2.p || np == 0) return UAPIC_OK;
+    int rc = UAPIC_OK;
+    if (!rc) rc = session_alloc(s, s->x2, 16 * np);
+    if (!rc) rc = session_alloc(s, s->v2, 16 * np);
+    if (!rc) rc = session_alloc(s, s->ep2, 16 * np);
+    if (!rc) rc = session_alloc(s, s->perm, 4 * np);
+    if (!rc) rc = session_alloc(s, s->perm2, 4 * np);
+    if (!rc) rc = session_alloc(s, s->binid, 2 * np);
+    if (!rc) rc = session_alloc(s, s->hist, 4 * 4096);
+    return rc;
+}
+
 int session_sort(uapic_session *s) {
     const size_t np = (size_t)s->cfg.nbpart;
     if (np == 0) return UAPIC_OK;
-    if (!s->x2.p) {
-        int rc = UAPIC_OK;
-        if (!rc) rc = session_alloc(s, s->x2, 16 * np);
-        if (!rc) rc = session_alloc(s, s->v2, 16 * np);
-        if (!rc) rc = session_alloc(s, s->ep2, 16 * np);
-        if (!rc) rc = session_alloc(s, s->perm, 4 * np);
-        if (!rc) rc = session_alloc(s, s->perm2, 4 * np);
-        if (!rc) rc = session_alloc(s, s->binid, 2 * np);
-        if (!rc) rc = session_alloc(s, s->hist, 4 * 4096);
-        if (rc) return rc;
-    }
+    TRY(session_alloc_sort_buffers(s));
     CU(launch_sort_particles(s->lc, s->m, s->sort_shift, s->cfg.nbpart, s->x.as<double2>(), s->v.as<double2>(), s->ep.as<double2>(),
                              s->permuted ? s->perm.as<uint32_t>() : nullptr, s->x2.as<double2>(), s->v2.as<double2>(),
                              s->ep2.as<double2>(), s->perm2.as<uint32_t>(), s->binid.as<uint16_t>(), s->hist.as<unsigned>()));
@@ -786,6 +799,106 @@ int uapic_session_step(uapic_session_t *s, int nsteps) {
         if (s->timing) CU(cudaEventRecord(e4[3], s->lc.stream));
         TRY(session_field_solve(s));           // :119
     }
+    return UAPIC_OK;
+}
+
+// One UA step with the particles living in HOST memory (the end-to-end pattern): the particle range is cut into chunks;
+// chunk c's upload overlaps phase A of chunk c-1, and chunk c's download overlaps phase B of chunk c+1.  Same result as
+// upload_particles + upload_particle_e + step(1) + download_particles.
+int uapic_session_step_host(uapic_session_t *s, const double *x_in, const double *v_in, const double *e_in, double *x_out,
+                            double *v_out) {
+    if (!s || !x_in || !v_in || !x_out || !v_out) return fail(UAPIC_EINVAL, "uapic_session_step_host: null pointer");
+    if (!s->fields_ready) return fail(UAPIC_ESTATE, "call uapic_session_init_fields before uapic_session_step_host");
+    TRY(session_bind(s));
+    const int64_t np = s->cfg.nbpart;
+    if (!s->onepass || np < (1 << 16)) {
+        // two-barrier kernels / tiny problems: nothing to overlap
+        TRY(uapic_session_upload_particles(s, x_in, v_in));
+        if (e_in) TRY(uapic_session_upload_particle_e(s, e_in));
+        TRY(uapic_session_step(s, 1));
+        return uapic_session_download_particles(s, x_out, v_out);
+    }
+    constexpr int kChunks = 16;
+    if (!s->up_stream) {
+        CU(cudaStreamCreateWithFlags(&s->up_stream, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&s->down_stream, cudaStreamNonBlocking));
+        for (int q = 0; q < 2 * kChunks + 2; ++q) {
+            cudaEvent_t e;
+            CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            s->chunk_ev.push_back(e);
+        }
+    }
+    if (s->permuted && !e_in) {
+        // particles.e stays on the device in sorted order: bring it back to the caller's order first
+        CU(launch_unpermute(s->lc, np, s->perm.as<uint32_t>(), s->ep.as<double2>(), s->ep2.as<double2>()));
+        s->ep.swap(s->ep2);
+    }
+    s->permuted = false;
+    TRY(session_alloc_sort_buffers(s));
+    cudaStream_t cs = s->lc.stream;
+    cudaEvent_t ev_start = s->chunk_ev[2 * kChunks], ev_done = s->chunk_ev[2 * kChunks + 1];
+    CU(cudaEventRecord(ev_start, cs));                       // earlier work on the session stream (previous step) is finished
+    CU(cudaStreamWaitEvent(s->up_stream, ev_start, 0));
+    CU(cudaStreamWaitEvent(s->down_stream, ev_start, 0));
+    TRY(session_clear_raw(s));
+    const int64_t per = ((np + kChunks - 1) / kChunks + 255) / 256 * 256;
+    OnepassParams op = session_onepass_params(s);
+    const size_t stride = onepass_store_bytes_per_particle(op.ntau, op.full);
+    const bool sort = s->sort_interval > 0;
+    // ---- uploads || reorder + phase A, chunk by chunk ----
+    for (int c = 0; c < kChunks; ++c) {
+        const int64_t lo = (int64_t)c * per, n = std::min(per, np - lo);
+        if (n <= 0) break;
+        CU(cudaMemcpyAsync(s->x.as<double2>() + lo, x_in + 2 * lo, 16 * (size_t)n, cudaMemcpyHostToDevice, s->up_stream));
+        CU(cudaMemcpyAsync(s->v.as<double2>() + lo, v_in + 2 * lo, 16 * (size_t)n, cudaMemcpyHostToDevice, s->up_stream));
+        if (e_in) CU(cudaMemcpyAsync(s->ep.as<double2>() + lo, e_in + 2 * lo, 16 * (size_t)n, cudaMemcpyHostToDevice, s->up_stream));
+        CU(cudaEventRecord(s->chunk_ev[c], s->up_stream));
+        CU(cudaStreamWaitEvent(cs, s->chunk_ev[c], 0));
+        OnepassParams pc = op;
+        pc.np = n;
+        if (sort) {
+            CU(launch_sort_particles(s->lc, s->m, s->sort_shift, n, s->x.as<double2>() + lo, s->v.as<double2>() + lo,
+                                     s->ep.as<double2>() + lo, nullptr, s->x2.as<double2>() + lo, s->v2.as<double2>() + lo,
+                                     s->ep2.as<double2>() + lo, s->perm2.as<uint32_t>() + lo, s->binid.as<uint16_t>() + lo,
+                                     s->hist.as<unsigned>(), (uint32_t)lo));
+            pc.x = s->x2.as<double2>() + lo; pc.v = s->v2.as<double2>() + lo; pc.ep = s->ep2.as<double2>() + lo;
+        } else {
+            pc.x = s->x.as<double2>() + lo; pc.v = s->v.as<double2>() + lo; pc.ep = s->ep.as<double2>() + lo;
+        }
+        pc.store = op.store + (size_t)lo * stride;
+        pc.rec = op.rec + 8 * lo;
+        pc.ehalo = s->ehalo.as<double2>();
+        CU(launch_onepass_a(s->lc, pc));
+    }
+    // ---- the one field barrier ----
+    TRY(session_reduce(s, 2));
+    TRY(session_solve(s, s->acc, s->emesh_p, s->ehalo_p));
+    TRY(session_solve(s, s->acc_c, s->emesh, s->ehalo));
+    // ---- phase B (+ undo the reordering) || downloads, chunk by chunk ----
+    for (int c = 0; c < kChunks; ++c) {
+        const int64_t lo = (int64_t)c * per, n = std::min(per, np - lo);
+        if (n <= 0) break;
+        OnepassParams pc = op;
+        pc.np = n;
+        pc.x = (sort ? s->x2 : s->x).as<double2>() + lo; pc.v = (sort ? s->v2 : s->v).as<double2>() + lo;
+        pc.ep = (sort ? s->ep2 : s->ep).as<double2>() + lo;
+        pc.store = op.store + (size_t)lo * stride;
+        pc.rec = op.rec + 8 * lo;
+        pc.ehalo = s->ehalo_p.as<double2>();
+        CU(launch_onepass_b(s->lc, pc));
+        if (sort) {   // perm2 holds global indices, all inside this chunk: x[perm2[i]] = x2[i]
+            CU(launch_unpermute(s->lc, n, s->perm2.as<uint32_t>() + lo, s->x2.as<double2>() + lo, s->x.as<double2>()));
+            CU(launch_unpermute(s->lc, n, s->perm2.as<uint32_t>() + lo, s->v2.as<double2>() + lo, s->v.as<double2>()));
+        }
+        CU(cudaEventRecord(s->chunk_ev[kChunks + c], cs));
+        CU(cudaStreamWaitEvent(s->down_stream, s->chunk_ev[kChunks + c], 0));
+        CU(cudaMemcpyAsync(x_out + 2 * lo, s->x.as<double2>() + lo, 16 * (size_t)n, cudaMemcpyDeviceToHost, s->down_stream));
+        CU(cudaMemcpyAsync(v_out + 2 * lo, s->v.as<double2>() + lo, 16 * (size_t)n, cudaMemcpyDeviceToHost, s->down_stream));
+    }
+    CU(cudaEventRecord(ev_done, s->down_stream));
+    CU(cudaStreamWaitEvent(cs, ev_done, 0));
+    CU(cudaStreamSynchronize(cs));
+    s->steps_done++;
     return UAPIC_OK;
 }
 

@@ -101,7 +101,7 @@ cudaError_t launch_onepass_b(const LaunchCtx &c, const OnepassParams &p);
 int sort_bins(const MeshDev &m, int bin_cells_log2);
 cudaError_t launch_sort_particles(const LaunchCtx &c, const MeshDev &m, int bin_cells_log2, int64_t np, const double2 *x,
                                   const double2 *v, const double2 *ep, const uint32_t *perm, double2 *x2, double2 *v2,
-                                  double2 *ep2, uint32_t *perm2, uint16_t *binid, unsigned *hist);
+                                  double2 *ep2, uint32_t *perm2, uint16_t *binid, unsigned *hist, uint32_t index_base = 0);
 cudaError_t launch_unpermute(const LaunchCtx &c, int64_t np, const uint32_t *perm, const double2 *a, double2 *out);
 
 // ---- loaders / diagnostics --------------------------------------------------------------------------------------

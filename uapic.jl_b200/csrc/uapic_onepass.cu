@@ -47,6 +47,9 @@ namespace {
 #else
 #define OP_STEP() __syncwarp()
 #endif
+#ifndef UAPIC_OP_PREFETCH
+#define UAPIC_OP_PREFETCH 0
+#endif
 #ifndef UAPIC_OP_GATHER_UNROLL
 #define UAPIC_OP_GATHER_UNROLL 1
 #endif
@@ -318,6 +321,16 @@ __global__ void __launch_bounds__(kOpBlockA, UAPIC_OP_MINB_A) k_onepass_a(OpDev 
         const int64_t ip = valid ? kraw : P.np - 1;
         const double2 xx = P.x[ip], vv = P.v[ip], ee = P.ep[ip];
         const double x1 = xx.x, x2 = xx.y, vx = vv.x, vy = vv.y;
+#if UAPIC_OP_PREFETCH
+        {   // the CTA's next tiles: their particle data would otherwise be a cold HBM access all warps of the CTA wait on together
+            const int64_t nk = kraw + nwarps * PW;
+            if (g == 0 && nk < P.np) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(P.x + nk));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(P.v + nk));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(P.ep + nk));
+            }
+        }
+#endif
 
         // ---- preparation (ua_steps.F90:49-113) ----
         const double b = bfield(x1, x2);                                     // :54

@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(kSortBlock) k_sort_scatter(int nbins, int64_t 
                                                              const double2 *__restrict__ v, const double2 *__restrict__ ep,
                                                              const uint32_t *__restrict__ perm, double2 *__restrict__ x2,
                                                              double2 *__restrict__ v2, double2 *__restrict__ ep2,
-                                                             uint32_t *__restrict__ perm2) {
+                                                             uint32_t *__restrict__ perm2, uint32_t index_base) {
     extern __shared__ unsigned sm[];
     unsigned *cnt = sm, *base = sm + nbins;
     for (int b = threadIdx.x; b < nbins; b += kSortBlock) cnt[b] = 0;
@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(kSortBlock) k_sort_scatter(int nbins, int64_t 
             const int b = binid[i];
             const size_t d = (size_t)base[b] + atomicAdd(&cnt[b], 1u);
             x2[d] = x[i]; v2[d] = v[i]; ep2[d] = ep[i];
-            perm2[d] = perm ? perm[i] : (uint32_t)i;
+            perm2[d] = perm ? perm[i] : index_base + (uint32_t)i;
         }
     }
 }
@@ -119,10 +119,11 @@ int sort_bins(const MeshDev &m, int bin_cells_log2) {
 }
 
 // x, v, ep, perm -> x2, v2, ep2, perm2 ordered by bin; binid: np uint16; hist: nbins unsigned (scratch).  perm may be
-// null (identity).  nbins = sort_bins(m, bin_cells_log2) must be <= 4096.
+// null (identity: slot i gets index_base + i, so that a sub-range of a larger array can be sorted on its own).
+// nbins = sort_bins(m, bin_cells_log2) must be <= 4096.
 cudaError_t launch_sort_particles(const LaunchCtx &c, const MeshDev &m, int bin_cells_log2, int64_t np, const double2 *x,
                                   const double2 *v, const double2 *ep, const uint32_t *perm, double2 *x2, double2 *v2,
-                                  double2 *ep2, uint32_t *perm2, uint16_t *binid, unsigned *hist) {
+                                  double2 *ep2, uint32_t *perm2, uint16_t *binid, unsigned *hist, uint32_t index_base) {
     if (np <= 0) return cudaSuccess;
     SortGeom g;
     g.inv_dx = 1.0 / m.dx; g.inv_dy = 1.0 / m.dy; g.inv_nx = 1.0 / (double)m.nx; g.inv_ny = 1.0 / (double)m.ny;
@@ -136,7 +137,7 @@ cudaError_t launch_sort_particles(const LaunchCtx &c, const MeshDev &m, int bin_
     const int grid = (int)((np + kSortChunk - 1) / kSortChunk);
     k_sort_count<<<grid, kSortBlock, sizeof(unsigned) * g.nbins, c.stream>>>(g, np, x, binid, hist);
     k_sort_scan<<<1, 1024, 0, c.stream>>>(g.nbins, hist);
-    k_sort_scatter<<<grid, kSortBlock, 2 * sizeof(unsigned) * g.nbins, c.stream>>>(g.nbins, np, binid, hist, x, v, ep, perm, x2, v2, ep2, perm2);
+    k_sort_scatter<<<grid, kSortBlock, 2 * sizeof(unsigned) * g.nbins, c.stream>>>(g.nbins, np, binid, hist, x, v, ep, perm, x2, v2, ep2, perm2, index_base);
     if (c.launches) *c.launches += 3;
     return cudaGetLastError();
 }

@@ -136,6 +136,20 @@ class Session:
         """nsteps UA steps (bupdate.F90:97-123); asynchronous on the session's stream"""
         check(lib().uapic_session_step(self._h, C.c_int(nsteps)))
 
+    def step_host(self, x_in: np.ndarray, v_in: np.ndarray, e_in: np.ndarray | None, x_out: np.ndarray, v_out: np.ndarray):
+        """one UA step with the particles in host memory ((2, nbpart) Fortran-ordered float64, ideally pinned): copies and
+        kernels are pipelined chunk by chunk inside the library; returns when x_out, v_out are complete"""
+        for a in (x_in, v_in, x_out, v_out) + ((e_in,) if e_in is not None else ()):
+            if a.dtype != np.float64 or a.shape != (2, self.nbpart) or not a.flags.f_contiguous:
+                raise ValueError("arrays must be Fortran-ordered float64 of shape (2, nbpart)")
+        check(lib().uapic_session_step_host(self._h, x_in.ctypes.data_as(_dp), v_in.ctypes.data_as(_dp),
+                                            e_in.ctypes.data_as(_dp) if e_in is not None else None,
+                                            x_out.ctypes.data_as(_dp), v_out.ctypes.data_as(_dp)))
+
+    def step_host_ptr(self, x_in: int, v_in: int, e_in: int, x_out: int, v_out: int):
+        check(lib().uapic_session_step_host(self._h, C.cast(x_in, _dp), C.cast(v_in, _dp), C.cast(e_in, _dp) if e_in else None,
+                                            C.cast(x_out, _dp), C.cast(v_out, _dp)))
+
     def synchronize(self):
         check(lib().uapic_session_synchronize(self._h))
 
