@@ -34,7 +34,7 @@ namespace uapic {
 namespace {
 
 #ifndef UAPIC_OP_MINB_A
-#define UAPIC_OP_MINB_A 2     // 2 x 6 warps at 168 registers: measured best (8 warps at 255: -7 %; 12 x 1: -6 %)
+#define UAPIC_OP_MINB_A 1     // one CTA of 12 warps at 168 registers per SM, in four lock-step groups of 3 warps: measured best
 #endif
 #ifndef UAPIC_OP_MINB_B
 #define UAPIC_OP_MINB_B 2
@@ -42,7 +42,19 @@ namespace {
 #ifndef UAPIC_OP_LOCKSTEP
 #define UAPIC_OP_LOCKSTEP 1
 #endif
-#if UAPIC_OP_LOCKSTEP
+#ifndef UAPIC_OP_LOCKMOD
+#define UAPIC_OP_LOCKMOD 0
+#endif
+#ifndef UAPIC_OP_LOCKGROUP
+#define UAPIC_OP_LOCKGROUP 3      // warps per lock-step group inside a CTA of phase A; 0 = the whole CTA
+#endif
+#if UAPIC_OP_LOCKSTEP && UAPIC_OP_LOCKGROUP
+#if UAPIC_OP_LOCKMOD   // group = warp % (warps / LOCKGROUP): the warps of a group sit on the same SM sub-partition
+#define OP_STEP() asm volatile("bar.sync %0, %1;" ::"r"(1 + (int)(threadIdx.x >> 5) % (UAPIC_OP_BLOCK_A / 32 / UAPIC_OP_LOCKGROUP)), "r"(32 * UAPIC_OP_LOCKGROUP) : "memory")
+#else
+#define OP_STEP() asm volatile("bar.sync %0, %1;" ::"r"(1 + (int)(threadIdx.x >> 5) / UAPIC_OP_LOCKGROUP), "r"(32 * UAPIC_OP_LOCKGROUP) : "memory")
+#endif
+#elif UAPIC_OP_LOCKSTEP
 #define OP_STEP() __syncthreads()
 #else
 #define OP_STEP() __syncwarp()
@@ -54,7 +66,7 @@ namespace {
 #define UAPIC_OP_GATHER_UNROLL 1
 #endif
 #ifndef UAPIC_OP_BLOCK_A
-#define UAPIC_OP_BLOCK_A 192
+#define UAPIC_OP_BLOCK_A 384
 #endif
 #ifndef UAPIC_OP_BLOCK_B
 #define UAPIC_OP_BLOCK_B 256
