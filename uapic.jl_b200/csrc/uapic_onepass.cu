@@ -76,7 +76,7 @@ constexpr int kGatherUnroll = UAPIC_OP_GATHER_UNROLL;
 constexpr int kRow = 36;                       // padded row (double2 units) of the per-warp exchange area: conflict-free
 constexpr int kTab = 108;                      // cos/sin table (32) + two [4][9]-padded tables: rows in distinct bank groups
 constexpr int kWarpSmA = 8 * kRow + 4 * kRow + 16 * 32;  // exchange rows + sin-product rows + yhat stash (double2 units)
-constexpr int kWarpSmB = 8 * kRow;
+constexpr int kWarpSmB = 8 * kRow + 256;       // W_n exchange rows + partial sums of the tau* evaluation
 
 constexpr double kRsqrt2 = 0.70710678118654752440;
 
@@ -547,8 +547,8 @@ __global__ void __launch_bounds__(kOpBlockA, UAPIC_OP_MINB_A) k_onepass_a(OpDev 
         if (valid && g == 0) {
             P.x[ip] = make_double2(xw, yw);                                  // compute_rho_m6.F90:86-87
             double2 *rec = reinterpret_cast<double2 *>(P.rec + 8 * ip);
-            rec[0] = make_double2(t, b);
-            rec[1] = make_double2(rb, qa1);
+            rec[0] = make_double2(b, rb);                                    // what every sample lane of phase B needs
+            rec[1] = make_double2(t, qa1);
             rec[2] = make_double2(qa2, e1.re);                               // cos(t/eps)
             rec[3] = make_double2(-e1.im, 0.0);                              // sin(t/eps)
         }
@@ -566,6 +566,7 @@ __global__ void __launch_bounds__(kOpBlockB, UAPIC_OP_MINB_B) k_onepass_b(OpDev 
     extern __shared__ double2 smem[];
     const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double2 *wx = smem + kTab + wib * kWarpSmB;    // [8][kRow]  W_n of the tile (LEAN only)
+    double2 *red = wx + 8 * kRow;                  // [PW][N]    per-sample terms of the two tau* sums
     OpLane<G> L; L.init(lane, smem);
     const int g = L.g, pin = lane / G;
     const double eps = P.eps, inv_eps = D.inv_eps, invN = 1.0 / (double)N;
@@ -580,7 +581,7 @@ __global__ void __launch_bounds__(kOpBlockB, UAPIC_OP_MINB_B) k_onepass_b(OpDev 
             const int64_t kraw = tile * PW + pin;
             const int64_t ip = kraw < P.np ? kraw : P.np - 1;
             const double2 *rec = reinterpret_cast<const double2 *>(P.rec + 8 * ip);
-            const double t = rec[0].x, rt = 1.0 / t;
+            const double t = rec[1].x, rt = 1.0 / t;
             const cd e1 = mk(rec[2].y, -rec[3].x);
             cd elt[8], wv[8];
             elt_modes<G>(L, t, eps, e1, elt);
@@ -603,9 +604,8 @@ __global__ void __launch_bounds__(kOpBlockB, UAPIC_OP_MINB_B) k_onepass_b(OpDev 
             const int64_t kraw = tile * PW + pp;
             const bool valid = kraw < P.np;
             const int64_t ip = valid ? kraw : P.np - 1;
-            const double2 *rec = reinterpret_cast<const double2 *>(P.rec + 8 * ip);
-            const double2 r0 = rec[0], r1 = rec[1], r2 = rec[2], r3 = rec[3];
-            const double b = r0.y, rb = r1.x, qa1 = r1.y, qa2 = r2.x, cs = r2.y, sn = r3.x;
+            const double2 r0 = *reinterpret_cast<const double2 *>(P.rec + 8 * ip);
+            const double b = r0.x, rb = r0.y;
             char *sbase = P.store + (size_t)ip * SM::stride;
             const double2 xs = SM::xtr(sbase)[n], ya = SM::yt1(sbase)[n], yb = SM::yt2(sbase)[n];
             double2 wn;
@@ -623,12 +623,30 @@ __global__ void __launch_bounds__(kOpBlockB, UAPIC_OP_MINB_B) k_onepass_b(OpDev 
             gather_tiled(P.m, P.ehalo, cell, e1, e2);
             cd gy1, gy2;
             fy_time(csn.x, csn.y, rb, iv, mk(ya.x, ya.y), mk(yb.x, yb.y), e1, e2, gy1, gy2);     // :177-183
-            // Re sum_n gy(tau_n) W_n
-            const double px = qa1 + group_sum<N>(fma(gy1.re, wn.x, -gy1.im * wn.y));
-            const double py = qa2 + group_sum<N>(fma(gy2.re, wn.x, -gy2.im * wn.y));
-            if (valid && n == 0) P.v[ip] = make_double2(cs * px + sn * py, cs * py - sn * px);     // :302-303
+            // terms of Re sum_n gy(tau_n) W_n: summed over n after the loop (one pass through shared memory instead of a
+            // shuffle tree per particle)
+            red[pp * N + n] = make_double2(fma(gy1.re, wn.x, -gy1.im * wn.y), fma(gy2.re, wn.x, -gy2.im * wn.y));
         }
-        (void)g;
+        __syncwarp();
+        {
+            // lane (p, g) of the phase-A layout adds 8 consecutive terms of particle p (rotated start: conflict-free), then a
+            // log2(G)-stage butterfly; lane g = 0 finishes compute_v (ua_steps.F90:293-303)
+            double sx = 0.0, sy = 0.0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const double2 q = red[pin * N + 8 * g + ((i + lane) & 7)];
+                sx += q.x; sy += q.y;
+            }
+            sx = grp_sum<G>(sx); sy = grp_sum<G>(sy);
+            const int64_t kraw = tile * PW + pin;
+            if (g == 0 && kraw < P.np) {
+                const double2 *rec = reinterpret_cast<const double2 *>(P.rec + 8 * kraw);
+                const double2 r1 = rec[1], r2 = rec[2], r3 = rec[3];
+                const double px = r1.y + sx, py = r2.x + sy, cs = r2.y, sn = r3.x;
+                P.v[kraw] = make_double2(cs * px + sn * py, cs * py - sn * px);                    // :302-303
+            }
+        }
+        __syncwarp();
     }
 }
 
