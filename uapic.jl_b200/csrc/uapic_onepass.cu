@@ -60,7 +60,7 @@ namespace {
 #define OP_STEP() __syncwarp()
 #endif
 #ifndef UAPIC_OP_PREFETCH
-#define UAPIC_OP_PREFETCH 0
+#define UAPIC_OP_PREFETCH 1
 #endif
 #ifndef UAPIC_OP_GATHER_UNROLL
 #define UAPIC_OP_GATHER_UNROLL 1
@@ -73,6 +73,13 @@ namespace {
 #endif
 constexpr int kOpBlockA = UAPIC_OP_BLOCK_A, kOpBlockB = UAPIC_OP_BLOCK_B;      // threads per CTA of the two kernels
 constexpr int kGatherUnroll = UAPIC_OP_GATHER_UNROLL;
+#ifndef UAPIC_OP_PREFETCH_B
+#define UAPIC_OP_PREFETCH_B 2
+#endif
+#ifndef UAPIC_OP_GATHER_UNROLL_B
+#define UAPIC_OP_GATHER_UNROLL_B 2
+#endif
+constexpr int kGatherUnrollB = UAPIC_OP_GATHER_UNROLL_B;
 constexpr int kRow = 36;                       // padded row (double2 units) of the per-warp exchange area: conflict-free
 constexpr int kTab = 108;                      // cos/sin table (32) + two [4][9]-padded tables: rows in distinct bank groups
 constexpr int kWarpSmA = 8 * kRow + 4 * kRow + 16 * 32;  // exchange rows + sin-product rows + yhat stash (double2 units)
@@ -598,7 +605,7 @@ __global__ void __launch_bounds__(kOpBlockB, UAPIC_OP_MINB_B) k_onepass_b(OpDev 
             for (int s = 0; s < 8; ++s) wx[s * kRow + lane] = make_double2(wv[s].re, -wv[s].im);
             __syncwarp();
         }
-#pragma unroll 2
+#pragma unroll (kGatherUnrollB)
         for (int j = 0; j < 8; ++j) {
             const int pp = j * PPI + lane / N;
             const int64_t kraw = tile * PW + pp;
@@ -607,6 +614,18 @@ __global__ void __launch_bounds__(kOpBlockB, UAPIC_OP_MINB_B) k_onepass_b(OpDev 
             const double2 r0 = *reinterpret_cast<const double2 *>(P.rec + 8 * ip);
             const double b = r0.x, rb = r0.y;
             char *sbase = P.store + (size_t)ip * SM::stride;
+#if UAPIC_OP_PREFETCH_B
+            {   // the store is streamed exactly once: ask L2 for the lines of the particle two iterations ahead
+                const int j2 = j + UAPIC_OP_PREFETCH_B;
+                const int64_t k2 = (j2 < 8 ? tile : tile + nwarps) * PW + (j2 & 7) * PPI + lane / N;
+                if ((n & 7) == 0 && k2 < P.np) {
+                    const char *b2 = P.store + (size_t)k2 * SM::stride + 16 * n;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(b2));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(b2 + 16 * N));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(b2 + 32 * N));
+                }
+            }
+#endif
             const double2 xs = SM::xtr(sbase)[n], ya = SM::yt1(sbase)[n], yb = SM::yt2(sbase)[n];
             double2 wn;
             double iv;
