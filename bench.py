@@ -220,7 +220,8 @@ def main():
                    storage_mode=MODES[storage])
     if world > 1:
         ub.dist.attach_torch_allreduce(s)
-    s.generate_particles(load, seed=20190101, first_global_index=lo)
+    # interleaved shards (global index = rank + k*world): the Landau load stratifies |v| by particle index
+    s.generate_particles(load, seed=20190101, first_global_index=rank, index_stride=world)
     s.init_fields()
     s.step(args.warmup)
     s.synchronize()

@@ -186,6 +186,11 @@ int uapic_session_phase_times(uapic_session_t *s, double *ms_phase_a, double *ms
    kind 1: Landau load (the intent of src/landau.jl:19-43)                                         */
 int uapic_session_generate_particles(uapic_session_t *s, int kind, uint64_t seed, int64_t first_global_index,
                                      double alpha, double kx);
+/* same, with the shard holding the global indices first, first+stride, first+2*stride, ...  The Landau load assigns |v| by
+   particle index (src/landau.jl:35): contiguous index ranges would give every rank a different velocity band (and the rank
+   with the fast particles, whose gyro-orbits span more mesh lines, would set the pace), interleaved ones do not. */
+int uapic_session_generate_particles_strided(uapic_session_t *s, int kind, uint64_t seed, int64_t first_global_index,
+                                             int64_t index_stride, double alpha, double kx);
 /* compute_rho_m6_real -> solve_poisson -> interpolate_eb_m6_real     bupdate.F90:89-93 */
 int uapic_session_init_fields(uapic_session_t *s);
 /* nsteps iterations of the loop body bupdate.F90:97-123 (dead third interpolation skipped) */

@@ -277,3 +277,20 @@ def test_step_host_equals_upload_step_download(with_e):
         xb, vb = s.download_particles()
     assert np.array_equal(view(hx), xa) and np.array_equal(view(hv), va)
     assert np.array_equal(xb, xa) and np.array_equal(vb, va) and np.array_equal(na, nb) and np.array_equal(ea, eb)
+
+
+def test_interleaved_shards_generate_the_same_particles():
+    """device loader: shards holding global indices rank, rank+W, ... (what bench.py uses to balance the index-stratified
+    |v| of the Landau load over the GPUs) reproduce the unsharded load particle for particle"""
+    mesh = ub.Mesh(0, DIMX, 128, 0, DIMY, 128)
+    npart, world = 30_000, 3
+    with ub.Session(mesh, 32, 0.1, DT, npart) as s:
+        s.generate_particles("landau", seed=17)
+        xf, vf = s.download_particles()
+    for rank in range(world):
+        with ub.Session(mesh, 32, 0.1, DT, npart // world, nbpart_global=npart) as s:
+            s.generate_particles("landau", seed=17, first_global_index=rank, index_stride=world)
+            x, v = s.download_particles()
+        assert np.array_equal(x, xf[:, rank::world]) and np.array_equal(v, vf[:, rank::world])
+    r = np.hypot(vf[0], vf[1])
+    assert r[: npart // 8].min() > r[-npart // 8:].max()      # |v| falls with the index: contiguous shards would be unbalanced

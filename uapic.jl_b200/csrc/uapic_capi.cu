@@ -733,16 +733,22 @@ int uapic_session_phase_times(uapic_session_t *s, double *ms_phase_a, double *ms
     return UAPIC_OK;
 }
 
-int uapic_session_generate_particles(uapic_session_t *s, int kind, uint64_t seed, int64_t first_global_index, double alpha,
-                                     double kx) {
+int uapic_session_generate_particles_strided(uapic_session_t *s, int kind, uint64_t seed, int64_t first_global_index,
+                                             int64_t index_stride, double alpha, double kx) {
     if (!s) return fail(UAPIC_EINVAL, "session is null");
     if (kind != 0 && kind != 1) return fail(UAPIC_EINVAL, "unknown load kind %d", kind);
+    if (index_stride < 1 || first_global_index < 0) return fail(UAPIC_EINVAL, "bad particle index range");
     TRY(session_bind(s));
-    CU(launch_generate(s->lc, s->m, kind, seed, first_global_index, s->cfg.nbpart, s->np_global, alpha, kx, s->x.as<double>(),
-                       s->v.as<double>()));
+    CU(launch_generate(s->lc, s->m, kind, seed, first_global_index, index_stride, s->cfg.nbpart, s->np_global, alpha, kx,
+                       s->x.as<double>(), s->v.as<double>()));
     s->permuted = false;
     s->have_particles = true;
     return UAPIC_OK;
+}
+
+int uapic_session_generate_particles(uapic_session_t *s, int kind, uint64_t seed, int64_t first_global_index, double alpha,
+                                     double kx) {
+    return uapic_session_generate_particles_strided(s, kind, seed, first_global_index, 1, alpha, kx);
 }
 
 int uapic_session_init_fields(uapic_session_t *s) {

@@ -105,7 +105,7 @@ cudaError_t launch_sort_particles(const LaunchCtx &c, const MeshDev &m, int bin_
 cudaError_t launch_unpermute(const LaunchCtx &c, int64_t np, const uint32_t *perm, const double2 *a, double2 *out);
 
 // ---- loaders / diagnostics --------------------------------------------------------------------------------------
-cudaError_t launch_generate(const LaunchCtx &c, const MeshDev &m, int kind, uint64_t seed, int64_t first, int64_t np,
+cudaError_t launch_generate(const LaunchCtx &c, const MeshDev &m, int kind, uint64_t seed, int64_t first, int64_t stride, int64_t np,
                             int64_t np_global, double alpha, double kx, double *x, double *v);
 cudaError_t launch_sum_v(const LaunchCtx &c, int64_t np, const double *v, double *out2);
 

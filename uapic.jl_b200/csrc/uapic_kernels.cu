@@ -536,10 +536,10 @@ DEVINL double uniform01(uint64_t seed, uint64_t particle, uint32_t stream, uint3
 }
 
 // kind 0: rejection sampling of particles.F90:68-103 / src/plasma.jl:17-48 ; kind 1: Landau (src/landau.jl:19-43 intent)
-__global__ void __launch_bounds__(kBlock) k_generate(MeshDev m, int kind, uint64_t seed, int64_t first, int64_t np, int64_t np_global,
-                                                     double alpha, double kx, double *x, double *v) {
+__global__ void __launch_bounds__(kBlock) k_generate(MeshDev m, int kind, uint64_t seed, int64_t first, int64_t stride, int64_t np,
+                                                     int64_t np_global, double alpha, double kx, double *x, double *v) {
     for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < np; k += (int64_t)gridDim.x * blockDim.x) {
-        const uint64_t id = (uint64_t)(first + k);
+        const uint64_t id = (uint64_t)(first + k * stride);
         double x1, x2, v1, v2;
         if (kind == 0) {
             uint32_t d = 0;
@@ -721,10 +721,10 @@ cudaError_t launch_poisson(const LaunchCtx &c, const MeshDev &m, const PoissonWo
     return cudaGetLastError();
 }
 
-cudaError_t launch_generate(const LaunchCtx &c, const MeshDev &m, int kind, uint64_t seed, int64_t first, int64_t np,
+cudaError_t launch_generate(const LaunchCtx &c, const MeshDev &m, int kind, uint64_t seed, int64_t first, int64_t stride, int64_t np,
                             int64_t np_global, double alpha, double kx, double *x, double *v) {
     if (np <= 0) return cudaSuccess;
-    k_generate<<<grid_for(c, np, kBlock), kBlock, 0, c.stream>>>(m, kind, seed, first, np, np_global, alpha, kx, x, v);
+    k_generate<<<grid_for(c, np, kBlock), kBlock, 0, c.stream>>>(m, kind, seed, first, stride, np, np_global, alpha, kx, x, v);
     count(c);
     return cudaGetLastError();
 }

@@ -644,16 +644,19 @@ __global__ void __launch_bounds__(kOpBlockB, UAPIC_OP_MINB_B) k_onepass_b(OpDev 
             fy_time(csn.x, csn.y, rb, iv, mk(ya.x, ya.y), mk(yb.x, yb.y), e1, e2, gy1, gy2);     // :177-183
             // terms of Re sum_n gy(tau_n) W_n: summed over n after the loop (one pass through shared memory instead of a
             // shuffle tree per particle)
-            red[pp * N + n] = make_double2(fma(gy1.re, wn.x, -gy1.im * wn.y), fma(gy2.re, wn.x, -gy2.im * wn.y));
+            // (column swizzle: the reader below takes its 8 terms in natural order, which keeps a particle's result independent
+            //  of the slot it sits in, and still hits 8 distinct bank groups per quarter warp)
+            red[pp * N + (n & ~7) + (((n & 7) + (n >> 3) + 4 * (pp & 1)) & 7)] =
+                make_double2(fma(gy1.re, wn.x, -gy1.im * wn.y), fma(gy2.re, wn.x, -gy2.im * wn.y));
         }
         __syncwarp();
         {
-            // lane (p, g) of the phase-A layout adds 8 consecutive terms of particle p (rotated start: conflict-free), then a
-            // log2(G)-stage butterfly; lane g = 0 finishes compute_v (ua_steps.F90:293-303)
+            // lane (p, g) of the phase-A layout adds the 8 consecutive terms n = 8g .. 8g+7 of particle p in this fixed order,
+            // then a log2(G)-stage butterfly; lane g = 0 finishes compute_v (ua_steps.F90:293-303)
             double sx = 0.0, sy = 0.0;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const double2 q = red[pin * N + 8 * g + ((i + lane) & 7)];
+                const double2 q = red[pin * N + 8 * g + ((i + g + 4 * (pin & 1)) & 7)];
                 sx += q.x; sy += q.y;
             }
             sx = grp_sum<G>(sx); sy = grp_sum<G>(sy);

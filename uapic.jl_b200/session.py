@@ -102,10 +102,13 @@ class Session:
         check(lib().uapic_session_phase_times(self._h, C.byref(a), C.byref(b), C.byref(n)))
         return a.value, b.value, n.value
 
-    def generate_particles(self, kind: str = "plasma", seed: int = 20190101, first_global_index: int = 0, alpha=0.05, kx=0.5):
+    def generate_particles(self, kind: str = "plasma", seed: int = 20190101, first_global_index: int = 0, alpha=0.05, kx=0.5,
+                           index_stride: int = 1):
+        """device-side load of this shard: global particle indices first, first+stride, ... (stride = world size and
+        first = rank interleaves the shards, which balances the index-stratified |v| of the Landau load)"""
         k = {"plasma": 0, "landau": 1}[kind]
-        check(lib().uapic_session_generate_particles(self._h, C.c_int(k), C.c_uint64(seed), C.c_int64(first_global_index),
-                                                     C.c_double(alpha), C.c_double(kx)))
+        check(lib().uapic_session_generate_particles_strided(self._h, C.c_int(k), C.c_uint64(seed), C.c_int64(first_global_index),
+                                                             C.c_int64(index_stride), C.c_double(alpha), C.c_double(kx)))
 
     def download_particles(self):
         x = np.zeros((2, self.nbpart), order="F")
