@@ -304,6 +304,19 @@ def main():
         dom = (kb, bytes_b, per_b, impl_b) if per_b >= per_a else (ka, bytes_a, per_a, impl_a)
         achieved = dom[1] / (dom[2] * 1e-3) / 1e9 if dom[2] > 0 else 0.0
         b_alg = 256 + 112 / ntau
+        # DRAM traffic of the dominant kernel: dram__bytes_read + dram__bytes_write of one `ncu --set full` capture at 2e6
+        # particles (profiles/r1n_traffic.json), scaled to this launch's particle-tau count (traffic is linear in it)
+        traffic, traffic_src = None, None
+        try:
+            with open(os.path.join(ROOT, "profiles", "r1n_traffic.json")) as f:
+                tj = json.load(f)
+            kshort = dom[0].split("::")[-1]
+            if onepass and storage == "onepass-lean" and ntau == tj["ntau"] and kshort in tj:
+                per_unit = (tj[kshort]["dram_bytes_read"] + tj[kshort]["dram_bytes_write"]) / (tj["particles"] * tj["ntau"])
+                traffic = int(per_unit * n_loc * ntau)
+                traffic_src = f"ncu capture at {tj['particles']} particles scaled by particle-tau count ({per_unit:.1f} B each); profiles/r1n_traffic.json"
+        except (OSError, KeyError, ValueError):
+            pass
         line = {
             "metric": "particle-tau updates/sec", "value": value, "unit": "particle-tau updates/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
@@ -321,7 +334,7 @@ def main():
             "e2e": e2e,
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": hbm, "unit": "GB/s",
-                         "frac": achieved / hbm, "traffic": None, "peak_source": hbm_src,
+                         "frac": achieved / hbm, "traffic": traffic, "traffic_source": traffic_src, "peak_source": hbm_src,
                          "ms_per_launch": dom[2], "algorithmic_bytes_per_launch": int(dom[1]),
                          "impl_bytes_per_launch": int(dom[3]), "impl_gbs": dom[3] / (dom[2] * 1e-3) / 1e9 if dom[2] > 0 else 0.0,
                          "phase_a_ms": per_a, "phase_b_ms": per_b,
