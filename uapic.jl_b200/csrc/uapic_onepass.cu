@@ -118,7 +118,7 @@ template <int G> struct OpLane {
     const double2 *tw;          // [G][9] exp(-2 pi i g k1 / N), row g (stride 9: the G lanes of a group hit distinct banks)
     const double2 *il;          // [G][9] (1/l_k, 1/l_k^2) of mode k = 8*kappa + k1, row kappa; zero for k = 0   ua_type.F90:51-56
 
-    DEVINL static int kappa_of(int g) { return G == 4 ? (((g & 1) << 1) | (g >> 1)) : g; }
+    __host__ __device__ static constexpr int kappa_of(int g) { return G == 4 ? (((g & 1) << 1) | (g >> 1)) : g; }
     DEVINL static double lmode(int k) { return (double)(k < N / 2 ? k : k - N); }
 
     // tab: kTab double2 of shared memory; every thread of the CTA must call; ends with __syncthreads
@@ -474,14 +474,30 @@ __global__ void __launch_bounds__(kOpBlockA, UAPIC_OP_MINB_A) k_onepass_a(OpDev 
 
         // ---- y: yt = B(yhat) (:105-110), fy in the time domain (:177-183), FFT, ua_step1 (:226), bracket sums ----
         OP_STEP();
+        // yhat1, yhat2 are spectra of real signals (:92-106) except for two coefficients: the Nyquist mode, which the filter
+        // -i/l turns purely imaginary, and the mean, which carries minus its value (:109-110).  So ONE backward transform of
+        // H = H1 + i H2 (H: Hermitian parts) gives Re yt1 + i Re yt2, and Im yt_n = Im yhat_0 + (-1)^n Im yhat_{N/2}.
         cd y1[8], y2[8];
+        {
+            constexpr int kNyqLane = OpLane<G>::kappa_of(G / 2), kNyqReg = (G == 1) ? 4 : 0;
+            const double2 m1 = yhs[gbase], m2 = yhs[8 * 32 + gbase];                                   // yhat_0 (lane kappa = 0)
+            const double2 q1 = yhs[kNyqReg * 32 + gbase + kNyqLane], q2 = yhs[(8 + kNyqReg) * 32 + gbase + kNyqLane];   // yhat_{N/2}
+            cd h[8];
 #pragma unroll
-        for (int k1 = 0; k1 < 8; ++k1) {
-            const double2 a = yhs[k1 * 32 + lane], c = yhs[(8 + k1) * 32 + lane];
-            y1[k1] = mk(a.x, a.y); y2[k1] = mk(c.x, c.y);
+            for (int k1 = 0; k1 < 8; ++k1) {
+                const double2 a = yhs[k1 * 32 + lane], c = yhs[(8 + k1) * 32 + lane];
+                h[k1] = mk(a.x - c.y, a.y + c.x);
+                if (k1 == 0 && L.kap == 0) h[k1] = mk(a.x, c.x);
+                if (k1 == kNyqReg && L.kap == G / 2) h[k1] = mk(0.0, 0.0);
+            }
+            bwdN<G>(h, L);
+#pragma unroll
+            for (int s = 0; s < 8; ++s) {
+                const bool odd = (G == 1) ? (s & 1) : (g & 1);                 // parity of n = g + G s
+                y1[s] = mk(h[s].re, odd ? m1.y - q1.y : m1.y + q1.y);
+                y2[s] = mk(h[s].im, odd ? m2.y - q2.y : m2.y + q2.y);
+            }
         }
-        bwdN<G>(y1, L);
-        bwdN<G>(y2, L);
 #pragma unroll
         for (int s = 0; s < 8; ++s) {
             const double2 c = L.cs[g + G * s], et = gx[s * kRow + lane];
