@@ -17,7 +17,8 @@ export compute_rho_m6!, interpol_eb_m6!
 export preparation!, update_particles_e!, update_particles_x!, compute_f!, ua_step!, compute_v!
 export fft_tau!, ifft_tau!
 export integrate, gnuplot, errors
-export Session, upload_particles!, init_fields!, step!, download_particles, download_fields, energy_history
+export Session, upload_particles!, init_fields!, step!, step_host!, generate_particles!, set_sort!, download_particles, download_fields, energy_history
+export STORE_FULL, STORE_HYBRID, STORE_ONEPASS, STORE_ONEPASS_LEAN
 export UAPICError
 
 const libuapic = get(ENV, "UAPIC_B200_LIB", joinpath(@__DIR__, "..", "..", "libuapic_b200.so"))
@@ -376,6 +377,14 @@ set_sort!(s::Session, interval, bin_cells_log2 = 3) =
     check(ccall((:uapic_session_set_sort, libuapic), Cint, (Ptr{Cvoid}, Cint, Cint), s.handle, interval, bin_cells_log2))
 upload_particles!(s::Session, p::Particles) =
     check(ccall((:uapic_session_upload_particles, libuapic), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}), s.handle, p.x, p.v))
+# one loop iteration of test/bupdate.jl:69-114 for particles kept on the host: copies and kernels pipelined in the library
+step_host!(s::Session, p::Particles) =
+    check(ccall((:uapic_session_step_host, libuapic), Cint,
+                (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}), s.handle, p.x, p.v, p.e, p.x, p.v))
+# device-side loads: kind 0 = plasma (src/plasma.jl), 1 = Landau (src/landau.jl); shard = global indices first:stride:...
+generate_particles!(s::Session, kind; seed = 20190101, first = 0, stride = 1, α = 0.05, kx = 0.5) =
+    check(ccall((:uapic_session_generate_particles_strided, libuapic), Cint,
+                (Ptr{Cvoid}, Cint, UInt64, Int64, Int64, Cdouble, Cdouble), s.handle, kind, seed, first, stride, α, kx))
 init_fields!(s::Session) = check(ccall((:uapic_session_init_fields, libuapic), Cint, (Ptr{Cvoid},), s.handle))
 step!(s::Session, nsteps = 1) = check(ccall((:uapic_session_step, libuapic), Cint, (Ptr{Cvoid}, Cint), s.handle, nsteps))
 
