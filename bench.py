@@ -171,6 +171,8 @@ def main():
     ap.add_argument("--storage", default="auto", choices=["auto", "full", "hybrid", "onepass", "onepass-lean"],
                     help="what crosses the field barrier per particle-tau: one-pass kernels 72 B (onepass) / 48 B (onepass-lean); "
                          "legacy two-barrier kernels 128 B (full) / 16 B + recompute (hybrid)")
+    ap.add_argument("--scheme", default="m6", choices=["m6", "cic"],
+                    help="shape function: m6 = what the reference ships (the metric is quoted on it); cic = build-defined bilinear variant")
     ap.add_argument("--cpu-sample", type=int, default=0, help="particles in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -217,7 +219,7 @@ def main():
                 break
     s = ub.Session(mesh, ntau, EPS, DT, hi - lo, nbpart_global=np_global, device=local, stream=stream,
                    deposit_mode=ub.DEPOSIT_FIXED_POINT if args.deposit == "fixed" else ub.DEPOSIT_FP64_ATOMIC,
-                   storage_mode=MODES[storage])
+                   storage_mode=MODES[storage], scheme=ub.SCHEME_CIC if args.scheme == "cic" else ub.SCHEME_M6)
     if world > 1:
         ub.dist.attach_torch_allreduce(s)
     # interleaved shards (global index = rank + k*world): the Landau load stratifies |v| by particle index
@@ -322,7 +324,7 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "strong" if mode == "total" else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": desc, "load": load, "ntau": ntau, "mesh": [nx, ny], "eps": EPS, "dt": DT, "scheme": "M6",
+            "config": {"workload": desc, "load": load, "ntau": ntau, "mesh": [nx, ny], "eps": EPS, "dt": DT, "scheme": args.scheme.upper(),
                        "particles_per_gpu": np_gpu, "particles_total": np_global, "deposit": args.deposit,
                        "storage": {"full": "store-full (128 B per particle-tau across the intra-step barrier, two barriers per step)",
                                    "hybrid": "hybrid (16 B per particle-tau across the barrier, predictor recomputed in phase B)",

@@ -46,7 +46,9 @@ extern "C" {
 
 /* shape functions */
 #define UAPIC_SCHEME_M6  0      /* quintic spline, the scheme the reference ships (compute_rho_m6.F90:28-45) */
-#define UAPIC_SCHEME_CIC 1      /* bilinear; build-defined from performance/test_cic.F90:73-81 (no reference parity) */
+#define UAPIC_SCHEME_CIC 1      /* bilinear; BUILD-DEFINED (the reference has no 2D CIC deposit and no CIC in the UA loop): weights of
+                                   performance/test_cic.F90:73-76 with the wrap, ghost copy, scaling and neutralisation of the M6
+                                   path; session API with UAPIC_STORE_ONEPASS_LEAN only; parity is against oracle/, not the reference */
 
 /* what crosses the intra-step barrier */
 #define UAPIC_STORE_FULL   0    /* 128 B per particle-tau kept in HBM between predictor and corrector */

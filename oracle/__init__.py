@@ -82,6 +82,13 @@ class _COracle:
     def max_threads(self):
         return int(self.lib.orc_get_max_threads())
 
+    def set_scheme(self, scheme):
+        """0 / "m6": the reference's shape function; 1 / "cic": the build-defined bilinear variant (uapic_oracle.c)"""
+        self.lib.orc_set_scheme(C.c_int({"m6": 0, "cic": 1}.get(scheme, scheme)))
+
+    def scheme(self):
+        return int(self.lib.orc_get_scheme())
+
     def f_m6(self, q):
         return float(self.lib.orc_f_m6(float(q)))
 

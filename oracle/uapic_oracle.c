@@ -218,6 +218,17 @@ typedef struct {
     double cx[7], cy[7];
 } m6_stencil;
 
+/* Shape function.  M6 is what the reference ships on this path.  CIC is BUILD-DEFINED (the reference has no 2D CIC
+   deposit and no CIC inside the UA loop): the bilinear weights of performance/test_cic.F90:73-76
+   (= the 2D restriction of fortran/compute_rho_cic.f90:46-53), a1 = (1-dpx)(1-dpy) on (i,j), a2 = dpx(1-dpy) on (i+1,j),
+   a3 = dpx dpy on (i+1,j+1), a4 = (1-dpx) dpy on (i,j+1), with the periodic index wrap, the ghost copy, the /(dx dy) and
+   the neutralisation of the M6 path.  Here they are the offsets 0 and +1 of the same 7 x 7 stencil structure. */
+#define ORC_SCHEME_M6 0
+#define ORC_SCHEME_CIC 1
+static int g_scheme = ORC_SCHEME_M6;
+void orc_set_scheme(int scheme) { g_scheme = (scheme == ORC_SCHEME_CIC) ? ORC_SCHEME_CIC : ORC_SCHEME_M6; }
+int orc_get_scheme(void) { return g_scheme; }
+
 /* cell + weights: compute_rho_m6.F90:89-131 / interpolation_m6.F90:87-127 (Fortran wrap);
    src/compute_rho.jl:63-73 / src/interpolation.jl:19-29 (Julia wrap).  xw/yw return the position
    the Julia variant stores back into particles.x */
@@ -243,6 +254,12 @@ static inline void m6_setup(const orc_mesh *m, double dx, double dy, double x, d
     for (int a = -3; a <= 3; a++) {
         s->ix[a + 3] = (a == 0) ? i : i_modulo(i + a, nx);   /* centre index is i+1 (1-based), NOT wrapped */
         s->jy[a + 3] = (a == 0) ? j : i_modulo(j + a, ny);
+    }
+    if (g_scheme == ORC_SCHEME_CIC) {
+        for (int a = 0; a < 7; a++) { s->cx[a] = 0.0; s->cy[a] = 0.0; }
+        s->cx[3] = 1.0 - dpx; s->cx[4] = dpx;          /* test_cic.F90:73-76 */
+        s->cy[3] = 1.0 - dpy; s->cy[4] = dpy;
+        return;
     }
     s->cx[0] = f_m6(3.0 + dpx); s->cx[6] = f_m6(3.0 - dpx);
     s->cx[1] = f_m6(2.0 + dpx); s->cx[5] = f_m6(2.0 - dpx);

@@ -49,6 +49,12 @@ def f_m6(q):
     return out / 120
 
 
+# shape function: "m6" (what the reference ships) or "cic" (BUILD-DEFINED: bilinear weights of
+# performance/test_cic.F90:73-76 = 2D restriction of fortran/compute_rho_cic.f90:46-53, with the wrap / ghost copy /
+# scaling / neutralisation of the M6 path; the reference has no 2D CIC deposit and no CIC in the UA loop)
+SCHEME = "m6"
+
+
 def _cell_weights(mesh, x, y):
     """src/interpolation.jl:19-64 / src/compute_rho.jl:63-110 : wrap, cell, 7+7 weights, wrapped indices.
     returns (xw, yw, ix[7,...], jy[7,...], cx[7,...], cy[7,...]) with 0-based node indices."""
@@ -65,8 +71,13 @@ def _cell_weights(mesh, x, y):
     offs = np.arange(-3, 4)
     ix = np.stack([(i if a == 0 else np.mod(i + a, mesh.nx)) for a in offs])
     jy = np.stack([(j if a == 0 else np.mod(j + a, mesh.ny)) for a in offs])
-    cx = np.stack([f_m6(3 + dpx), f_m6(2 + dpx), f_m6(1 + dpx), f_m6(dpx), f_m6(1 - dpx), f_m6(2 - dpx), f_m6(3 - dpx)])
-    cy = np.stack([f_m6(3 + dpy), f_m6(2 + dpy), f_m6(1 + dpy), f_m6(dpy), f_m6(1 - dpy), f_m6(2 - dpy), f_m6(3 - dpy)])
+    if SCHEME == "cic":
+        z = np.zeros_like(dpx)
+        cx = np.stack([z, z, z, 1 - dpx, dpx, z, z])
+        cy = np.stack([z, z, z, 1 - dpy, dpy, z, z])
+    else:
+        cx = np.stack([f_m6(3 + dpx), f_m6(2 + dpx), f_m6(1 + dpx), f_m6(dpx), f_m6(1 - dpx), f_m6(2 - dpx), f_m6(3 - dpx)])
+        cy = np.stack([f_m6(3 + dpy), f_m6(2 + dpy), f_m6(1 + dpy), f_m6(dpy), f_m6(1 - dpy), f_m6(2 - dpy), f_m6(3 - dpy)])
     return xn + mesh.xmin, yn + mesh.ymin, ix, jy, cx, cy
 
 

@@ -294,3 +294,44 @@ def test_interleaved_shards_generate_the_same_particles():
         assert np.array_equal(x, xf[:, rank::world]) and np.array_equal(v, vf[:, rank::world])
     r = np.hypot(vf[0], vf[1])
     assert r[: npart // 8].min() > r[-npart // 8:].max()      # |v| falls with the index: contiguous shards would be unbalanced
+
+
+@pytest.fixture
+def cic_oracle(corc):
+    corc.set_scheme("cic")
+    yield corc
+    corc.set_scheme("m6")
+
+
+@pytest.mark.parametrize("ntau,nx,ny,npart,nstep,eps", [(16, 128, 64, 20000, 8, 0.1), (32, 128, 128, 6001, 4, 0.1), (8, 64, 32, 5003, 3, 1e-2)])
+def test_cic_scheme_vs_oracle(cic_oracle, ntau, nx, ny, npart, nstep, eps):
+    """UAPIC_SCHEME_CIC (build-defined: bilinear weights of performance/test_cic.F90:73-76 in the same UA loop) against the
+    oracle's statement of the same definition; also Julia wrap and fixed-point determinism"""
+    import oracle
+    om, x0, v0 = seeded_load(npart, nx, ny, seed=8)
+    mesh = ub.Mesh(0, DIMX, nx, 0, DIMY, ny)
+    w = DIMX * DIMY / npart
+    xo, vo = x0.copy(order="F"), v0.copy(order="F")
+    eno, _, _, emesh_o = cic_oracle.run_bupdate(om, ntau, eps, DT, nstep, xo, vo, w)
+    xg, vg, eng, emesh_g, _, _ = _run(mesh, ntau, eps, nstep, x0, v0, w, ub.STORE_ONEPASS_LEAN, scheme=ub.SCHEME_CIC)
+    _compare(xg, vg, eng, xo, vo, eno, eps)
+    assert np.abs(emesh_g - emesh_o).max() < 1e-10 * np.abs(emesh_o).max()
+    # it is a different scheme from M6, not a relabelling
+    xm, vm, enm, _, _, _ = _run(mesh, ntau, eps, nstep, x0, v0, w, ub.STORE_ONEPASS_LEAN)
+    assert np.abs(enm - eng).max() > 1e-6 * np.abs(enm).max()
+    xo2, vo2 = x0.copy(order="F"), v0.copy(order="F")
+    eno2, _, _, _ = cic_oracle.run_bupdate(om, ntau, eps, DT, nstep, xo2, vo2, w, wrap=oracle.WRAP_JULIA)
+    xj, vj, enj, _, _, _ = _run(mesh, ntau, eps, nstep, x0, v0, w, ub.STORE_ONEPASS_LEAN, scheme=ub.SCHEME_CIC, wrap=ub.WRAP_JULIA)
+    _compare(xj, vj, enj, xo2, vo2, eno2, eps)
+    a = _run(mesh, ntau, eps, nstep, x0, v0, w, ub.STORE_ONEPASS_LEAN, scheme=ub.SCHEME_CIC, deposit_mode=ub.DEPOSIT_FIXED_POINT)
+    b = _run(mesh, ntau, eps, nstep, x0, v0, w, ub.STORE_ONEPASS_LEAN, scheme=ub.SCHEME_CIC, deposit_mode=ub.DEPOSIT_FIXED_POINT, sort=(0, 3))
+    for p, q in zip(a[:5], b[:5]):
+        assert np.array_equal(p, q)
+    _compare(a[0], a[1], a[2], xo, vo, eno, eps)
+
+
+def test_cic_needs_the_lean_one_pass_layout():
+    mesh = ub.Mesh(0, DIMX, 32, 0, DIMY, 16)
+    for mode in (ub.STORE_FULL, ub.STORE_HYBRID, ub.STORE_ONEPASS):
+        with pytest.raises(ub.UapicError, match="UAPIC_EUNSUPPORTED"):
+            ub.Session(mesh, 16, 0.1, DT, 100, scheme=ub.SCHEME_CIC, storage_mode=mode)

@@ -162,3 +162,45 @@ def test_c_oracle_against_golden(corc, path):
     assert np.abs(v - g["v"]).max() < tolv
     assert np.abs(en - g["energy"]).max() / np.abs(g["energy"]).max() < 1e-12
     assert np.abs(emesh - g["emesh"]).max() < 1e-11
+
+
+def test_cic_variant_c_vs_numpy_and_properties():
+    """the build-defined CIC scheme (bilinear weights of performance/test_cic.F90:73-76 inside the UA loop; the reference has no
+    such path): the two oracles state it independently and must agree; bilinear interpolation reproduces a bilinear field
+    exactly away from the periodic seam; the deposit is neutral after the epilogue"""
+    import oracle
+    from oracle import uapic_oracle_np as onp
+    c = oracle.corc()
+    dimx, dimy = 4 * np.pi, 2 * np.pi
+    om = oracle.mesh(0, dimx, 64, 0, dimy, 32)
+    m = onp.Mesh(0, dimx, 64, 0, dimy, 32)
+    rng = np.random.default_rng(5)
+    npart = 2000
+    x0, v0, _ = c.plasma_from_uniforms(om, npart, 0.05, 0.5, rng.random(npart * 80))
+    w = dimx * dimy / npart
+    dt = np.pi / 16
+    try:
+        c.set_scheme("cic"); onp.SCHEME = "cic"
+        assert c.scheme() == 1
+        xo, vo = x0.copy(order="F"), v0.copy(order="F")
+        en, _, _, _ = c.run_bupdate(om, 16, 0.1, dt, 4, xo, vo, w)
+        xn, vn, enn, _, _ = onp.run_bupdate(m, 16, 0.1, dt, 4, x0, v0, w)
+        assert np.abs(np.mod(xo[0] - xn[0] + dimx / 2, dimx) - dimx / 2).max() < 1e-12 * dimx
+        assert np.abs(vo - vn).max() < 1e-11 * np.abs(vo).max()
+        assert np.abs(en - enn).max() < 1e-13 * np.abs(en).max()
+        # bilinear field e1 = x*y, e2 = x - 2y on the nodes: reproduced exactly in the interior
+        e = np.zeros((2, 65, 33), order="F")
+        xs, ys = np.arange(65) * m.dx, np.arange(33) * m.dy
+        e[0], e[1] = np.outer(xs, ys), xs[:, None] - 2 * ys[None, :]
+        xp = np.asfortranarray(np.stack([rng.random(500) * (dimx - 2 * m.dx) + 0.5 * m.dx, rng.random(500) * (dimy - 2 * m.dy) + 0.5 * m.dy]))
+        ep = np.zeros_like(xp)
+        onp.interpol_eb_m6(m, e, xp.copy(), ep)
+        assert np.abs(ep[0] - xp[0] * xp[1]).max() < 1e-12 and np.abs(ep[1] - (xp[0] - 2 * xp[1])).max() < 1e-12
+        rho = np.zeros((65, 33))
+        onp.compute_rho_m6(m, rho, x0.copy(), w)
+        assert abs(rho[:64, :32].sum() * m.dx * m.dy) < 1e-10
+    finally:
+        c.set_scheme("m6"); onp.SCHEME = "m6"
+    xo, vo = x0.copy(order="F"), v0.copy(order="F")
+    en6, _, _, _ = c.run_bupdate(om, 16, 0.1, dt, 4, xo, vo, w)
+    assert np.abs(en6 - en).max() > 1e-6 * np.abs(en6).max()      # M6 and CIC are different schemes

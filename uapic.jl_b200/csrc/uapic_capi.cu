@@ -507,7 +507,7 @@ int session_field_solve(uapic_session *s) {
 OnepassParams session_onepass_params(uapic_session *s) {
     OnepassParams p;
     p.m = s->m; p.eps = s->cfg.eps; p.dt = s->cfg.dt; p.weight = s->cfg.weight; p.np = s->cfg.nbpart;
-    p.wrap = s->cfg.wrap; p.ntau = s->cfg.ntau; p.full = s->cfg.storage_mode == UAPIC_STORE_ONEPASS;
+    p.wrap = s->cfg.wrap; p.ntau = s->cfg.ntau; p.full = s->cfg.storage_mode == UAPIC_STORE_ONEPASS; p.scheme = s->cfg.scheme;
     p.x = s->x.as<double2>(); p.v = s->v.as<double2>(); p.ep = s->ep.as<double2>();
     p.ehalo = s->ehalo.as<double2>();
     p.store = s->store.as<char>(); p.rec = s->rec.as<double>();
@@ -575,7 +575,9 @@ int uapic_session_create(const uapic_config_t *cfg, uapic_session_t **out) {
     TRY(check_ntau(cfg->ntau));
     if (cfg->nbpart < 0) return fail(UAPIC_EINVAL, "nbpart must be >= 0");
     if (!(cfg->eps > 0) || !(cfg->dt > 0) || !(cfg->weight > 0)) return fail(UAPIC_EINVAL, "eps, dt and weight must be positive");
-    if (cfg->scheme != UAPIC_SCHEME_M6) return fail(UAPIC_EUNSUPPORTED, "only UAPIC_SCHEME_M6 is implemented in the session path");
+    if (cfg->scheme != UAPIC_SCHEME_M6 && cfg->scheme != UAPIC_SCHEME_CIC) return fail(UAPIC_EINVAL, "unknown scheme %d", cfg->scheme);
+    if (cfg->scheme == UAPIC_SCHEME_CIC && cfg->storage_mode != UAPIC_STORE_ONEPASS_LEAN)
+        return fail(UAPIC_EUNSUPPORTED, "UAPIC_SCHEME_CIC is implemented for storage_mode UAPIC_STORE_ONEPASS_LEAN only (ntau = 8, 16, 32)");
     const bool onepass = cfg->storage_mode == UAPIC_STORE_ONEPASS || cfg->storage_mode == UAPIC_STORE_ONEPASS_LEAN;
     if (cfg->storage_mode != UAPIC_STORE_FULL && cfg->storage_mode != UAPIC_STORE_HYBRID && !onepass) return fail(UAPIC_EINVAL, "unknown storage_mode %d", cfg->storage_mode);
     if (onepass && !onepass_ntau_supported(cfg->ntau)) return fail(UAPIC_EUNSUPPORTED, "the one-pass storage modes need ntau = 8, 16 or 32 (got %d)", cfg->ntau);
@@ -757,9 +759,9 @@ int uapic_session_init_fields(uapic_session_t *s) {
     TRY(session_bind(s));
     s->n_energy = 0;
     TRY(session_clear_raw(s));
-    CU(launch_deposit(s->lc, s->m, s->cfg.nbpart, s->x.as<double>(), s->cfg.weight, s->acc, s->cfg.wrap));   // bupdate.F90:89
+    CU(launch_deposit(s->lc, s->m, s->cfg.nbpart, s->x.as<double>(), s->cfg.weight, s->acc, s->cfg.wrap, s->cfg.scheme));   // bupdate.F90:89
     TRY(session_field_solve(s));                                                                              // :91
-    CU(launch_gather(s->lc, s->m, s->emesh.as<double>(), s->cfg.nbpart, s->x.as<double>(), s->ep.as<double>(), s->cfg.wrap));  // :93
+    CU(launch_gather(s->lc, s->m, s->emesh.as<double>(), s->cfg.nbpart, s->x.as<double>(), s->ep.as<double>(), s->cfg.wrap, s->cfg.scheme));  // :93
     s->fields_ready = true;
     return UAPIC_OK;
 }

@@ -103,6 +103,27 @@ DEVINL void gather_tiled(const MeshDev &m, const double2 *__restrict__ ehalo, co
     e1 = s1; e2 = s2;
 }
 
+// ---- CIC (bilinear), BUILD-DEFINED: the reference has no 2D CIC deposit and no CIC in the UA loop.
+// Weights of performance/test_cic.F90:73-76 (= 2D restriction of fortran/compute_rho_cic.f90:46-53) on nodes (i,j), (i+1,j),
+// (i+1,j+1), (i,j+1); wrap, ghost copy, /(dx dy) and neutralisation as on the M6 path.  oracle/uapic_oracle.c states the same.
+DEVINL void gather_cic_tiled(const MeshDev &m, const double2 *__restrict__ ehalo, const Cell &c, double &e1, double &e2) {
+    const int ntx = halo_tiled_ntx(m);
+    const int I = c.i + 2, J = c.j + 2;                 // halo coordinates of node (i, j); (i+1, j+1) never needs a wrap there
+    const double2 e00 = __ldg(ehalo + halo_tiled_index(ntx, I, J)), e10 = __ldg(ehalo + halo_tiled_index(ntx, I + 1, J));
+    const double2 e01 = __ldg(ehalo + halo_tiled_index(ntx, I, J + 1)), e11 = __ldg(ehalo + halo_tiled_index(ntx, I + 1, J + 1));
+    const double ax = 1.0 - c.dpx, ay = 1.0 - c.dpy;
+    const double a1 = ax * ay, a2 = c.dpx * ay, a3 = c.dpx * c.dpy, a4 = ax * c.dpy;
+    e1 = fma(a4, e01.x, fma(a3, e11.x, fma(a2, e10.x, a1 * e00.x)));
+    e2 = fma(a4, e01.y, fma(a3, e11.y, fma(a2, e10.y, a1 * e00.y)));
+}
+
+// tap q of the 4-tap CIC deposit: 0 (i,j), 1 (i+1,j), 2 (i,j+1), 3 (i+1,j+1)
+DEVINL void deposit_cic_tap(const MeshDev &m, const RhoAcc &r, const Cell &c, double weight, int q) {
+    const int ox = q & 1, oy = q >> 1;
+    const double wx = ox ? c.dpx : 1.0 - c.dpx, wy = oy ? c.dpy : 1.0 - c.dpy;
+    rho_add(r, wrap_fast(c.i, ox, m.nx) + wrap_fast(c.j, oy, m.ny) * m.ld, wx * wy * weight);
+}
+
 // f_m6 without branches (q >= 0): the three pieces of compute_rho_m6.F90:33-41 are the same sum of truncated powers
 DEVINL double f_m6_branchless(double q) {
     const double a = fmax(3.0 - q, 0.0), b = fmax(2.0 - q, 0.0), c = fmax(1.0 - q, 0.0);

@@ -37,9 +37,9 @@ cudaError_t launch_deposit_tau(const LaunchCtx &c, const MeshDev &m, int ntau, d
 cudaError_t launch_compute_v(const LaunchCtx &c, int ntau, double eps, int64_t np, const double *t, const double *yt,
                              int yt_is_fourier, double *v);
 cudaError_t launch_deposit(const LaunchCtx &c, const MeshDev &m, int64_t np, double *x, double w, const RhoAcc &acc,
-                           int wrap);
+                           int wrap, int scheme = 0);
 cudaError_t launch_gather(const LaunchCtx &c, const MeshDev &m, const double *emesh, int64_t np, double *x, double *ep,
-                          int wrap);
+                          int wrap, int scheme = 0);
 
 // ---- mesh kernels ---------------------------------------------------------------------------------------------
 // raw accumulation (fp64 or fixed point) -> neutralised rho with ghosts; rho_total (1 double) may be null
@@ -84,6 +84,7 @@ struct OnepassParams {
     int wrap;
     int ntau;              // 8, 16 or 32
     int full;              // 1: 72 B per particle-tau (W_n and interv stored); 0: 48 B (phase B recomputes them)
+    int scheme;            // UAPIC_SCHEME_M6 (0) or UAPIC_SCHEME_CIC (1, build-defined; lean layout only)
     double2 *x;            // (2,np): read and rewritten (corrector position) by A
     double2 *v;            // (2,np): read by A, written by B
     const double2 *ep;     // (2,np): particles.e, frozen after init

@@ -255,25 +255,44 @@ __global__ void __launch_bounds__(kBlock) k_compute_v(double eps, int64_t np, co
 }
 
 // compute_rho_m6_real (per-particle part)              compute_rho_m6.F90:221-327 / src/compute_rho.jl:195-300
-__global__ void __launch_bounds__(kBlock) k_deposit(MeshDev m, int64_t np, double *x, double w, RhoAcc acc, int wrap) {
+__global__ void __launch_bounds__(kBlock) k_deposit(MeshDev m, int64_t np, double *x, double w, RhoAcc acc, int wrap, int scheme) {
     for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < np; k += (int64_t)gridDim.x * blockDim.x) {
         const double2 xx = ld2(x, k);
         double xw, yw;
         const Cell c = m6_cell_exact(m, xx.x, xx.y, wrap, xw, yw);
         if (wrap == kWrapJulia) reinterpret_cast<double2 *>(x)[k] = make_double2(xw, yw);
-        m6_scatter(m, acc, c, w, 0, 1);
+        if (scheme == 1) {      // build-defined CIC: weights of performance/test_cic.F90:73-76, products in the oracle's order
+            for (int q = 0; q < 4; ++q) {
+                const int ox = q >> 1, oy = q & 1;
+                const double wx = ox ? c.dpx : __dsub_rn(1.0, c.dpx), wy = oy ? c.dpy : __dsub_rn(1.0, c.dpy);
+                rho_add(acc, wrap_index(c.i, ox, m.nx) + wrap_index(c.j, oy, m.ny) * m.ld, __dmul_rn(__dmul_rn(wx, wy), w));
+            }
+        } else {
+            m6_scatter(m, acc, c, w, 0, 1);
+        }
     }
 }
 
 // interpolate_eb_m6_real                               interpolation_m6.F90:193-327 / src/interpolation.jl:125-247
 __global__ void __launch_bounds__(kBlock) k_gather(MeshDev m, const double2 *__restrict__ emesh, int64_t np, double *x, double *ep,
-                                                   int wrap) {
+                                                   int wrap, int scheme) {
     for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < np; k += (int64_t)gridDim.x * blockDim.x) {
         const double2 xx = ld2(x, k);
         double xw, yw;
         const Cell c = m6_cell_exact(m, xx.x, xx.y, wrap, xw, yw);
         if (wrap == kWrapJulia) reinterpret_cast<double2 *>(x)[k] = make_double2(xw, yw);
         double e1, e2;
+        if (scheme == 1) {      // build-defined CIC, summed in the oracle's order: x offset outer, y offset inner
+            e1 = 0.0; e2 = 0.0;
+            for (int q = 0; q < 4; ++q) {
+                const int ox = q >> 1, oy = q & 1;
+                const double wx = ox ? c.dpx : __dsub_rn(1.0, c.dpx), wy = oy ? c.dpy : __dsub_rn(1.0, c.dpy);
+                const double2 ev = emesh[wrap_index(c.i, ox, m.nx) + wrap_index(c.j, oy, m.ny) * m.ld];
+                const double wq = __dmul_rn(wx, wy);
+                e1 = __dadd_rn(e1, __dmul_rn(wq, ev.x));
+                e2 = __dadd_rn(e2, __dmul_rn(wq, ev.y));
+            }
+        } else
         m6_gather_exact(m, emesh, c, e1, e2);
         reinterpret_cast<double2 *>(ep)[k] = make_double2(e1, e2);
     }
@@ -676,17 +695,17 @@ cudaError_t launch_compute_v(const LaunchCtx &c, int ntau, double eps, int64_t n
 }
 
 cudaError_t launch_deposit(const LaunchCtx &c, const MeshDev &m, int64_t np, double *x, double w, const RhoAcc &acc,
-                           int wrap) {
+                           int wrap, int scheme) {
     if (np <= 0) return cudaSuccess;
-    k_deposit<<<grid_for(c, np, kBlock), kBlock, 0, c.stream>>>(m, np, x, w, acc, wrap);
+    k_deposit<<<grid_for(c, np, kBlock), kBlock, 0, c.stream>>>(m, np, x, w, acc, wrap, scheme);
     count(c);
     return cudaGetLastError();
 }
 
 cudaError_t launch_gather(const LaunchCtx &c, const MeshDev &m, const double *emesh, int64_t np, double *x, double *ep,
-                          int wrap) {
+                          int wrap, int scheme) {
     if (np <= 0) return cudaSuccess;
-    k_gather<<<grid_for(c, np, kBlock), kBlock, 0, c.stream>>>(m, reinterpret_cast<const double2 *>(emesh), np, x, ep, wrap);
+    k_gather<<<grid_for(c, np, kBlock), kBlock, 0, c.stream>>>(m, reinterpret_cast<const double2 *>(emesh), np, x, ep, wrap, scheme);
     count(c);
     return cudaGetLastError();
 }

@@ -89,6 +89,7 @@ constexpr int kWarpSmA = 8 * kRow + 4 * kRow + 16 * 32;  // exchange rows + sin-
 constexpr int kWarpSmB = 8 * kRow + 256;       // W_n exchange rows + partial sums of the tau* evaluation
 
 constexpr double kRsqrt2 = 0.70710678118654752440;
+constexpr int kSchemeM6 = 0, kSchemeCic = 1;      // UAPIC_SCHEME_*
 
 // ---- 8-point FFT in registers, natural order in and out; SGN = -1 forward (exp(-i..)), +1 backward ---------------
 template <int SGN> DEVINL cd mul_i(cd a) { return SGN > 0 ? mk(-a.im, a.re) : mk(a.im, -a.re); }            // a * (SGN i)
@@ -331,7 +332,7 @@ template <int N, bool FULL> struct StoreMap {
 };
 
 // =================================================================================================
-template <int G, bool FULL>
+template <int G, bool FULL, int SCHEME>
 __global__ void __launch_bounds__(kOpBlockA, UAPIC_OP_MINB_A) k_onepass_a(OpDev D) {
     constexpr int N = 8 * G, PW = 32 / G, PPI = 32 / N;     // particles per warp tile / per gather iteration
     constexpr int kOpWarps = kOpBlockA / 32;
@@ -391,7 +392,7 @@ __global__ void __launch_bounds__(kOpBlockA, UAPIC_OP_MINB_A) k_onepass_a(OpDev 
             const double2 pos = gx[row * kRow + col];
             double xw, yw, e1, e2;
             const Cell cell = cell_fast(P.m, D.f, pos.x, pos.y, P.wrap, xw, yw);
-            gather_tiled(P.m, P.ehalo, cell, e1, e2);
+            if (SCHEME == kSchemeCic) gather_cic_tiled(P.m, P.ehalo, cell, e1, e2); else gather_tiled(P.m, P.ehalo, cell, e1, e2);
             gx[row * kRow + col] = make_double2(e1, e2);
             sps[row * kRow + col] = sin(pos.x) * sin(pos.y);
         }
@@ -582,9 +583,23 @@ __global__ void __launch_bounds__(kOpBlockA, UAPIC_OP_MINB_A) k_onepass_a(OpDev 
         qa1 = grp_sum<G>(qa1); qa2 = grp_sum<G>(qa2);
         double xw, yw;
         const Cell cp = cell_fast(P.m, D.f, posp1, posp2, P.wrap, xw, yw);
-        deposit_split<G>(P.m, P.rho_p, cp, P.weight, g, valid);              // compute_rho_m6.F90:89-187 (predictor)
+        if (SCHEME == kSchemeCic) {
+            if (valid) {
+#pragma unroll
+                for (int q = 0; q < 4 / G; ++q) deposit_cic_tap(P.m, P.rho_p, cp, P.weight, g * (4 / G) + q);
+            }
+        } else {
+            deposit_split<G>(P.m, P.rho_p, cp, P.weight, g, valid);          // compute_rho_m6.F90:89-187 (predictor)
+        }
         const Cell cc = cell_fast(P.m, D.f, posc1, posc2, P.wrap, xw, yw);
-        deposit_split<G>(P.m, P.rho_c, cc, P.weight, g, valid);              // (corrector)
+        if (SCHEME == kSchemeCic) {
+            if (valid) {
+#pragma unroll
+                for (int q = 0; q < 4 / G; ++q) deposit_cic_tap(P.m, P.rho_c, cc, P.weight, g * (4 / G) + q);
+            }
+        } else {
+            deposit_split<G>(P.m, P.rho_c, cc, P.weight, g, valid);          // (corrector)
+        }
         if (valid && g == 0) {
             P.x[ip] = make_double2(xw, yw);                                  // compute_rho_m6.F90:86-87
             double2 *rec = reinterpret_cast<double2 *>(P.rec + 8 * ip);
@@ -598,7 +613,7 @@ __global__ void __launch_bounds__(kOpBlockA, UAPIC_OP_MINB_A) k_onepass_a(OpDev 
 }
 
 // =================================================================================================
-template <int G, bool FULL>
+template <int G, bool FULL, int SCHEME>
 __global__ void __launch_bounds__(kOpBlockB, UAPIC_OP_MINB_B) k_onepass_b(OpDev D) {
     constexpr int N = 8 * G, PW = 32 / G, PPI = 32 / N;
     constexpr int kOpWarps = kOpBlockB / 32;
@@ -673,7 +688,7 @@ __global__ void __launch_bounds__(kOpBlockB, UAPIC_OP_MINB_B) k_onepass_b(OpDev 
             // ---- gather E_pred at the predicted samples (interpolation_m6.F90:83-189) ----
             double xw, yw, e1, e2;
             const Cell cell = cell_fast(P.m, D.f, xs.x, xs.y, P.wrap, xw, yw);
-            gather_tiled(P.m, P.ehalo, cell, e1, e2);
+            if (SCHEME == kSchemeCic) gather_cic_tiled(P.m, P.ehalo, cell, e1, e2); else gather_tiled(P.m, P.ehalo, cell, e1, e2);
             cd gy1, gy2;
             fy_time(csn.x, csn.y, rb, iv, mk(ya.x, ya.y), mk(yb.x, yb.y), e1, e2, gy1, gy2);     // :177-183
             // terms of Re sum_n gy(tau_n) W_n: summed over n after the loop (one pass through shared memory instead of a
@@ -737,15 +752,17 @@ template <typename K> cudaError_t op_launch(K kernel, const LaunchCtx &c, const 
 bool onepass_ntau_supported(int ntau) { return ntau == 8 || ntau == 16 || ntau == 32; }
 size_t onepass_store_bytes_per_particle(int ntau, int full) { return (size_t)(full ? 72 : 48) * (size_t)ntau; }
 
-#define UAPIC_OP_DISPATCH(KERNEL, MINB, BLOCK, SMEM)                                                               \
-    switch (p.ntau) {                                                                                              \
-        case 8:  return p.full ? op_launch(KERNEL<1, true>, c, D, op_grid(c, p.np, 8, MINB, BLOCK), BLOCK, SMEM)   \
-                               : op_launch(KERNEL<1, false>, c, D, op_grid(c, p.np, 8, MINB, BLOCK), BLOCK, SMEM); \
-        case 16: return p.full ? op_launch(KERNEL<2, true>, c, D, op_grid(c, p.np, 16, MINB, BLOCK), BLOCK, SMEM)  \
-                               : op_launch(KERNEL<2, false>, c, D, op_grid(c, p.np, 16, MINB, BLOCK), BLOCK, SMEM);\
-        case 32: return p.full ? op_launch(KERNEL<4, true>, c, D, op_grid(c, p.np, 32, MINB, BLOCK), BLOCK, SMEM)  \
-                               : op_launch(KERNEL<4, false>, c, D, op_grid(c, p.np, 32, MINB, BLOCK), BLOCK, SMEM);\
-        default: return cudaErrorInvalidValue;                                                                     \
+#define UAPIC_OP_LAUNCH(KERNEL, GG, MINB, BLOCK, SMEM)                                                                       \
+    (p.scheme == kSchemeCic ? op_launch(KERNEL<GG, false, kSchemeCic>, c, D, op_grid(c, p.np, 8 * GG, MINB, BLOCK), BLOCK, SMEM)     \
+     : p.full             ? op_launch(KERNEL<GG, true, kSchemeM6>, c, D, op_grid(c, p.np, 8 * GG, MINB, BLOCK), BLOCK, SMEM)       \
+                          : op_launch(KERNEL<GG, false, kSchemeM6>, c, D, op_grid(c, p.np, 8 * GG, MINB, BLOCK), BLOCK, SMEM))
+#define UAPIC_OP_DISPATCH(KERNEL, MINB, BLOCK, SMEM)                  \
+    if (p.scheme == kSchemeCic && p.full) return cudaErrorInvalidValue; \
+    switch (p.ntau) {                                                 \
+        case 8:  return UAPIC_OP_LAUNCH(KERNEL, 1, MINB, BLOCK, SMEM); \
+        case 16: return UAPIC_OP_LAUNCH(KERNEL, 2, MINB, BLOCK, SMEM); \
+        case 32: return UAPIC_OP_LAUNCH(KERNEL, 4, MINB, BLOCK, SMEM); \
+        default: return cudaErrorInvalidValue;                        \
     }
 
 cudaError_t launch_onepass_a(const LaunchCtx &c, const OnepassParams &p) {
