@@ -52,6 +52,8 @@ def _run(mesh, ntau, eps, nstep, x0, v0, w, mode, sort=None, **kw):
     (16, 128, 64, 6000, 4, 1e-3),
     (32, 256, 256, 3000, 2, 0.1),       # config 5 mesh
     (32, 20, 12, 777, 3, 0.1),          # non power-of-two mesh, fewer particles than one CTA sweep
+    (16, 32, 16, 7, 2, 0.1),            # fewer particles than one warp tile
+    (8, 32, 16, 1, 2, 0.1),             # a single particle
 ])
 def test_onepass_session_vs_oracle(corc, mode, ntau, nx, ny, npart, nstep, eps):
     om, x0, v0 = seeded_load(npart, nx, ny, seed=5)
