@@ -62,6 +62,24 @@ namespace {
 #ifndef UAPIC_OP_PREFETCH
 #define UAPIC_OP_PREFETCH 1
 #endif
+// sync points of phase A: OP_STEP_SM also orders shared-memory accesses inside the warp (must at least be a __syncwarp);
+// OP_STEP_OPT only keeps the lock-step group together
+#ifndef UAPIC_OP_SYNC_VARIANT
+#define UAPIC_OP_SYNC_VARIANT 0
+#endif
+#if UAPIC_OP_SYNC_VARIANT == 0
+#define OP_STEP_OPT() OP_STEP()
+#define OP_STEP_SM() OP_STEP()
+#elif UAPIC_OP_SYNC_VARIANT == 1
+#define OP_STEP_OPT() ((void)0)
+#define OP_STEP_SM() OP_STEP()
+#elif UAPIC_OP_SYNC_VARIANT == 2
+#define OP_STEP_OPT() OP_STEP()
+#define OP_STEP_SM() __syncwarp()
+#else
+#define OP_STEP_OPT() ((void)0)
+#define OP_STEP_SM() __syncwarp()
+#endif
 #ifndef UAPIC_OP_GATHER_UNROLL
 #define UAPIC_OP_GATHER_UNROLL 1
 #endif
@@ -76,8 +94,32 @@ constexpr int kGatherUnroll = UAPIC_OP_GATHER_UNROLL;
 #ifndef UAPIC_OP_TWIDDLE_TABLE
 #define UAPIC_OP_TWIDDLE_TABLE 1     // 0: powers of u1 by recurrence (measured slower: +4 live registers tip phase A into 400 B of spills)
 #endif
+#ifndef UAPIC_OP_BLOCKED_A
+#define UAPIC_OP_BLOCKED_A 0
+#endif
+#ifndef UAPIC_OP_BLOCKED_B
+#define UAPIC_OP_BLOCKED_B 1
+#endif
 #ifndef UAPIC_OP_PREFETCH_B
 #define UAPIC_OP_PREFETCH_B 2
+#endif
+// sync points of phase A: OP_STEP_SM also orders shared-memory accesses inside the warp (must at least be a __syncwarp);
+// OP_STEP_OPT only keeps the lock-step group together
+#ifndef UAPIC_OP_SYNC_VARIANT
+#define UAPIC_OP_SYNC_VARIANT 0
+#endif
+#if UAPIC_OP_SYNC_VARIANT == 0
+#define OP_STEP_OPT() OP_STEP()
+#define OP_STEP_SM() OP_STEP()
+#elif UAPIC_OP_SYNC_VARIANT == 1
+#define OP_STEP_OPT() ((void)0)
+#define OP_STEP_SM() OP_STEP()
+#elif UAPIC_OP_SYNC_VARIANT == 2
+#define OP_STEP_OPT() OP_STEP()
+#define OP_STEP_SM() __syncwarp()
+#else
+#define OP_STEP_OPT() ((void)0)
+#define OP_STEP_SM() __syncwarp()
 #endif
 #ifndef UAPIC_OP_GATHER_UNROLL_B
 #define UAPIC_OP_GATHER_UNROLL_B 2
@@ -347,22 +389,31 @@ __global__ void __launch_bounds__(kOpBlockA, UAPIC_OP_MINB_A) k_onepass_a(OpDev 
     const int g = L.g, pin = lane / G, gbase = lane - g;
     const double eps = P.eps, inv_eps = D.inv_eps, invN = 1.0 / (double)N;
     const int64_t ntiles = (P.np + PW - 1) / PW;
+#if UAPIC_OP_BLOCKED_A
+    // every CTA owns a CONTIGUOUS range of tiles (experiment: did NOT help phase A -- the strided sweep, where all CTAs write
+    // one moving window of the store, is 6 % faster)
+    const int64_t tiles_per_cta = (ntiles + gridDim.x - 1) / gridDim.x;
+    const int64_t t_first = (int64_t)blockIdx.x * tiles_per_cta, t_end = min(t_first + tiles_per_cta, ntiles);
+    const int64_t nwarps = kOpWarps;
+#else
+    const int64_t t_first = (int64_t)blockIdx.x * kOpWarps, t_end = ntiles;
     const int64_t nwarps = (int64_t)gridDim.x * kOpWarps;
+#endif
 
     // the trip count is uniform over the CTA (a warp past the end works on a clamped copy of the last particle with its
     // stores and deposits switched off) so that the warps of a CTA can be kept in step: they then share instruction
     // fetches of this long straight-line kernel (UAPIC_OP_LOCKSTEP)
-    for (int64_t tbase = (int64_t)blockIdx.x * kOpWarps; tbase < ntiles; tbase += nwarps) {
+    for (int64_t tbase = t_first; tbase < t_end; tbase += nwarps) {
         const int64_t tile = tbase + wib;
         const int64_t kraw = tile * PW + pin;
-        const bool valid = kraw < P.np;
+        const bool valid = tile < t_end && kraw < P.np;
         const int64_t ip = valid ? kraw : P.np - 1;
         const double2 xx = P.x[ip], vv = P.v[ip], ee = P.ep[ip];
         const double x1 = xx.x, x2 = xx.y, vx = vv.x, vy = vv.y;
 #if UAPIC_OP_PREFETCH
         {   // the CTA's next tiles: their particle data would otherwise be a cold HBM access all warps of the CTA wait on together
             const int64_t nk = kraw + nwarps * PW;
-            if (g == 0 && nk < P.np) {
+            if (g == 0 && nk < P.np && tile + nwarps < t_end) {
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(P.x + nk));
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(P.v + nk));
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(P.ep + nk));
@@ -382,7 +433,7 @@ __global__ void __launch_bounds__(kOpBlockA, UAPIC_OP_MINB_A) k_onepass_a(OpDev 
             const double xt2 = x2 + eps * (c.y * vyb + c.x * vxb) - eps * vxb;   // :79-82
             gx[s * kRow + lane] = make_double2(xt1, xt2);
         }
-        OP_STEP();
+        OP_STEP_SM();
         // ---- gather E_n at the samples, lane = sample (interpolation_m6.F90:83-189); the sines of :87 ride along so that
         //      the 16 sin() of a lane sit in this rolled loop instead of the unrolled code below ----
 #pragma unroll (kGatherUnroll)
@@ -433,7 +484,7 @@ __global__ void __launch_bounds__(kOpBlockA, UAPIC_OP_MINB_A) k_onepass_a(OpDev 
                 yhs[(8 + k1) * 32 + lane] = make_double2(y2.re, y2.im);
             }
         }
-        OP_STEP();
+        OP_STEP_SM();
 
         // ---- exp(-i l t/eps), pl, ql/t, w = ql/t * conj(elt) for the lane's modes ----
         cd e1;
@@ -492,7 +543,7 @@ __global__ void __launch_bounds__(kOpBlockA, UAPIC_OP_MINB_A) k_onepass_a(OpDev 
         }
 
         // ---- y: yt = B(yhat) (:105-110), fy in the time domain (:177-183), FFT, ua_step1 (:226), bracket sums ----
-        OP_STEP();
+        OP_STEP_OPT();
         // yhat1, yhat2 are spectra of real signals (:92-106) except for two coefficients: the Nyquist mode, which the filter
         // -i/l turns purely imaginary, and the mean, which carries minus its value (:109-110).  So ONE backward transform of
         // H = H1 + i H2 (H: Hermitian parts) gives Re yt1 + i Re yt2, and Im yt_n = Im yhat_0 + (-1)^n Im yhat_{N/2}.
@@ -523,7 +574,7 @@ __global__ void __launch_bounds__(kOpBlockA, UAPIC_OP_MINB_A) k_onepass_a(OpDev 
             const double iv = (1.0 + 0.5 * sps[s * kRow + lane] - b) * inv_eps;       // :177, same as :87
             fy_time(c.x, c.y, rb, iv, y1[s], y2[s], et.x, et.y, y1[s], y2[s]);
         }
-        OP_STEP();
+        OP_STEP_OPT();
         fwdN<G>(y1, L);                                                      // :189-190
         fwdN<G>(y2, L);
         double qa1 = 0.0, qa2 = 0.0;
@@ -556,7 +607,7 @@ __global__ void __launch_bounds__(kOpBlockA, UAPIC_OP_MINB_A) k_onepass_a(OpDev 
                 swg2 += re_mul(wv[k1], gx2);
             }
         }
-        OP_STEP();
+        OP_STEP_OPT();
         bwdN<G>(y1, L);                                                      // :232
         bwdN<G>(y2, L);
         if (valid) {
@@ -582,6 +633,10 @@ __global__ void __launch_bounds__(kOpBlockA, UAPIC_OP_MINB_A) k_onepass_a(OpDev 
         const double posc1 = posp1 + grp_sum<G>(swg1 - swf1), posc2 = posp2 + grp_sum<G>(swg2 - swf2);
         qa1 = grp_sum<G>(qa1); qa2 = grp_sum<G>(qa2);
         double xw, yw;
+#ifdef UAPIC_OP_EXPERIMENT_NO_DEPOSIT      // timing experiment only: what the two deposits cost
+        const bool valid_dep = valid && P.np < 0;
+#define valid valid_dep
+#endif
         const Cell cp = cell_fast(P.m, D.f, posp1, posp2, P.wrap, xw, yw);
         if (SCHEME == kSchemeCic) {
             if (valid) {
@@ -600,6 +655,9 @@ __global__ void __launch_bounds__(kOpBlockA, UAPIC_OP_MINB_A) k_onepass_a(OpDev 
         } else {
             deposit_split<G>(P.m, P.rho_c, cc, P.weight, g, valid);          // (corrector)
         }
+#ifdef UAPIC_OP_EXPERIMENT_NO_DEPOSIT
+#undef valid
+#endif
         if (valid && g == 0) {
             P.x[ip] = make_double2(xw, yw);                                  // compute_rho_m6.F90:86-87
             double2 *rec = reinterpret_cast<double2 *>(P.rec + 8 * ip);
@@ -629,9 +687,16 @@ __global__ void __launch_bounds__(kOpBlockB, UAPIC_OP_MINB_B) k_onepass_b(OpDev 
     const int n = lane & (N - 1);
     const double2 csn = L.cs[n];
     const int64_t ntiles = (P.np + PW - 1) / PW;
+#if UAPIC_OP_BLOCKED_B   // a contiguous range of tiles per CTA: measured -2 % for phase B (+6 % for phase A, which keeps the strided sweep)
+    const int64_t tiles_per_cta = (ntiles + gridDim.x - 1) / gridDim.x;
+    const int64_t t_first = (int64_t)blockIdx.x * tiles_per_cta, t_end = min(t_first + tiles_per_cta, ntiles);
+    const int64_t nwarps = kOpWarps;
+#else
+    const int64_t t_first = (int64_t)blockIdx.x * kOpWarps, t_end = ntiles;
     const int64_t nwarps = (int64_t)gridDim.x * kOpWarps;
+#endif
 
-    for (int64_t tile = (int64_t)blockIdx.x * kOpWarps + wib; tile < ntiles; tile += nwarps) {
+    for (int64_t tile = t_first + wib; tile < t_end; tile += nwarps) {
         if (!FULL) {
             // W_n of the tile's particles in the phase-A layout, handed to the sample lanes through shared memory
             const int64_t kraw = tile * PW + pin;
@@ -667,7 +732,7 @@ __global__ void __launch_bounds__(kOpBlockB, UAPIC_OP_MINB_B) k_onepass_b(OpDev 
             {   // the store is streamed exactly once: ask L2 for the lines of the particle two iterations ahead
                 const int j2 = j + UAPIC_OP_PREFETCH_B;
                 const int64_t k2 = (j2 < 8 ? tile : tile + nwarps) * PW + (j2 & 7) * PPI + lane / N;
-                if ((n & 7) == 0 && k2 < P.np) {
+                if ((n & 7) == 0 && k2 < P.np && (j2 < 8 || tile + nwarps < t_end)) {
                     const char *b2 = P.store + (size_t)k2 * SM::stride + 16 * n;
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(b2));
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(b2 + 16 * N));
