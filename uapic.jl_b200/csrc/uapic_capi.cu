@@ -417,6 +417,9 @@ int uapic_compute_v(int ntau, double eps, int64_t nbpart, const double *t, const
 // session
 // ================================================================================================
 
+#ifndef UAPIC_RAW_COPIES
+#define UAPIC_RAW_COPIES 1
+#endif
 struct uapic_session {
     uapic_config_t cfg;
     MeshDev m;
@@ -614,7 +617,7 @@ int uapic_session_create(const uapic_config_t *cfg, uapic_session_t **out) {
     if (!rc && !onepass) rc = session_alloc(s, s->tb, 16 * (np ? np : 1));
     const size_t per_tau = onepass ? (cfg->storage_mode == UAPIC_STORE_ONEPASS ? 72 : 48) : (cfg->storage_mode == UAPIC_STORE_HYBRID ? 16 : 128);
     if (!rc) rc = session_alloc(s, s->store, per_tau * N * (np ? np : 1));
-    if (!rc) rc = session_alloc(s, s->raw, 8 * nrho * (onepass ? 2 : 1));
+    if (!rc) rc = session_alloc(s, s->raw, 8 * nrho * (onepass ? 2 * UAPIC_RAW_COPIES : 1));
     if (onepass) {
         if (!rc) rc = session_alloc(s, s->rec, 64 * (np ? np : 1));
         if (!rc) rc = session_alloc(s, s->emesh_p, 16 * nrho);

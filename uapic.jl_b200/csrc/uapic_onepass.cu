@@ -637,23 +637,33 @@ __global__ void __launch_bounds__(kOpBlockA, UAPIC_OP_MINB_A) k_onepass_a(OpDev 
         const bool valid_dep = valid && P.np < 0;
 #define valid valid_dep
 #endif
+#ifdef UAPIC_OP_EXPERIMENT_PRIVATE_RHO   // timing experiment only (results are wrong): CTA-private copies of the raw meshes
+        RhoAcc rp = P.rho_p, rc = P.rho_c;
+        { const size_t off = (size_t)(blockIdx.x % UAPIC_OP_EXPERIMENT_PRIVATE_RHO) * 2 * (size_t)P.m.ld * (P.m.ny + 1);
+          if (rp.f64) { rp.f64 += off; rc.f64 += off; } else { rp.i64 += off; rc.i64 += off; } }
+#define rho_p_sel rp
+#define rho_c_sel rc
+#else
+#define rho_p_sel P.rho_p
+#define rho_c_sel P.rho_c
+#endif
         const Cell cp = cell_fast(P.m, D.f, posp1, posp2, P.wrap, xw, yw);
         if (SCHEME == kSchemeCic) {
             if (valid) {
 #pragma unroll
-                for (int q = 0; q < 4 / G; ++q) deposit_cic_tap(P.m, P.rho_p, cp, P.weight, g * (4 / G) + q);
+                for (int q = 0; q < 4 / G; ++q) deposit_cic_tap(P.m, rho_p_sel, cp, P.weight, g * (4 / G) + q);
             }
         } else {
-            deposit_split<G>(P.m, P.rho_p, cp, P.weight, g, valid);          // compute_rho_m6.F90:89-187 (predictor)
+            deposit_split<G>(P.m, rho_p_sel, cp, P.weight, g, valid);          // compute_rho_m6.F90:89-187 (predictor)
         }
         const Cell cc = cell_fast(P.m, D.f, posc1, posc2, P.wrap, xw, yw);
         if (SCHEME == kSchemeCic) {
             if (valid) {
 #pragma unroll
-                for (int q = 0; q < 4 / G; ++q) deposit_cic_tap(P.m, P.rho_c, cc, P.weight, g * (4 / G) + q);
+                for (int q = 0; q < 4 / G; ++q) deposit_cic_tap(P.m, rho_c_sel, cc, P.weight, g * (4 / G) + q);
             }
         } else {
-            deposit_split<G>(P.m, P.rho_c, cc, P.weight, g, valid);          // (corrector)
+            deposit_split<G>(P.m, rho_c_sel, cc, P.weight, g, valid);          // (corrector)
         }
 #ifdef UAPIC_OP_EXPERIMENT_NO_DEPOSIT
 #undef valid
