@@ -205,7 +205,8 @@ def main():
     np_global = np_cfg * world if mode == "per_gpu" else np_cfg
     np_gpu = np_global // world
     mesh = ub.Mesh(0, DIMX, nx, 0, DIMY, ny)
-    lo, hi = ub.dist.shard_range(np_global, rank, world)
+    first, stride, n_mine = ub.dist.interleaved_shard(np_global, rank, world)   # global index = rank + k*world (see dist.py)
+    lo, hi = 0, n_mine
     stream = torch.cuda.current_stream().cuda_stream
     free_b, _ = torch.cuda.mem_get_info()
     PER_TAU = {"full": 128, "hybrid": 16, "onepass": 72, "onepass-lean": 48}
@@ -223,7 +224,7 @@ def main():
     if world > 1:
         ub.dist.attach_torch_allreduce(s)
     # interleaved shards (global index = rank + k*world): the Landau load stratifies |v| by particle index
-    s.generate_particles(load, seed=20190101, first_global_index=rank, index_stride=world)
+    s.generate_particles(load, seed=20190101, first_global_index=first, index_stride=stride)
     s.init_fields()
     s.step(args.warmup)
     s.synchronize()

@@ -24,6 +24,17 @@ def test_shard_range_partitions_exactly():
             assert max(sizes) - min(sizes) <= 1
 
 
+def test_interleaved_shard_partitions_exactly():
+    for n in (0, 1, 7, 204800, 10**8 + 3):
+        for world in (1, 2, 3, 8):
+            parts = [ub.dist.interleaved_shard(n, r, world) for r in range(world)]
+            assert sum(c for _, _, c in parts) == n
+            if n <= 204800:
+                ids = np.concatenate([f + st * np.arange(c) for f, st, c in parts]) if n else np.zeros(0)
+                assert np.array_equal(np.sort(ids), np.arange(n))
+            assert max(c for _, _, c in parts) - min(c for _, _, c in parts) <= 1
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))

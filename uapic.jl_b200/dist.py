@@ -1,4 +1,4 @@
-"""Multi-GPU plumbing: particles are sharded by contiguous index ranges, one process per GPU; the per-deposit
+"""Multi-GPU plumbing: particles are sharded by contiguous or interleaved index sets, one process per GPU; the per-deposit
 exchange is one all-reduce (sum) of the raw rho mesh over NCCL/NVLink (`gloo` on CPU for the host-logic tests).
 Everything after the sum (ghost fold, neutralisation, Poisson, energy) runs redundantly and identically on
 every rank, so no broadcast is needed.
@@ -13,6 +13,14 @@ def shard_range(nbpart_global: int, rank: int, world_size: int) -> tuple[int, in
     lo = nbpart_global * rank // world_size
     hi = nbpart_global * (rank + 1) // world_size
     return lo, hi
+
+
+def interleaved_shard(nbpart_global: int, rank: int, world_size: int) -> tuple[int, int, int]:
+    """(first, stride, count): `rank` owns the global particle indices first, first+stride, ... (count of them).
+    For loads whose particle properties depend on the index -- the Landau load assigns |v| by index, src/landau.jl:35 --
+    interleaving gives every rank the same mix; contiguous ranges (shard_range) give each rank a velocity band."""
+    count = (nbpart_global - rank + world_size - 1) // world_size if nbpart_global > rank else 0
+    return rank, world_size, count
 
 
 class _CudaView:
