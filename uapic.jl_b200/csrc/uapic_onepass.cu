@@ -25,7 +25,16 @@
 // one-sample-per-lane butterfly network of uapic_fused.cu; everything per particle (b, 1/b, sincos(t/eps)) is amortised
 // over 8 samples; exp(-i l t/eps) comes from a recurrence over the lane's 8 consecutive modes.
 // The M6 gathers run in the "lane = tau sample" layout (positions and fields are exchanged through shared memory), where
-// one load instruction touches the orbit of a single particle.
+// one load instruction touches the orbit of a single particle; E is read from a halo copy whose 128-byte lines hold 2 x 4
+// nodes (uapic_fast.cuh).  Phase B lives entirely in that layout.
+//
+// Execution shape (every choice below was measured, profiles/README.md): phase A runs ONE CTA of 12 warps per SM at 168
+// registers, split into four lock-step groups of 3 warps (named barriers between the stages of a tile): a group shares
+// the instruction fetches of this 6100-instruction straight-line kernel, the groups sit in different stages so that the
+// gather (LSU) and the FFT (fp64) phases overlap on the SM; the barriers also fence the scheduler, which keeps the live
+// ranges short (without them ptxas spills 1.3 KB per thread).  Phase B runs 2 CTAs x 8 free-running warps, a contiguous
+// range of tiles per CTA.  Both kernels are bound by the L1TEX LSU data pipe, not by HBM.
+// The UAPIC_OP_* macros keep the measured alternatives compilable; the defaults are the winners.
 #include "uapic_internal.h"
 #include "uapic_fast.cuh"
 
