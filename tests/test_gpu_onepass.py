@@ -337,3 +337,25 @@ def test_cic_needs_the_lean_one_pass_layout():
     for mode in (ub.STORE_FULL, ub.STORE_HYBRID, ub.STORE_ONEPASS):
         with pytest.raises(ub.UapicError, match="UAPIC_EUNSUPPORTED"):
             ub.Session(mesh, 16, 0.1, DT, 100, scheme=ub.SCHEME_CIC, storage_mode=mode)
+
+
+@pytest.mark.parametrize("mode,npart", [(ub.STORE_FULL, 70_000), (ub.STORE_ONEPASS_LEAN, 5_000), (ub.STORE_ONEPASS, 70_000)])
+def test_step_host_fallback_and_other_layouts(mode, npart):
+    """step_host on the two-barrier kernels and on problems too small to pipeline takes the plain upload -> step -> download
+    route; on the 72 B layout it pipelines: all must equal stepping on the device (bit for bit in fixed-point mode)"""
+    ntau, eps = 16, 0.1
+    _, x0, v0 = seeded_load(npart, seed=23)
+    mesh = ub.Mesh(0, DIMX, 128, 0, DIMY, 64)
+    w = DIMX * DIMY / npart
+    kw = dict(weight=w, storage_mode=mode, deposit_mode=ub.DEPOSIT_FIXED_POINT)
+    with ub.Session(mesh, ntau, eps, DT, npart, **kw) as s:
+        s.upload_particles(x0, v0); s.init_fields(); s.step(2); s.synchronize()
+        xa, va = s.download_particles(); na = s.energy_history()
+    with ub.Session(mesh, ntau, eps, DT, npart, **kw) as s:
+        s.upload_particles(x0, v0); s.init_fields(); s.synchronize()
+        x, v = x0.copy(order="F"), v0.copy(order="F")
+        e = s.download_particle_e()
+        s.step_host(x, v, e, x, v)
+        s.step_host(x, v, None, x, v)
+        nb = s.energy_history()
+    assert np.array_equal(x, xa) and np.array_equal(v, va) and np.array_equal(na, nb)
