@@ -26,6 +26,9 @@ DEVINL Cell cell_fast(const MeshDev &m, const MeshFast &f, double x, double y, i
     Cell c;
     c.i = __double2int_rd(px); c.dpx = px - (double)c.i;
     c.j = __double2int_rd(py); c.dpy = py - (double)c.j;
+    // memory safety only: a non-finite position (NaN input, b -> 0) must not turn into an out-of-range mesh address
+    c.i = min(max(c.i, 0), m.nx - 1);
+    c.j = min(max(c.j, 0), m.ny - 1);
     return c;
 }
 
