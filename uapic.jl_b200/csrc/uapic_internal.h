@@ -43,6 +43,8 @@ cudaError_t launch_gather(const LaunchCtx &c, const MeshDev &m, const double *em
 
 // ---- mesh kernels ---------------------------------------------------------------------------------------------
 // raw accumulation (fp64 or fixed point) -> neutralised rho with ghosts; rho_total (1 double) may be null
+// raw[i] += sum_{c >= 1} raw[c*n + i] for i < n (fold the CTA-private copies of the one-pass deposits; exact for int64)
+cudaError_t launch_fold_raw(const LaunchCtx &c, const RhoAcc &acc, int64_t n, int copies);
 cudaError_t launch_rho_epilogue(const LaunchCtx &c, const MeshDev &m, const RhoAcc &acc, double *rho, double *rho_total);
 struct PoissonWork { double2 *rk; double2 *ek; };   // rk: (nx/2+1)*ny ; ek: 2*(nx/2+1)*ny
 cudaError_t launch_poisson(const LaunchCtx &c, const MeshDev &m, const PoissonWork &w, const double *rho, double *emesh,
@@ -92,6 +94,7 @@ struct OnepassParams {
     char *store;           // np * onepass_store_bytes_per_particle(ntau, full)
     double *rec;           // np * 8 doubles: t, b, 1/b, bracket sums (2), cos(t/eps), sin(t/eps), unused
     RhoAcc rho_p, rho_c;   // raw accumulation meshes of the predictor and the corrector deposit (A only)
+    int rho_copies;        // >= 1: CTA b deposits into copy b % rho_copies (copy c of both meshes starts 2*c*nrho elements on)
 };
 bool onepass_ntau_supported(int ntau);
 size_t onepass_store_bytes_per_particle(int ntau, int full);

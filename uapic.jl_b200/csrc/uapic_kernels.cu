@@ -710,6 +710,29 @@ cudaError_t launch_gather(const LaunchCtx &c, const MeshDev &m, const double *em
     return cudaGetLastError();
 }
 
+namespace {
+__global__ void __launch_bounds__(kBlock) k_fold_raw(RhoAcc acc, int64_t n, int copies) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        if (acc.i64) {
+            unsigned long long t = acc.i64[i];
+            for (int c = 1; c < copies; ++c) t += acc.i64[(size_t)c * n + i];       // fixed order; integer sum is exact anyway
+            acc.i64[i] = t;
+        } else {
+            double t = acc.f64[i];
+            for (int c = 1; c < copies; ++c) t += acc.f64[(size_t)c * n + i];
+            acc.f64[i] = t;
+        }
+    }
+}
+}  // namespace
+
+cudaError_t launch_fold_raw(const LaunchCtx &c, const RhoAcc &acc, int64_t n, int copies) {
+    if (copies <= 1 || n <= 0) return cudaSuccess;
+    k_fold_raw<<<grid_for(c, n, kBlock), kBlock, 0, c.stream>>>(acc, n, copies);
+    count(c);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_rho_epilogue(const LaunchCtx &c, const MeshDev &m, const RhoAcc &acc, double *rho, double *rho_total) {
     k_rho_epilogue<<<1, kMeshBlock, 0, c.stream>>>(m, acc, rho, rho_total);
     count(c);

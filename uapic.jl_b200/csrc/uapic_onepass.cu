@@ -646,16 +646,15 @@ __global__ void __launch_bounds__(kOpBlockA, UAPIC_OP_MINB_A) k_onepass_a(OpDev 
         const bool valid_dep = valid && P.np < 0;
 #define valid valid_dep
 #endif
-#ifdef UAPIC_OP_EXPERIMENT_PRIVATE_RHO   // timing experiment only (results are wrong): CTA-private copies of the raw meshes
+        // the CTAs of a sweep all work in the same sorted bin, i.e. on the same few hundred mesh nodes: spread their atomics
+        // over P.rho_copies private copies of the two raw meshes (folded before the field solve)
         RhoAcc rp = P.rho_p, rc = P.rho_c;
-        { const size_t off = (size_t)(blockIdx.x % UAPIC_OP_EXPERIMENT_PRIVATE_RHO) * 2 * (size_t)P.m.ld * (P.m.ny + 1);
-          if (rp.f64) { rp.f64 += off; rc.f64 += off; } else { rp.i64 += off; rc.i64 += off; } }
+        {
+            const size_t off = (size_t)(blockIdx.x % P.rho_copies) * 2 * (size_t)P.m.ld * (P.m.ny + 1);
+            if (rp.f64) { rp.f64 += off; rc.f64 += off; } else { rp.i64 += off; rc.i64 += off; }
+        }
 #define rho_p_sel rp
 #define rho_c_sel rc
-#else
-#define rho_p_sel P.rho_p
-#define rho_c_sel P.rho_c
-#endif
         const Cell cp = cell_fast(P.m, D.f, posp1, posp2, P.wrap, xw, yw);
         if (SCHEME == kSchemeCic) {
             if (valid) {
