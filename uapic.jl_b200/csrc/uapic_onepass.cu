@@ -51,18 +51,11 @@ namespace {
 #ifndef UAPIC_OP_LOCKSTEP
 #define UAPIC_OP_LOCKSTEP 1
 #endif
-#ifndef UAPIC_OP_LOCKMOD
-#define UAPIC_OP_LOCKMOD 0
-#endif
 #ifndef UAPIC_OP_LOCKGROUP
 #define UAPIC_OP_LOCKGROUP 3      // warps per lock-step group inside a CTA of phase A; 0 = the whole CTA
 #endif
 #if UAPIC_OP_LOCKSTEP && UAPIC_OP_LOCKGROUP
-#if UAPIC_OP_LOCKMOD   // group = warp % (warps / LOCKGROUP): the warps of a group sit on the same SM sub-partition
-#define OP_STEP() asm volatile("bar.sync %0, %1;" ::"r"(1 + (int)(threadIdx.x >> 5) % (UAPIC_OP_BLOCK_A / 32 / UAPIC_OP_LOCKGROUP)), "r"(32 * UAPIC_OP_LOCKGROUP) : "memory")
-#else
 #define OP_STEP() asm volatile("bar.sync %0, %1;" ::"r"(1 + (int)(threadIdx.x >> 5) / UAPIC_OP_LOCKGROUP), "r"(32 * UAPIC_OP_LOCKGROUP) : "memory")
-#endif
 #elif UAPIC_OP_LOCKSTEP
 #define OP_STEP() __syncthreads()
 #else
@@ -71,24 +64,8 @@ namespace {
 #ifndef UAPIC_OP_PREFETCH
 #define UAPIC_OP_PREFETCH 1
 #endif
-// sync points of phase A: OP_STEP_SM also orders shared-memory accesses inside the warp (must at least be a __syncwarp);
-// OP_STEP_OPT only keeps the lock-step group together
-#ifndef UAPIC_OP_SYNC_VARIANT
-#define UAPIC_OP_SYNC_VARIANT 0
-#endif
-#if UAPIC_OP_SYNC_VARIANT == 0
-#define OP_STEP_OPT() OP_STEP()
-#define OP_STEP_SM() OP_STEP()
-#elif UAPIC_OP_SYNC_VARIANT == 1
-#define OP_STEP_OPT() ((void)0)
-#define OP_STEP_SM() OP_STEP()
-#elif UAPIC_OP_SYNC_VARIANT == 2
-#define OP_STEP_OPT() OP_STEP()
-#define OP_STEP_SM() __syncwarp()
-#else
-#define OP_STEP_OPT() ((void)0)
-#define OP_STEP_SM() __syncwarp()
-#endif
+// sync points of phase A.  Besides keeping a lock-step group together they fence ptxas' scheduler: without the three that
+// no shared-memory hand-over needs, live ranges grow and the kernel spills 1.3 KB per thread (measured, +17 % time).
 #ifndef UAPIC_OP_GATHER_UNROLL
 #define UAPIC_OP_GATHER_UNROLL 1
 #endif
@@ -112,24 +89,9 @@ constexpr int kGatherUnroll = UAPIC_OP_GATHER_UNROLL;
 #ifndef UAPIC_OP_PREFETCH_B
 #define UAPIC_OP_PREFETCH_B 2
 #endif
-// sync points of phase A: OP_STEP_SM also orders shared-memory accesses inside the warp (must at least be a __syncwarp);
-// OP_STEP_OPT only keeps the lock-step group together
-#ifndef UAPIC_OP_SYNC_VARIANT
-#define UAPIC_OP_SYNC_VARIANT 0
-#endif
-#if UAPIC_OP_SYNC_VARIANT == 0
-#define OP_STEP_OPT() OP_STEP()
-#define OP_STEP_SM() OP_STEP()
-#elif UAPIC_OP_SYNC_VARIANT == 1
-#define OP_STEP_OPT() ((void)0)
-#define OP_STEP_SM() OP_STEP()
-#elif UAPIC_OP_SYNC_VARIANT == 2
-#define OP_STEP_OPT() OP_STEP()
-#define OP_STEP_SM() __syncwarp()
-#else
-#define OP_STEP_OPT() ((void)0)
-#define OP_STEP_SM() __syncwarp()
-#endif
+// The sync points of phase A (OP_STEP) do two jobs: they keep a lock-step group together, and they fence ptxas' scheduler --
+// without the three that no shared-memory hand-over needs, live ranges grow and the kernel spills 1.3 KB per thread
+// (measured: +17 % time).
 #ifndef UAPIC_OP_GATHER_UNROLL_B
 #define UAPIC_OP_GATHER_UNROLL_B 2
 #endif
@@ -442,7 +404,7 @@ __global__ void __launch_bounds__(kOpBlockA, UAPIC_OP_MINB_A) k_onepass_a(OpDev 
             const double xt2 = x2 + eps * (c.y * vyb + c.x * vxb) - eps * vxb;   // :79-82
             gx[s * kRow + lane] = make_double2(xt1, xt2);
         }
-        OP_STEP_SM();
+        OP_STEP();
         // ---- gather E_n at the samples, lane = sample (interpolation_m6.F90:83-189); the sines of :87 ride along so that
         //      the 16 sin() of a lane sit in this rolled loop instead of the unrolled code below ----
 #pragma unroll (kGatherUnroll)
@@ -493,7 +455,7 @@ __global__ void __launch_bounds__(kOpBlockA, UAPIC_OP_MINB_A) k_onepass_a(OpDev 
                 yhs[(8 + k1) * 32 + lane] = make_double2(y2.re, y2.im);
             }
         }
-        OP_STEP_SM();
+        OP_STEP();
 
         // ---- exp(-i l t/eps), pl, ql/t, w = ql/t * conj(elt) for the lane's modes ----
         cd e1;
@@ -552,7 +514,7 @@ __global__ void __launch_bounds__(kOpBlockA, UAPIC_OP_MINB_A) k_onepass_a(OpDev 
         }
 
         // ---- y: yt = B(yhat) (:105-110), fy in the time domain (:177-183), FFT, ua_step1 (:226), bracket sums ----
-        OP_STEP_OPT();
+        OP_STEP();
         // yhat1, yhat2 are spectra of real signals (:92-106) except for two coefficients: the Nyquist mode, which the filter
         // -i/l turns purely imaginary, and the mean, which carries minus its value (:109-110).  So ONE backward transform of
         // H = H1 + i H2 (H: Hermitian parts) gives Re yt1 + i Re yt2, and Im yt_n = Im yhat_0 + (-1)^n Im yhat_{N/2}.
@@ -583,7 +545,7 @@ __global__ void __launch_bounds__(kOpBlockA, UAPIC_OP_MINB_A) k_onepass_a(OpDev 
             const double iv = (1.0 + 0.5 * sps[s * kRow + lane] - b) * inv_eps;       // :177, same as :87
             fy_time(c.x, c.y, rb, iv, y1[s], y2[s], et.x, et.y, y1[s], y2[s]);
         }
-        OP_STEP_OPT();
+        OP_STEP();
         fwdN<G>(y1, L);                                                      // :189-190
         fwdN<G>(y2, L);
         double qa1 = 0.0, qa2 = 0.0;
@@ -616,7 +578,7 @@ __global__ void __launch_bounds__(kOpBlockA, UAPIC_OP_MINB_A) k_onepass_a(OpDev 
                 swg2 += re_mul(wv[k1], gx2);
             }
         }
-        OP_STEP_OPT();
+        OP_STEP();
         bwdN<G>(y1, L);                                                      // :232
         bwdN<G>(y2, L);
         if (valid) {
@@ -642,10 +604,6 @@ __global__ void __launch_bounds__(kOpBlockA, UAPIC_OP_MINB_A) k_onepass_a(OpDev 
         const double posc1 = posp1 + grp_sum<G>(swg1 - swf1), posc2 = posp2 + grp_sum<G>(swg2 - swf2);
         qa1 = grp_sum<G>(qa1); qa2 = grp_sum<G>(qa2);
         double xw, yw;
-#ifdef UAPIC_OP_EXPERIMENT_NO_DEPOSIT      // timing experiment only: what the two deposits cost
-        const bool valid_dep = valid && P.np < 0;
-#define valid valid_dep
-#endif
         // the CTAs of a sweep all work in the same sorted bin, i.e. on the same few hundred mesh nodes: spread their atomics
         // over P.rho_copies private copies of the two raw meshes (folded before the field solve)
         RhoAcc rp = P.rho_p, rc = P.rho_c;
@@ -673,9 +631,6 @@ __global__ void __launch_bounds__(kOpBlockA, UAPIC_OP_MINB_A) k_onepass_a(OpDev 
         } else {
             deposit_split<G>(P.m, rho_c_sel, cc, P.weight, g, valid);          // (corrector)
         }
-#ifdef UAPIC_OP_EXPERIMENT_NO_DEPOSIT
-#undef valid
-#endif
         if (valid && g == 0) {
             P.x[ip] = make_double2(xw, yw);                                  // compute_rho_m6.F90:86-87
             double2 *rec = reinterpret_cast<double2 *>(P.rec + 8 * ip);
