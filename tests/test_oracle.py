@@ -204,3 +204,19 @@ def test_cic_variant_c_vs_numpy_and_properties():
     xo, vo = x0.copy(order="F"), v0.copy(order="F")
     en6, _, _, _ = c.run_bupdate(om, 16, 0.1, dt, 4, xo, vo, w)
     assert np.abs(en6 - en).max() > 1e-6 * np.abs(en6).max()      # M6 and CIC are different schemes
+
+
+def test_gnuplot_dump_layout(tmp_path):
+    """src/gnuplot.jl:4-27: (nx+1)(ny+1) records `x  y  e1  e2  rho`, x outer, y inner, a blank line after every x column"""
+    import uapic_b200 as ub
+    m = ub.Mesh(0, 4 * np.pi, 4, 0, 2 * np.pi, 2)
+    f = ub.MeshFields(m)
+    f.e[0], f.e[1] = 1.5, -2.0
+    f.rho[:] = np.arange(15).reshape(5, 3)
+    p = tmp_path / "fields.dat"
+    ub.gnuplot(str(p), f)
+    lines = p.read_text().split("\n")
+    assert len(lines) == 5 * 3 + 5 + 1 and lines[3] == "" and lines[-1] == ""
+    rec = [float(t) for t in lines[4].split()]            # i = 1, j = 0
+    assert rec == [m.dx, 0.0, 1.5, -2.0, 3.0]
+    assert lines[0].count("  ") == 4

@@ -245,3 +245,14 @@ def integrate(field: np.ndarray, mesh: Mesh) -> float:
 def errors(computed: MeshFields, reference: MeshFields) -> float:
     """src/gnuplot.jl:29-35"""
     return float(np.max(np.abs(computed.e - reference.e)))
+
+
+def gnuplot(filename: str, fields: MeshFields) -> None:
+    """src/gnuplot.jl:4-27: one line `x  y  e1  e2  rho` per node, x outer / y inner, a blank line after every x column
+    (host-side diagnostic dump, same record order and separators as the reference; numbers in Python's shortest repr)"""
+    m = fields.mesh
+    with open(filename, "w") as f:
+        for i in range(m.nx + 1):
+            for j in range(m.ny + 1):
+                f.write(f"{i * m.dx!r}  {j * m.dy!r}  {float(fields.e[0, i, j])!r}  {float(fields.e[1, i, j])!r}  {float(fields.rho[i, j])!r}\n")
+            f.write("\n")
