@@ -374,12 +374,19 @@ __global__ void __launch_bounds__(kOpBlockA, UAPIC_OP_MINB_A) k_onepass_a(OpDev 
     // the trip count is uniform over the CTA (a warp past the end works on a clamped copy of the last particle with its
     // stores and deposits switched off) so that the warps of a CTA can be kept in step: they then share instruction
     // fetches of this long straight-line kernel (UAPIC_OP_LOCKSTEP)
+    // the particle data of a tile are loaded while the previous tile is finishing (its deposits hide the latency)
+    double2 xx_n, vv_n, ee_n;
+    {
+        const int64_t k0 = (t_first + wib) * PW + pin;
+        const int64_t i0 = (t_first + wib < t_end && k0 < P.np) ? k0 : P.np - 1;
+        xx_n = P.x[i0]; vv_n = P.v[i0]; ee_n = P.ep[i0];
+    }
     for (int64_t tbase = t_first; tbase < t_end; tbase += nwarps) {
         const int64_t tile = tbase + wib;
         const int64_t kraw = tile * PW + pin;
         const bool valid = tile < t_end && kraw < P.np;
         const int64_t ip = valid ? kraw : P.np - 1;
-        const double2 xx = P.x[ip], vv = P.v[ip], ee = P.ep[ip];
+        const double2 xx = xx_n, vv = vv_n, ee = ee_n;
         const double x1 = xx.x, x2 = xx.y, vx = vv.x, vy = vv.y;
 #if UAPIC_OP_PREFETCH
         {   // the CTA's next tiles: their particle data would otherwise be a cold HBM access all warps of the CTA wait on together
@@ -599,6 +606,11 @@ __global__ void __launch_bounds__(kOpBlockA, UAPIC_OP_MINB_A) k_onepass_a(OpDev 
             }
         }
 
+        {   // next tile of this warp (clamped like the current one)
+            const int64_t kn = kraw + nwarps * PW;
+            const int64_t in = (tile + nwarps < t_end && kn < P.np) ? kn : P.np - 1;
+            xx_n = P.x[in]; vv_n = P.v[in]; ee_n = P.ep[in];
+        }
         // ---- both deposit positions, deposits, per-particle record ----
         posp1 = grp_sum<G>(posp1); posp2 = grp_sum<G>(posp2);
         const double posc1 = posp1 + grp_sum<G>(swg1 - swf1), posc2 = posp2 + grp_sum<G>(swg2 - swf2);
