@@ -215,7 +215,8 @@ def main():
     if storage == "auto":
         storage = "hybrid"
         for cand in ("onepass-lean",):          # measured: the lean layout is also the faster one (W_n and interv are cheaper to redo)
-            if ntau in (8, 16, 32) and (hi - lo) * (ntau * PER_TAU[cand] + 128) + (3 << 29) < free_b:
+            # store + particle arrays and records (128 B) + reordering buffers (58 B) per particle, + 1.5 GiB of slack
+            if ntau in (8, 16, 32) and (hi - lo) * (ntau * PER_TAU[cand] + 128 + 58) + (3 << 29) < free_b:
                 storage = cand
                 break
     s = ub.Session(mesh, ntau, EPS, DT, hi - lo, nbpart_global=np_global, device=local, stream=stream,
