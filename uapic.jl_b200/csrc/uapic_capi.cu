@@ -417,6 +417,9 @@ int uapic_compute_v(int ntau, double eps, int64_t nbpart, const double *t, const
 // session
 // ================================================================================================
 
+#ifndef UAPIC_HOST_CHUNKS
+#define UAPIC_HOST_CHUNKS 32     // particle chunks of uapic_session_step_host (copies of a chunk overlap the kernels of its neighbours)
+#endif
 #ifndef UAPIC_RAW_COPIES
 #define UAPIC_RAW_COPIES 8      // CTA-private copies of the two raw deposit meshes of the one-pass kernels (measured: -2 % on phase A)
 #endif
@@ -830,7 +833,7 @@ int uapic_session_step_host(uapic_session_t *s, const double *x_in, const double
         TRY(uapic_session_step(s, 1));
         return uapic_session_download_particles(s, x_out, v_out);
     }
-    constexpr int kChunks = 16;
+    constexpr int kChunks = UAPIC_HOST_CHUNKS;
     if (!s->up_stream) {
         CU(cudaStreamCreateWithFlags(&s->up_stream, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithFlags(&s->down_stream, cudaStreamNonBlocking));
