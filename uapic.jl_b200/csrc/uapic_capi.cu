@@ -519,6 +519,7 @@ OnepassParams session_onepass_params(uapic_session *s) {
     p.ehalo = s->ehalo.as<double2>();
     p.store = s->store.as<char>(); p.rec = s->rec.as<double>();
     p.rho_p = s->acc; p.rho_c = s->acc_c; p.rho_copies = UAPIC_RAW_COPIES;
+    p.out_perm = nullptr; p.x_out = nullptr; p.v_out = nullptr;
     return p;
 }
 
@@ -877,6 +878,8 @@ int uapic_session_step_host(uapic_session_t *s, const double *x_in, const double
                                      s->ep2.as<double2>() + lo, s->perm2.as<uint32_t>() + lo, s->binid.as<uint16_t>() + lo,
                                      s->hist.as<unsigned>(), (uint32_t)lo));
             pc.x = s->x2.as<double2>() + lo; pc.v = s->v2.as<double2>() + lo; pc.ep = s->ep2.as<double2>() + lo;
+            // the new x goes straight back to the caller's order (perm2 holds global indices, all inside this chunk)
+            pc.out_perm = s->perm2.as<uint32_t>() + lo; pc.x_out = s->x.as<double2>(); pc.v_out = s->v.as<double2>();
         } else {
             pc.x = s->x.as<double2>() + lo; pc.v = s->v.as<double2>() + lo; pc.ep = s->ep.as<double2>() + lo;
         }
@@ -900,11 +903,8 @@ int uapic_session_step_host(uapic_session_t *s, const double *x_in, const double
         pc.store = op.store + (size_t)lo * stride;
         pc.rec = op.rec + 8 * lo;
         pc.ehalo = s->ehalo_p.as<double2>();
+        if (sort) { pc.out_perm = s->perm2.as<uint32_t>() + lo; pc.x_out = s->x.as<double2>(); pc.v_out = s->v.as<double2>(); }
         CU(launch_onepass_b(s->lc, pc));
-        if (sort) {   // perm2 holds global indices, all inside this chunk: x[perm2[i]] = x2[i]
-            CU(launch_unpermute(s->lc, n, s->perm2.as<uint32_t>() + lo, s->x2.as<double2>() + lo, s->x.as<double2>()));
-            CU(launch_unpermute(s->lc, n, s->perm2.as<uint32_t>() + lo, s->v2.as<double2>() + lo, s->v.as<double2>()));
-        }
         CU(cudaEventRecord(s->chunk_ev[kChunks + c], cs));
         CU(cudaStreamWaitEvent(s->down_stream, s->chunk_ev[kChunks + c], 0));
         CU(cudaMemcpyAsync(x_out + 2 * lo, s->x.as<double2>() + lo, 16 * (size_t)n, cudaMemcpyDeviceToHost, s->down_stream));

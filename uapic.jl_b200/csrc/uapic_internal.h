@@ -94,6 +94,8 @@ struct OnepassParams {
     char *store;           // np * onepass_store_bytes_per_particle(ntau, full)
     double *rec;           // np * 8 doubles: t, b, 1/b, bracket sums (2), cos(t/eps), sin(t/eps), unused
     RhoAcc rho_p, rho_c;   // raw accumulation meshes of the predictor and the corrector deposit (A only)
+    const uint32_t *out_perm;   // null, or slot -> caller's particle index: A writes the new x, B the new v, straight to
+    double2 *x_out, *v_out;     //   x_out[out_perm[slot]] / v_out[out_perm[slot]] (host-resident stepping) instead of x / v in place
     int rho_copies;        // >= 1: CTA b deposits into copy b % rho_copies (copy c of both meshes starts 2*c*nrho elements on)
 };
 bool onepass_ntau_supported(int ntau);

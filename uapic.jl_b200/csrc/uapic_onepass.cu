@@ -644,7 +644,8 @@ __global__ void __launch_bounds__(kOpBlockA, UAPIC_OP_MINB_A) k_onepass_a(OpDev 
             deposit_split<G>(P.m, rho_c_sel, cc, P.weight, g, valid);          // (corrector)
         }
         if (valid && g == 0) {
-            P.x[ip] = make_double2(xw, yw);                                  // compute_rho_m6.F90:86-87
+            if (P.out_perm) P.x_out[P.out_perm[ip]] = make_double2(xw, yw);
+            else P.x[ip] = make_double2(xw, yw);                             // compute_rho_m6.F90:86-87
             double2 *rec = reinterpret_cast<double2 *>(P.rec + 8 * ip);
             rec[0] = make_double2(b, rb);                                    // what every sample lane of phase B needs
             rec[1] = make_double2(t, qa1);
@@ -764,7 +765,8 @@ __global__ void __launch_bounds__(kOpBlockB, UAPIC_OP_MINB_B) k_onepass_b(OpDev 
                 const double2 *rec = reinterpret_cast<const double2 *>(P.rec + 8 * kraw);
                 const double2 r1 = rec[1], r2 = rec[2], r3 = rec[3];
                 const double px = r1.y + sx, py = r2.x + sy, cs = r2.y, sn = r3.x;
-                P.v[kraw] = make_double2(cs * px + sn * py, cs * py - sn * px);                    // :302-303
+                const double2 vn = make_double2(cs * px + sn * py, cs * py - sn * px);             // :302-303
+                if (P.out_perm) P.v_out[P.out_perm[kraw]] = vn; else P.v[kraw] = vn;
             }
         }
         __syncwarp();
