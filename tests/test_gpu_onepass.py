@@ -359,3 +359,17 @@ def test_step_host_fallback_and_other_layouts(mode, npart):
         s.step_host(x, v, None, x, v)
         nb = s.energy_history()
     assert np.array_equal(x, xa) and np.array_equal(v, va) and np.array_equal(na, nb)
+
+
+def test_reordering_also_works_with_the_two_barrier_kernels():
+    """set_sort is a session feature, not a one-pass feature: the two-barrier kernels must give bit-identical fixed-point
+    results with the particle arrays reordered every step"""
+    npart, ntau, eps, nstep = 9000, 16, 0.1, 3
+    _, x0, v0 = seeded_load(npart, seed=77)
+    mesh = ub.Mesh(0, DIMX, 128, 0, DIMY, 64)
+    w = DIMX * DIMY / npart
+    for mode in (ub.STORE_FULL, ub.STORE_HYBRID):
+        a = _run(mesh, ntau, eps, nstep, x0, v0, w, mode, deposit_mode=ub.DEPOSIT_FIXED_POINT)
+        b = _run(mesh, ntau, eps, nstep, x0, v0, w, mode, deposit_mode=ub.DEPOSIT_FIXED_POINT, sort=(1, 3))
+        for p, q in zip(a[:5], b[:5]):
+            assert np.array_equal(p, q)
