@@ -89,6 +89,12 @@ constexpr int kGatherUnroll = UAPIC_OP_GATHER_UNROLL;
 #ifndef UAPIC_OP_PREFETCH_B
 #define UAPIC_OP_PREFETCH_B 2
 #endif
+// OP_SYNC(i): sync point i of a tile (0..6).  Bit i of UAPIC_OP_BARRIER_MASK set = lock-step barrier of the group; clear = just
+// __syncwarp(), which still orders the warp's shared-memory accesses and still fences ptxas' scheduler
+#ifndef UAPIC_OP_BARRIER_MASK
+#define UAPIC_OP_BARRIER_MASK 0x47
+#endif
+#define OP_SYNC(i) do { if ((UAPIC_OP_BARRIER_MASK >> (i)) & 1) { OP_STEP(); } else { __syncwarp(); } } while (0)
 // The sync points of phase A (OP_STEP) do two jobs: they keep a lock-step group together, and they fence ptxas' scheduler --
 // without the three that no shared-memory hand-over needs, live ranges grow and the kernel spills 1.3 KB per thread
 // (measured: +17 % time).
@@ -411,7 +417,7 @@ __global__ void __launch_bounds__(kOpBlockA, UAPIC_OP_MINB_A) k_onepass_a(OpDev 
             const double xt2 = x2 + eps * (c.y * vyb + c.x * vxb) - eps * vxb;   // :79-82
             gx[s * kRow + lane] = make_double2(xt1, xt2);
         }
-        OP_STEP();
+        OP_SYNC(0);
         // ---- gather E_n at the samples, lane = sample (interpolation_m6.F90:83-189); the sines of :87 ride along so that
         //      the 16 sin() of a lane sit in this rolled loop instead of the unrolled code below ----
 #pragma unroll (kGatherUnroll)
@@ -425,7 +431,7 @@ __global__ void __launch_bounds__(kOpBlockA, UAPIC_OP_MINB_A) k_onepass_a(OpDev 
             gx[row * kRow + col] = make_double2(e1, e2);
             sps[row * kRow + col] = sin(pos.x) * sin(pos.y);
         }
-        OP_STEP();
+        OP_SYNC(1);
 
         cd z[8];
 #pragma unroll
@@ -462,7 +468,7 @@ __global__ void __launch_bounds__(kOpBlockA, UAPIC_OP_MINB_A) k_onepass_a(OpDev 
                 yhs[(8 + k1) * 32 + lane] = make_double2(y2.re, y2.im);
             }
         }
-        OP_STEP();
+        OP_SYNC(2);
 
         // ---- exp(-i l t/eps), pl, ql/t, w = ql/t * conj(elt) for the lane's modes ----
         cd e1;
@@ -521,7 +527,7 @@ __global__ void __launch_bounds__(kOpBlockA, UAPIC_OP_MINB_A) k_onepass_a(OpDev 
         }
 
         // ---- y: yt = B(yhat) (:105-110), fy in the time domain (:177-183), FFT, ua_step1 (:226), bracket sums ----
-        OP_STEP();
+        OP_SYNC(3);
         // yhat1, yhat2 are spectra of real signals (:92-106) except for two coefficients: the Nyquist mode, which the filter
         // -i/l turns purely imaginary, and the mean, which carries minus its value (:109-110).  So ONE backward transform of
         // H = H1 + i H2 (H: Hermitian parts) gives Re yt1 + i Re yt2, and Im yt_n = Im yhat_0 + (-1)^n Im yhat_{N/2}.
@@ -552,7 +558,7 @@ __global__ void __launch_bounds__(kOpBlockA, UAPIC_OP_MINB_A) k_onepass_a(OpDev 
             const double iv = (1.0 + 0.5 * sps[s * kRow + lane] - b) * inv_eps;       // :177, same as :87
             fy_time(c.x, c.y, rb, iv, y1[s], y2[s], et.x, et.y, y1[s], y2[s]);
         }
-        OP_STEP();
+        OP_SYNC(4);
         fwdN<G>(y1, L);                                                      // :189-190
         fwdN<G>(y2, L);
         double qa1 = 0.0, qa2 = 0.0;
@@ -585,7 +591,7 @@ __global__ void __launch_bounds__(kOpBlockA, UAPIC_OP_MINB_A) k_onepass_a(OpDev 
                 swg2 += re_mul(wv[k1], gx2);
             }
         }
-        OP_STEP();
+        OP_SYNC(5);
         bwdN<G>(y1, L);                                                      // :232
         bwdN<G>(y2, L);
         if (valid) {
@@ -652,7 +658,7 @@ __global__ void __launch_bounds__(kOpBlockA, UAPIC_OP_MINB_A) k_onepass_a(OpDev 
             rec[2] = make_double2(qa2, e1.re);                               // cos(t/eps)
             rec[3] = make_double2(-e1.im, 0.0);                              // sin(t/eps)
         }
-        OP_STEP();
+        OP_SYNC(6);
     }
 }
 
