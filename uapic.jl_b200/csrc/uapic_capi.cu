@@ -834,11 +834,13 @@ int uapic_session_step_host(uapic_session_t *s, const double *x_in, const double
         TRY(uapic_session_step(s, 1));
         return uapic_session_download_particles(s, x_out, v_out);
     }
-    constexpr int kChunks = UAPIC_HOST_CHUNKS;
+    constexpr int kMaxChunks = UAPIC_HOST_CHUNKS;
+    // chunks of at least 2^20 particles: smaller ones cost more in launch tails than their overlap hides
+    const int kChunks = (int)std::min<int64_t>(kMaxChunks, std::max<int64_t>(2, np >> 20));
     if (!s->up_stream) {
         CU(cudaStreamCreateWithFlags(&s->up_stream, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithFlags(&s->down_stream, cudaStreamNonBlocking));
-        for (int q = 0; q < 2 * kChunks + 2; ++q) {
+        for (int q = 0; q < 2 * kMaxChunks + 2; ++q) {
             cudaEvent_t e;
             CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
             s->chunk_ev.push_back(e);
@@ -852,7 +854,7 @@ int uapic_session_step_host(uapic_session_t *s, const double *x_in, const double
     s->permuted = false;
     TRY(session_alloc_sort_buffers(s));
     cudaStream_t cs = s->lc.stream;
-    cudaEvent_t ev_start = s->chunk_ev[2 * kChunks], ev_done = s->chunk_ev[2 * kChunks + 1];
+    cudaEvent_t ev_start = s->chunk_ev[2 * kMaxChunks], ev_done = s->chunk_ev[2 * kMaxChunks + 1];
     CU(cudaEventRecord(ev_start, cs));                       // earlier work on the session stream (previous step) is finished
     CU(cudaStreamWaitEvent(s->up_stream, ev_start, 0));
     CU(cudaStreamWaitEvent(s->down_stream, ev_start, 0));
@@ -905,8 +907,8 @@ int uapic_session_step_host(uapic_session_t *s, const double *x_in, const double
         pc.ehalo = s->ehalo_p.as<double2>();
         if (sort) { pc.out_perm = s->perm2.as<uint32_t>() + lo; pc.x_out = s->x.as<double2>(); pc.v_out = s->v.as<double2>(); }
         CU(launch_onepass_b(s->lc, pc));
-        CU(cudaEventRecord(s->chunk_ev[kChunks + c], cs));
-        CU(cudaStreamWaitEvent(s->down_stream, s->chunk_ev[kChunks + c], 0));
+        CU(cudaEventRecord(s->chunk_ev[kMaxChunks + c], cs));
+        CU(cudaStreamWaitEvent(s->down_stream, s->chunk_ev[kMaxChunks + c], 0));
         CU(cudaMemcpyAsync(x_out + 2 * lo, s->x.as<double2>() + lo, 16 * (size_t)n, cudaMemcpyDeviceToHost, s->down_stream));
         CU(cudaMemcpyAsync(v_out + 2 * lo, s->v.as<double2>() + lo, 16 * (size_t)n, cudaMemcpyDeviceToHost, s->down_stream));
     }
