@@ -41,9 +41,14 @@ WORKLOADS = {
     "config3-shard": ("landau", 32, 128, 128, 12_500_000, "per_gpu",
                       "per-GPU shard of BASELINE config 3 (12.5e6 particles/GPU = 1e8 at 8 GPUs), weak scaling"),
     "config2": ("plasma", 16, 128, 64, 1_000_000, "total", "BASELINE config 2: bupdate case, M6, 1e6 particles, ntau=16, 128x64"),
+    "config4": ("plasma", 16, 128, 64, 10_000_000, "total",
+                "BASELINE config 4: eps sweep case, bupdate densities, 1e7 particles, ntau=16, 128x64, M6 (pass --eps)"),
     "config5": ("landau", 32, 256, 256, 15_625_000, "per_gpu",
                 "BASELINE config 5 weak point: 5e8 particle-tau samples/GPU, ntau=32, 256x256, M6"),
+    "config5-strong": ("landau", 32, 256, 256, 31_250_000, "total",
+                       "BASELINE config 5 strong: 1e9 particle-tau samples in total, ntau=32, 256x256, M6"),
 }
+SEED = 20190101
 
 
 def peaks():
@@ -104,26 +109,19 @@ class ClockSampler:
         return out
 
 
-def cpu_oracle_rate(workload, steps, warmup, sample_particles, threads=None, faithful=True):
-    """particle-tau updates/s of the CPU oracle (port of the Fortran reference) on a bounded sample of the workload"""
+def cpu_oracle_rate(workload, steps, warmup, sample_particles, np_global, eps, threads=None, faithful=True):
+    """particle-tau updates/s of the CPU oracle (port of the Fortran reference) on a bounded sample of the workload: the
+    SAME particles the device generator makes (oracle.generate = k_generate, same seed), every (np_global/sample)-th one,
+    so the sample spans the |v| strata of the Landau load like the full problem does"""
     import oracle
     load, ntau, nx, ny = WORKLOADS[workload][:4]
     orc = oracle.corc()
     nthreads = threads or orc.max_threads()
     orc.set_threads(nthreads)
     om = oracle.mesh(0, DIMX, nx, 0, DIMY, ny)
-    rng = np.random.default_rng(12345)
-    n = sample_particles
-    if load == "landau":
-        x = np.zeros((2, n), order="F"); v = np.zeros((2, n), order="F")
-        r = rng.random((n, 3))
-        x[0] = r[:, 1] * DIMX + 0.05 * np.sin(0.5 * r[:, 1] * DIMX)      # close enough to the Landau profile for timing
-        x[1] = r[:, 2] * DIMY
-        vv = np.sqrt(-2 * np.log((np.arange(1, n + 1) - 0.5) / n))
-        v[0], v[1] = vv * np.cos(2 * np.pi * r[:, 0]), vv * np.sin(2 * np.pi * r[:, 0])
-    else:
-        x, v, _ = orc.plasma_from_uniforms(om, n, 0.05, 0.5, rng.random(n * 80))
-    sim = orc.sim(om, ntau, EPS, DT, x, v, DIMX * DIMY / n, faithful=faithful)
+    n = min(sample_particles, np_global)
+    x, v = orc.generate(om, load, SEED, n, np_global=np_global, first=0, stride=max(1, np_global // n))
+    sim = orc.sim(om, ntau, eps, DT, x, v, DIMX * DIMY / n, faithful=faithful)
     sim.init()
     for _ in range(warmup):
         sim.step()
@@ -136,6 +134,42 @@ def cpu_oracle_rate(workload, steps, warmup, sample_particles, threads=None, fai
     return n * ntau * steps / dt, dt / steps * 1e3, nthreads
 
 
+def cpu_baseline_block(workload, np_global, eps, sample, steps=2, warmup=1):
+    """all host cores, and one core on an eighth of the sample (B1 = the stand-in for the README's
+    single-core Fortran figure)"""
+    ntau = WORKLOADS[workload][1]
+    rate, _, threads = cpu_oracle_rate(workload, steps, warmup, sample, np_global, eps)
+    s1 = max(2000, sample // 8)
+    rate1, _, _ = cpu_oracle_rate(workload, steps, warmup, s1, np_global, eps, threads=1)
+    what = "C port of fortran/bupdate.F90 (3 gathers/step as the Fortran does), same generated particles as the GPU arm (every k-th)"
+    return {"value": rate, "unit": "particle-tau updates/s", "cores": threads, "kind": "port",
+            "sample": f"{min(sample, np_global)} particles x ntau={ntau} x {steps} steps of the same workload; {what}",
+            "one_core": {"value": rate1, "cores": 1, "sample": f"{min(s1, np_global)} particles x ntau={ntau} x {steps} steps"}}
+
+
+def run_peaks(args):
+    """--peaks: measure the chip's DFMA issue rate (uapic_probe_fp64_peak) and write profiles/fp64_peak.json"""
+    import torch
+    import uapic_b200 as ub
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    sampler = ClockSampler(local)
+    best, best_ms = 0.0, 0.0
+    for _ in range(5):
+        r, ms = ub.probe_fp64_peak(local, 20)
+        if r > best:
+            best, best_ms = r, ms
+    clocks = sampler.stop()
+    out = {"dfma_per_s": best, "fp64_tflops": 2 * best / 1e12, "ms_per_launch": best_ms,
+           "how": "pure DFMA loop, 8 independent chains/thread, 256 threads x 8 CTAs/SM, 2^16 iterations, best of 5 x 20 launches (CUDA events)",
+           "gpu": torch.cuda.get_device_name(local), "clocks": clocks,
+           "nominal_dfma_per_s": 148 * 64 * 1.965e9}
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    for d in ("profiles", "gpurun_out"):
+        with open(os.path.join(ROOT, d, "fp64_peak.json"), "w") as f:
+            json.dump(out, f, indent=1)
+    print(json.dumps(out), flush=True)
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path.  Neither Julia nor a Fortran compiler nor
     FFTW exist in this image, so it is the line-by-line C port (oracle/uapic_oracle.c, three gathers per step as the
@@ -143,17 +177,19 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    load, ntau, nx, ny, _, mode, desc = WORKLOADS[args.workload]
+    load, ntau, nx, ny, np_cfg, mode, desc = WORKLOADS[args.workload]
+    np_global = args.particles or (np_cfg * args.gpus if mode == "per_gpu" else np_cfg)
     sample = args.cpu_sample or 200_000
-    rate, ms, threads = cpu_oracle_rate(args.workload, args.steps, args.warmup, sample)
+    rate, ms, threads = cpu_oracle_rate(args.workload, args.steps, args.warmup, sample, np_global, args.eps)
     line = {
         "impl": "reference", "metric": "particle-tau updates/sec", "value": rate, "unit": "particle-tau updates/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "strong" if mode == "total" else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": desc, "ntau": ntau, "mesh": [nx, ny], "eps": EPS, "scheme": "M6",
-                   "note": "CPU port timed on a bounded sample; cost is linear in the particle count"},
+        "config": {"workload": desc, "load": load, "ntau": ntau, "mesh": [nx, ny], "eps": args.eps, "dt": DT, "scheme": "M6",
+                   "particles_total": np_global,
+                   "note": "CPU port timed on a bounded sample of the same generated particles (every k-th of the full load); cost is linear in the particle count"},
         "cpu_baseline": {"value": rate, "unit": "particle-tau updates/s", "cores": threads, "kind": "port",
-                         "sample": f"{sample} particles x ntau={ntau} x {args.steps} steps of the same workload (Fortran-faithful: 3 gathers/step)"},
+                         "sample": f"{min(sample, np_global)} particles x ntau={ntau} x {args.steps} steps of the same workload (Fortran-faithful: 3 gathers/step)"},
         "e2e": {"value": rate, "unit": "particle-tau updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -173,6 +209,11 @@ def main():
                          "legacy two-barrier kernels 128 B (full) / 16 B + recompute (hybrid)")
     ap.add_argument("--scheme", default="m6", choices=["m6", "cic"],
                     help="shape function: m6 = what the reference ships (the metric is quoted on it); cic = build-defined bilinear variant")
+    ap.add_argument("--reduce", default="nccl", choices=["nccl", "torch"],
+                    help="N > 1: who sums the raw rho meshes -- nccl: ncclAllReduce enqueued by the library (default); torch: host callback")
+    ap.add_argument("--eps", type=float, default=EPS, help="the small parameter (bupdate.F90:18: 0.1); BASELINE config 4 sweeps 1e-1 .. 1e-5")
+    ap.add_argument("--particles", type=int, default=0, help="override the workload's TOTAL particle count (strong scaling)")
+    ap.add_argument("--peaks", action="store_true", help="measure the fp64 DFMA peak of the device, write profiles/fp64_peak.json, exit")
     ap.add_argument("--cpu-sample", type=int, default=0, help="particles in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -182,6 +223,9 @@ def main():
 
     if args.impl == "reference":
         run_reference(args)
+        return
+    if args.peaks:
+        run_peaks(args)
         return
 
     import torch
@@ -202,6 +246,10 @@ def main():
     if args.particles_per_gpu:
         mode, np_cfg = "per_gpu", args.particles_per_gpu
         desc += f" [overridden: {np_cfg} particles per GPU, weak scaling]"
+    if args.particles:
+        mode, np_cfg = "total", args.particles
+        desc += f" [overridden: {np_cfg} particles in total]"
+    eps = args.eps
     np_global = np_cfg * world if mode == "per_gpu" else np_cfg
     np_gpu = np_global // world
     mesh = ub.Mesh(0, DIMX, nx, 0, DIMY, ny)
@@ -224,15 +272,18 @@ def main():
                 storage = "onepass-lean"
             elif base < free_b:
                 storage, sort_on = "onepass-lean", False
-    s = ub.Session(mesh, ntau, EPS, DT, hi - lo, nbpart_global=np_global, device=local, stream=stream,
+    s = ub.Session(mesh, ntau, eps, DT, hi - lo, nbpart_global=np_global, device=local, stream=stream,
                    deposit_mode=ub.DEPOSIT_FIXED_POINT if args.deposit == "fixed" else ub.DEPOSIT_FP64_ATOMIC,
                    storage_mode=MODES[storage], scheme=ub.SCHEME_CIC if args.scheme == "cic" else ub.SCHEME_M6)
     if not sort_on:
         s.set_sort(0)
     if world > 1:
-        ub.dist.attach_torch_allreduce(s)
+        if args.reduce == "nccl":
+            ub.dist.attach_nccl(s)                 # the library owns the communicator and enqueues ncclAllReduce itself
+        else:
+            ub.dist.attach_torch_allreduce(s)      # host-callback hook (torch.distributed)
     # interleaved shards (global index = rank + k*world): the Landau load stratifies |v| by particle index
-    s.generate_particles(load, seed=20190101, first_global_index=first, index_stride=stride)
+    s.generate_particles(load, seed=SEED, first_global_index=first, index_stride=stride)
     s.init_fields()
     s.step(args.warmup)
     s.synchronize()
@@ -333,7 +384,7 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "strong" if mode == "total" else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": desc, "load": load, "ntau": ntau, "mesh": [nx, ny], "eps": EPS, "dt": DT, "scheme": args.scheme.upper(),
+            "config": {"workload": desc, "load": load, "ntau": ntau, "mesh": [nx, ny], "eps": eps, "dt": DT, "scheme": args.scheme.upper(),
                        "particles_per_gpu": np_gpu, "particles_total": np_global, "deposit": args.deposit,
                        "storage": {"full": "store-full (128 B per particle-tau across the intra-step barrier, two barriers per step)",
                                    "hybrid": "hybrid (16 B per particle-tau across the barrier, predictor recomputed in phase B)",
@@ -341,7 +392,7 @@ def main():
                                    "onepass-lean": "one-pass lean (one field barrier per step, 48 B per particle-tau across it)"}[storage],
                        "hbm_free_gb_before_alloc": round(free_b / 1e9, 1), "particle_reordering": "every step, 8x8-cell bins" if (sort_on and onepass) else "off",
                        "l2": f"inputs larger than L2: {s.device_bytes / 1e9:.1f} GB of particle state per GPU streamed every step",
-                       "parallelism": f"particle shards x{world}, allreduce(rho) over NCCL" if world > 1 else "single GPU"},
+                       "parallelism": f"particle shards x{world}, allreduce(rho) over NCCL ({'in-library ncclAllReduce' if args.reduce == 'nccl' else 'torch.distributed callback'})" if world > 1 else "single GPU"},
             "e2e": e2e,
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": hbm, "unit": "GB/s",
@@ -353,11 +404,9 @@ def main():
                          "algorithmic_bytes_per_update": b_alg},
             "clocks": clocks,
         }
-        if not args.no_cpu_baseline and world == 1:
-            sample = args.cpu_sample or 100_000
-            rate, ms_cpu, threads = cpu_oracle_rate(args.workload, 2, 1, sample)
-            line["cpu_baseline"] = {"value": rate, "unit": "particle-tau updates/s", "cores": threads, "kind": "port",
-                                    "sample": f"{sample} particles x ntau={ntau} x 2 steps of the same workload, C port of fortran/bupdate.F90 with OpenMP (3 gathers/step)"}
+        if not args.no_cpu_baseline:
+            # rank 0 only, after every timed region (the other ranks wait at the final barrier)
+            line["cpu_baseline"] = cpu_baseline_block(args.workload, np_global, eps, args.cpu_sample or (100_000 if world == 1 else 50_000))
         else:
             line["cpu_baseline"] = None
         print(json.dumps(line), flush=True)

@@ -73,6 +73,10 @@ int uapic_compiled_arch(void);
 int uapic_fixed_point_scale(double total_mass, double *scale);
 /* number of usable CUDA devices (0 and UAPIC_ENODEVICE when none) */
 int uapic_device_count(int *count);
+/* measurement aid (bench.py --peaks): DFMA instructions per second the whole chip sustains in a pure fused-multiply-add
+   loop (8 independent chains per thread), over `launches` back-to-back launches timed with CUDA events.  The fp64-pipe
+   roofline of SURVEY.md section 8d is 2 flop x this number; nothing on the product path calls it. */
+int uapic_probe_fp64_peak(int device, int launches, double *dfma_per_s, double *ms_per_launch);
 
 /* ------------------------------------------------------------------------------------------
  * Stage API: one entry point per exported Julia function on the hot path.
@@ -168,6 +172,19 @@ typedef int (*uapic_allreduce_fn)(void *ctx, void *buf, int64_t count, int dtype
 int uapic_session_create(const uapic_config_t *cfg, uapic_session_t **out);
 int uapic_session_destroy(uapic_session_t *s);
 int uapic_session_set_allreduce(uapic_session_t *s, uapic_allreduce_fn fn, void *ctx);
+
+/* In-library NCCL: the library binds libnccl.so.2 at run time (dlopen; $UAPIC_NCCL_LIB overrides the
+   name) and enqueues ncclAllReduce(sum) of the raw rho meshes on the session's stream itself -- no host callback, so a Julia or
+   C caller gets the multi-GPU path with two calls and the step stays capturable in a CUDA graph.
+   One process per GPU: rank 0 calls uapic_nccl_unique_id and hands the 128 bytes to the other ranks by any means it has (MPI,
+   a file, torch.distributed); every rank then calls uapic_session_init_nccl (collective: ncclCommInitRank on the session's
+   device).  The communicator is destroyed with the session.  uapic_session_set_nccl_comm adopts an existing ncclComm_t
+   instead (not destroyed by the session; NULL detaches).  Takes precedence over uapic_session_set_allreduce. */
+#define UAPIC_NCCL_ID_BYTES 128
+int uapic_nccl_unique_id(void *id128);
+int uapic_nccl_version(int *version);
+int uapic_session_init_nccl(uapic_session_t *s, const void *id128, int nranks, int rank);
+int uapic_session_set_nccl_comm(uapic_session_t *s, void *nccl_comm);
 
 /* x, v (2,nbpart) host (pageable or pinned) -> device SoA */
 int uapic_session_upload_particles(uapic_session_t *s, const double *x, const double *v);

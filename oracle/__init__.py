@@ -193,6 +193,16 @@ class _COracle:
         """persistent-state driver (init / step separately timed by bench.py's CPU baseline)"""
         return _Sim(self, m, ntau, eps, dt, x, v, w, wrap, faithful)
 
+    def generate(self, m, kind, seed, npart, np_global=None, first=0, stride=1, alpha=0.05, kx=0.5):
+        """the counter-based synthetic loads of the benchmark configs, same particles as the device generator
+        (kind "plasma"/0: particles.F90:68-103 densities; "landau"/1: intent of src/landau.jl:19-43)"""
+        kind = {"plasma": 0, "landau": 1}.get(kind, kind)
+        x = np.zeros((2, npart), order="F")
+        v = np.zeros((2, npart), order="F")
+        self.lib.orc_generate(C.byref(m), C.c_int(kind), C.c_uint64(seed), C.c_int64(first), C.c_int64(stride), C.c_int64(npart),
+                              C.c_int64(np_global if np_global is not None else npart), C.c_double(alpha), C.c_double(kx), _p(x), _p(v))
+        return x, v
+
     def plasma_from_uniforms(self, m, npart, alpha, kx, u):
         x = np.zeros((2, npart), order="F")
         v = np.zeros((2, npart), order="F")

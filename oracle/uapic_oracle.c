@@ -938,3 +938,77 @@ int64_t orc_plasma_from_uniforms(const orc_mesh *m, int64_t np, double alpha, do
     }
     return iu;
 }
+
+/* ------------------------------------------------------------------------------------ */
+/* Counter-based synthetic loads of the BENCHMARK configs (*/
+/* "counter-based RNG keyed by (seed, particle index)").  Not reference code: the reference  */
+/* draws from the Fortran RANDOM_NUMBER stream (particles.F90:68-103) or from Sobol points   */
+/* (src/landau.jl:19-43), neither of which can hand a shard its slice.  Stated here so that  */
+/* the CPU arm of bench.py and the parity tests run on the SAME particles as the device      */
+/* generator k_generate (uapic.jl_b200/csrc/uapic_kernels.cu): same hash, same draw order,   */
+/* same densities (kind 0: particles.F90:68-103; kind 1: the intent of src/landau.jl:19-43). */
+/* global particle id = first + k*stride.                                                    */
+/* ------------------------------------------------------------------------------------ */
+static uint64_t orc_splitmix64(uint64_t z)
+{
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+static double orc_uniform01(uint64_t seed, uint64_t particle, uint32_t stream, uint32_t draw)
+{
+    uint64_t h = orc_splitmix64(seed ^ orc_splitmix64(particle * 0xD1342543DE82EF95ull + stream));
+    h = orc_splitmix64(h + draw);
+    return (double)(h >> 11) * (1.0 / 9007199254740992.0);
+}
+
+void orc_generate(const orc_mesh *m, int kind, uint64_t seed, int64_t first, int64_t stride, int64_t np, int64_t np_global,
+                  double alpha, double kx, double *x, double *v)
+{
+    const double dimx = m->xmax - m->xmin, dimy = m->ymax - m->ymin;
+    const double pi = 3.14159265358979323846;
+    #pragma omp parallel for schedule(static) num_threads(g_threads)
+    for (int64_t k = 0; k < np; ++k) {
+        const uint64_t id = (uint64_t)(first + k * stride);
+        double x1, x2, v1, v2;
+        if (kind == 0) {
+            uint32_t d = 0;
+            for (;;) {
+                const double xi = orc_uniform01(seed, id, 0, d) * dimx;
+                const double yi = orc_uniform01(seed, id, 0, d + 1) * dimy;
+                const double zi = (2.0 + alpha) * orc_uniform01(seed, id, 0, d + 2);
+                d += 3;
+                if (1.0 + sin(yi) + alpha * cos(kx * xi) >= zi) { x1 = xi; x2 = yi; break; }
+            }
+            d = 0;
+            for (;;) {
+                const double xi = (orc_uniform01(seed, id, 1, d) - 0.5) * 10.0;
+                const double yi = (orc_uniform01(seed, id, 1, d + 1) - 0.5) * 10.0;
+                const double zi = orc_uniform01(seed, id, 1, d + 2);
+                d += 3;
+                const double temm = (exp(-((xi - 2.0) * (xi - 2.0) + yi * yi) / 2.0) + exp(-((xi + 2.0) * (xi + 2.0) + yi * yi) / 2.0)) / 2.0;
+                if (temm >= zi) { v1 = xi; v2 = yi; break; }
+            }
+            x1 += m->xmin; x2 += m->ymin;
+        } else {
+            const double r1 = orc_uniform01(seed, id, 2, 0), r2 = orc_uniform01(seed, id, 2, 1), r3 = orc_uniform01(seed, id, 2, 2);
+            const double target = r2 * (2.0 * pi / kx);
+            double x0 = target;
+            for (int it = 0; it < 50; ++it) {
+                const double pfun = x0 + alpha * sin(kx * x0) / kx;
+                const double f = 1.0 + alpha * cos(kx * x0);
+                const double xn = x0 - (pfun - target) / f;
+                const int done = fabs(xn - x0) <= 1e-12;
+                x0 = xn;
+                if (done) break;
+            }
+            x1 = m->xmin + x0;
+            x2 = m->ymin + r3 * dimy;
+            const double vv = sqrt(-2.0 * log(((double)id + 0.5) / (double)np_global));
+            v1 = vv * cos(2.0 * pi * r1); v2 = vv * sin(2.0 * pi * r1);
+        }
+        x[2 * k] = x1; x[2 * k + 1] = x2;
+        v[2 * k] = v1; v[2 * k + 1] = v2;
+    }
+}

@@ -18,12 +18,15 @@ import uapic_b200 as ub  # noqa: E402
 from conftest import seeded_load  # noqa: E402
 
 
-def run(mode, npart, ntau, nstep, x0, v0, mesh, w, rank, world, local):
+def run(mode, npart, ntau, nstep, x0, v0, mesh, w, rank, world, local, reducer="nccl"):
     lo, hi = ub.dist.shard_range(npart, rank, world)
     s = ub.Session(mesh, ntau, 0.1, np.pi / 16, hi - lo, weight=w, nbpart_global=npart, deposit_mode=mode, device=local,
                    stream=torch.cuda.current_stream().cuda_stream)
     if world > 1:
-        ub.dist.attach_torch_allreduce(s)
+        if reducer == "nccl":
+            ub.dist.attach_nccl(s)              # in-library ncclAllReduce (uapic_session_init_nccl)
+        else:
+            ub.dist.attach_torch_allreduce(s)   # host callback hook (uapic_session_set_allreduce)
     s.upload_particles(np.asfortranarray(x0[:, lo:hi]), np.asfortranarray(v0[:, lo:hi]))
     s.init_fields()
     s.step(nstep)
@@ -45,8 +48,9 @@ def main():
     mesh = ub.Mesh(0, 4 * np.pi, 128, 0, 2 * np.pi, 64)
     w = 8 * np.pi ** 2 / npart
     res = {}
-    for name, mode in (("fixed", ub.DEPOSIT_FIXED_POINT), ("fp64", ub.DEPOSIT_FP64_ATOMIC)):
-        x, v, en, e = run(mode, npart, ntau, nstep, x0, v0, mesh, w, rank, world, local)
+    for name, mode, reducer in (("fixed", ub.DEPOSIT_FIXED_POINT, "nccl"), ("fp64", ub.DEPOSIT_FP64_ATOMIC, "nccl"),
+                                ("fixed_callback", ub.DEPOSIT_FIXED_POINT, "torch")):
+        x, v, en, e = run(mode, npart, ntau, nstep, x0, v0, mesh, w, rank, world, local, reducer)
         # gather the shards on rank 0
         xs = [None] * world
         vs = [None] * world

@@ -1,5 +1,5 @@
 """Multi-GPU parity (needs >= 2 GPUs; skipped otherwise): particles sharded over ranks, raw rho summed with NCCL through
-the C ABI's all-reduce hook.  Fixed-point deposition must give bit-identical results for 1 and N GPUs; fp64-atomic
+NCCL inside the library (uapic_session_init_nccl) and, once, through the C ABI's all-reduce callback hook.  Fixed-point deposition must give bit-identical results for 1 and N GPUs; fp64-atomic
 deposition must agree to the 1e-10 tolerance of the north star."""
 import json
 import os
@@ -28,6 +28,8 @@ def test_sharded_run_matches_single_gpu(tmp_path):
     fx = res["fixed"]
     assert fx["bit_identical_x"] and fx["bit_identical_v"] and fx["bit_identical_energy"] and fx["bit_identical_emesh"], fx
     assert fx["ranks_agree_on_energy"]
+    fc = res["fixed_callback"]      # the host-callback hook gives the same bits as the in-library collective
+    assert fc["bit_identical_x"] and fc["bit_identical_v"] and fc["bit_identical_energy"] and fc["bit_identical_emesh"], fc
     fp = res["fp64"]
     assert fp["max_abs_dx"] < 1e-10 * 4 * 3.15 and fp["max_abs_dv"] < 1e-9 and fp["max_rel_denergy"] < 1e-10, fp
     assert fp["ranks_agree_on_energy"]

@@ -5,7 +5,7 @@
 All compute happens in `libuapic_b200.so` (hand-written sm_100a CUDA).  There is no CPU fallback.
 """
 from ._lib import (DEPOSIT_FIXED_POINT, DEPOSIT_FP64_ATOMIC, LIB_PATH, SCHEME_CIC, SCHEME_M6, STORE_FULL, STORE_HYBRID,  # noqa: F401
-                   STORE_ONEPASS, STORE_ONEPASS_LEAN, WRAP_FORTRAN, WRAP_JULIA, EXPORTS, UapicError, device_count, lib)
+                   STORE_ONEPASS, STORE_ONEPASS_LEAN, WRAP_FORTRAN, WRAP_JULIA, EXPORTS, UapicError, device_count, lib, probe_fp64_peak)
 from .api import (UA, Mesh, MeshFields, Particles, Poisson, compute_f, compute_rho_m6, compute_v, errors, fft_tau,  # noqa: F401
                   gnuplot, ifft_tau, integrate, interpol_eb_m6, preparation, ua_step, ua_step1, ua_step2, update_particles_e,
                   update_particles_x)

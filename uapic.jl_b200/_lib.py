@@ -23,11 +23,12 @@ ERROR_NAMES = {-1: "UAPIC_EINVAL", -2: "UAPIC_ENODEVICE", -3: "UAPIC_ECUDA", -4:
 
 # every symbol include/uapic_b200.h declares (tests check the library exports all of them)
 EXPORTS = [
-    "uapic_last_error", "uapic_version", "uapic_compiled_arch", "uapic_device_count", "uapic_fixed_point_scale",
+    "uapic_last_error", "uapic_version", "uapic_compiled_arch", "uapic_device_count", "uapic_fixed_point_scale", "uapic_probe_fp64_peak",
     "uapic_compute_rho_m6", "uapic_interpol_eb_m6", "uapic_poisson", "uapic_preparation", "uapic_interpol_eb_m6_tau",
     "uapic_compute_f", "uapic_fft_tau", "uapic_ua_step_predict", "uapic_ua_step_correct", "uapic_ua_step1",
     "uapic_ua_step2", "uapic_compute_rho_m6_tau", "uapic_compute_v",
-    "uapic_session_create", "uapic_session_destroy", "uapic_session_set_allreduce", "uapic_session_upload_particles", "uapic_session_upload_particle_e",
+    "uapic_session_create", "uapic_session_destroy", "uapic_session_set_allreduce", "uapic_nccl_unique_id", "uapic_nccl_version",
+    "uapic_session_init_nccl", "uapic_session_set_nccl_comm", "uapic_session_upload_particles", "uapic_session_upload_particle_e",
     "uapic_session_enable_timing", "uapic_session_phase_times", "uapic_session_set_sort",
     "uapic_session_generate_particles", "uapic_session_generate_particles_strided", "uapic_session_init_fields", "uapic_session_step", "uapic_session_step_host", "uapic_session_synchronize",
     "uapic_session_download_particles", "uapic_session_download_particle_e", "uapic_session_download_fields",
@@ -89,3 +90,10 @@ def fixed_point_scale(total_mass: float) -> float:
     s = C.c_double(0.0)
     check(lib().uapic_fixed_point_scale(C.c_double(total_mass), C.byref(s)))
     return s.value
+
+
+def probe_fp64_peak(device: int = 0, launches: int = 20):
+    """(DFMA instructions/s of the whole chip in a pure FMA loop, ms per launch) -- bench.py --peaks"""
+    r, ms = C.c_double(0.0), C.c_double(0.0)
+    check(lib().uapic_probe_fp64_peak(C.c_int(device), C.c_int(launches), C.byref(r), C.byref(ms)))
+    return r.value, ms.value

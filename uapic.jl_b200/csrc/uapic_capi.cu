@@ -9,6 +9,8 @@
 #include <string>
 #include <vector>
 
+#include <dlfcn.h>
+
 #include "../../include/uapic_b200.h"
 #include "uapic_internal.h"
 
@@ -176,6 +178,16 @@ int uapic_device_count(int *count) {
     if (e != cudaSuccess) { cudaGetLastError(); n = 0; }
     if (count) *count = n;
     if (n <= 0) return fail(UAPIC_ENODEVICE, "no CUDA device available; libuapic_b200 has no CPU fallback");
+    return UAPIC_OK;
+}
+
+int uapic_probe_fp64_peak(int device, int launches, double *dfma_per_s, double *ms_per_launch) {
+    if (launches < 1 || !dfma_per_s) return fail(UAPIC_EINVAL, "uapic_probe_fp64_peak: bad argument");
+    DeviceInfo di{};
+    TRY(device_info(device, &di));
+    CU(cudaSetDevice(device));
+    LaunchCtx lc{0, di.sm_count, nullptr};
+    CU(probe_fp64_peak(lc, launches, dfma_per_s, ms_per_launch));
     return UAPIC_OK;
 }
 
@@ -423,6 +435,55 @@ int uapic_compute_v(int ntau, double eps, int64_t nbpart, const double *t, const
 #ifndef UAPIC_RAW_COPIES
 #define UAPIC_RAW_COPIES 8      // CTA-private copies of the two raw deposit meshes of the one-pass kernels (measured: -2 % on phase A)
 #endif
+// ---- NCCL, bound at run time (dlopen): the library links nothing but the CUDA runtime -------------------------------
+// Prototypes restated from nccl.h (NCCL 2.x ABI; ncclUniqueId is 128 opaque bytes passed by value; ncclSum = 0, ncclInt64 = 4,
+// ncclFloat64 = 8).  Lookup order: $UAPIC_NCCL_LIB, then "libnccl.so.2" (which resolves to an NCCL the process has already
+// loaded -- e.g. the one bundled with torch -- before the system copy).
+namespace {
+struct NcclId { char internal[128]; };
+struct NcclApi {
+    void *h = nullptr;
+    int (*GetVersion)(int *) = nullptr;
+    int (*GetUniqueId)(NcclId *) = nullptr;
+    int (*CommInitRank)(void **, int, NcclId, int) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    std::string err;
+};
+NcclApi *nccl_api() {
+    static NcclApi api;
+    static bool tried = false;
+    if (tried) return &api;
+    tried = true;
+    const char *env = getenv("UAPIC_NCCL_LIB");
+    const char *names[] = {env, "libnccl.so.2", "libnccl.so"};
+    for (const char *n : names) {
+        if (!n || !*n) continue;
+        api.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (api.h) break;
+        api.err = dlerror();
+    }
+    if (!api.h) return &api;
+    bool ok = true;
+    auto sym = [&](const char *n) { void *p = dlsym(api.h, n); if (!p) { ok = false; api.err = std::string("missing symbol ") + n; } return p; };
+    api.GetVersion = reinterpret_cast<int (*)(int *)>(sym("ncclGetVersion"));
+    api.GetUniqueId = reinterpret_cast<int (*)(NcclId *)>(sym("ncclGetUniqueId"));
+    api.CommInitRank = reinterpret_cast<int (*)(void **, int, NcclId, int)>(sym("ncclCommInitRank"));
+    api.CommDestroy = reinterpret_cast<int (*)(void *)>(sym("ncclCommDestroy"));
+    api.AllReduce = reinterpret_cast<int (*)(const void *, void *, size_t, int, int, void *, cudaStream_t)>(sym("ncclAllReduce"));
+    api.GetErrorString = reinterpret_cast<const char *(*)(int)>(sym("ncclGetErrorString"));
+    if (!ok) { dlclose(api.h); api.h = nullptr; }
+    return &api;
+}
+int nccl_need(NcclApi **out) {
+    NcclApi *a = nccl_api();
+    if (!a->h) return fail(UAPIC_EUNSUPPORTED, "NCCL is not loadable (%s); set UAPIC_NCCL_LIB or LD_LIBRARY_PATH to a libnccl.so.2", a->err.c_str());
+    *out = a;
+    return UAPIC_OK;
+}
+}  // namespace
+
 struct uapic_session {
     uapic_config_t cfg;
     MeshDev m;
@@ -437,6 +498,7 @@ struct uapic_session {
     // spatial reordering (uapic_sort.cu): alternate buffers, slot -> original index, scratch; allocated at the first sort
     DevBuf x2, v2, ep2, perm, perm2, binid, hist;
     bool permuted = false;             // device arrays are in sorted order, perm is valid
+    bool sort_bufs_ready = false;      // the whole set of alternate buffers exists (all-or-nothing)
     int sort_interval = 0, sort_shift = 3;
     int64_t steps_done = 0;
     // uapic_session_step_host: copy streams and per-chunk events (created at first use)
@@ -445,6 +507,9 @@ struct uapic_session {
     int64_t n_energy = 0, cap_energy = 0;
     uapic_allreduce_fn reduce = nullptr;
     void *reduce_ctx = nullptr;
+    void *nccl_comm = nullptr;         // ncclComm_t: the library sums the raw rho meshes itself (uapic_session_init_nccl)
+    bool nccl_owned = false;
+    int nccl_rank = 0, nccl_nranks = 1;
     bool have_particles = false, fields_ready = false;
     int64_t bytes = 0;
     // optional per-kernel timing
@@ -457,6 +522,7 @@ struct uapic_session {
         for (cudaEvent_t e : chunk_ev) cudaEventDestroy(e);
         if (up_stream) cudaStreamDestroy(up_stream);
         if (down_stream) cudaStreamDestroy(down_stream);
+        if (nccl_comm && nccl_owned) { NcclApi *a = nccl_api(); if (a->h) a->CommDestroy(nccl_comm); }
     }
 };
 
@@ -486,7 +552,14 @@ int session_clear_raw(uapic_session *s) {
 // sum the raw deposit mesh(es) over the ranks (the only exchange of the scheme)
 int session_reduce(uapic_session *s, int nmesh) {
     if (s->onepass && nmesh == 2) CU(launch_fold_raw(s->lc, s->acc, 2 * (int64_t)s->m.ld * (s->m.ny + 1), UAPIC_RAW_COPIES));
-    if (s->reduce) {
+    if (s->nccl_comm) {
+        // in-library collective on the session's stream: no host callback, capturable in a CUDA graph
+        NcclApi *a = nccl_api();
+        const size_t n = (size_t)s->m.ld * (s->m.ny + 1) * nmesh;
+        const int rc = a->AllReduce(s->raw.p, s->raw.p, n, s->acc.i64 ? 4 /* ncclInt64 */ : 8 /* ncclFloat64 */, 0 /* ncclSum */,
+                                    s->nccl_comm, s->lc.stream);
+        if (rc) return fail(UAPIC_ECUDA, "ncclAllReduce failed: %s", a->GetErrorString(rc));
+    } else if (s->reduce) {
         const int64_t n = (int64_t)s->m.ld * (s->m.ny + 1) * nmesh;
         int rc = s->reduce(s->reduce_ctx, s->raw.p, n, s->acc.i64 ? 1 : 0, (void *)s->lc.stream);
         if (rc) return fail(UAPIC_ECUDA, "allreduce callback failed with code %d", rc);
@@ -497,7 +570,7 @@ int session_reduce(uapic_session *s, int nmesh) {
 // summed raw deposits -> neutralised rho -> E (+ halo copy), energy appended      compute_rho_m6.F90:191-200 + poisson_2d.f90:85-111
 int session_solve(uapic_session *s, const RhoAcc &acc, DevBuf &emesh, DevBuf &ehalo) {
     CU(launch_rho_epilogue(s->lc, s->m, acc, s->rho.as<double>(), nullptr));
-    if (s->n_energy >= s->cap_energy) return fail(UAPIC_ESTATE, "energy history full (%lld entries)", (long long)s->cap_energy);
+    if (s->n_energy >= s->cap_energy) return fail(UAPIC_ESTATE, "energy history full (%lld entries): session_reserve_energy was not called", (long long)s->cap_energy);
     PoissonWork pw{s->rk.as<double2>(), s->ek.as<double2>()};
     CU(launch_poisson(s->lc, s->m, pw, s->rho.as<double>(), emesh.as<double>(), s->energy.as<double>() + s->n_energy));
     if (s->onepass) CU(launch_extend_emesh_tiled(s->lc, s->m, emesh.as<double>(), ehalo.as<double2>()));
@@ -526,7 +599,7 @@ OnepassParams session_onepass_params(uapic_session *s) {
 // reorder x, v, ep by coarse mesh bin; callers never see the order (downloads undo it)
 int session_alloc_sort_buffers(uapic_session *s) {
     const size_t np = (size_t)s->cfg.nbpart;
-    if (s->x2.p || np == 0) return UAPIC_OK;
+    if (s->sort_bufs_ready || np == 0) return UAPIC_OK;
     int rc = UAPIC_OK;
     if (!rc) rc = session_alloc(s, s->x2, 16 * np);
     if (!rc) rc = session_alloc(s, s->v2, 16 * np);
@@ -535,7 +608,42 @@ int session_alloc_sort_buffers(uapic_session *s) {
     if (!rc) rc = session_alloc(s, s->perm2, 4 * np);
     if (!rc) rc = session_alloc(s, s->binid, 2 * np);
     if (!rc) rc = session_alloc(s, s->hist, 4 * 4096);
-    return rc;
+    if (rc) {
+        // all or nothing: a partial set would let a later step write through null buffers
+        for (DevBuf *b : {&s->x2, &s->v2, &s->ep2, &s->perm, &s->perm2, &s->binid, &s->hist}) {
+            if (b->p) { s->bytes -= (int64_t)b->bytes; cudaFree(b->p); b->p = nullptr; b->bytes = 0; }
+        }
+        return rc;
+    }
+    s->sort_bufs_ready = true;
+    return UAPIC_OK;
+}
+
+// the reordering is an optimisation: if its buffers do not fit, run without it rather than fail the step
+int session_want_sort(uapic_session *s, bool *on) {
+    *on = false;
+    if (s->sort_interval <= 0 || s->cfg.nbpart == 0) return UAPIC_OK;
+    const int rc = session_alloc_sort_buffers(s);
+    if (rc == UAPIC_ENOMEM) { s->sort_interval = 0; return UAPIC_OK; }
+    if (rc) return rc;
+    *on = true;
+    return UAPIC_OK;
+}
+
+// room for `need` more entries of the energy history (checked BEFORE anything of a step is launched); grows by doubling
+int session_reserve_energy(uapic_session *s, int64_t need) {
+    if (s->n_energy + need <= s->cap_energy) return UAPIC_OK;
+    int64_t cap = s->cap_energy;
+    while (cap < s->n_energy + need) cap *= 2;
+    DevBuf nb;
+    cudaError_t e = nb.alloc(8 * (size_t)cap);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(UAPIC_ENOMEM, "cannot grow the energy history to %lld entries", (long long)cap); }
+    CU(cudaMemcpyAsync(nb.p, s->energy.p, 8 * (size_t)s->n_energy, cudaMemcpyDeviceToDevice, s->lc.stream));
+    CU(cudaStreamSynchronize(s->lc.stream));
+    s->bytes += (int64_t)nb.bytes - (int64_t)s->energy.bytes;
+    s->energy.swap(nb);
+    s->cap_energy = cap;
+    return UAPIC_OK;
 }
 
 int session_sort(uapic_session *s) {
@@ -609,7 +717,7 @@ int uapic_session_create(const uapic_config_t *cfg, uapic_session_t **out) {
     const size_t np = (size_t)cfg->nbpart, N = (size_t)cfg->ntau;
     const size_t nrho = (size_t)s->m.ld * (s->m.ny + 1), nk = (size_t)(s->m.nx / 2 + 1) * s->m.ny;
     int rc = UAPIC_OK;
-    s->cap_energy = 1 << 16;
+    s->cap_energy = 1 << 12;
     if (!rc) rc = session_alloc(s, s->x, 16 * (np ? np : 1));
     if (!rc) rc = session_alloc(s, s->v, 16 * (np ? np : 1));
     if (!rc) rc = session_alloc(s, s->ep, 16 * (np ? np : 1));
@@ -634,7 +742,7 @@ int uapic_session_create(const uapic_config_t *cfg, uapic_session_t **out) {
     if (!rc) rc = session_alloc(s, s->rk, 16 * nk);
     if (!rc) rc = session_alloc(s, s->ek, 32 * nk);
     if (!rc) rc = session_alloc(s, s->energy, 8 * (size_t)s->cap_energy);
-    if (!rc) rc = session_alloc(s, s->sumv, 16);
+    if (!rc) rc = session_alloc(s, s->sumv, 16 + sum_v_scratch_bytes());
     if (rc) { delete s; return rc; }
     if (cfg->deposit_mode == UAPIC_DEPOSIT_FIXED_POINT) {
         s->acc.f64 = nullptr; s->acc.i64 = s->raw.as<unsigned long long>(); s->acc.scale = fixed_point_scale(total_mass);
@@ -663,6 +771,55 @@ int uapic_session_destroy(uapic_session_t *s) {
 int uapic_session_set_allreduce(uapic_session_t *s, uapic_allreduce_fn fn, void *ctx) {
     if (!s) return fail(UAPIC_EINVAL, "session is null");
     s->reduce = fn; s->reduce_ctx = ctx;
+    return UAPIC_OK;
+}
+
+int uapic_nccl_unique_id(void *id128) {
+    if (!id128) return fail(UAPIC_EINVAL, "uapic_nccl_unique_id: null pointer");
+    NcclApi *a = nullptr;
+    TRY(nccl_need(&a));
+    NcclId id;
+    const int rc = a->GetUniqueId(&id);
+    if (rc) return fail(UAPIC_ECUDA, "ncclGetUniqueId failed: %s", a->GetErrorString(rc));
+    memcpy(id128, id.internal, sizeof(id.internal));
+    return UAPIC_OK;
+}
+
+int uapic_nccl_version(int *version) {
+    if (!version) return fail(UAPIC_EINVAL, "uapic_nccl_version: null pointer");
+    NcclApi *a = nullptr;
+    TRY(nccl_need(&a));
+    const int rc = a->GetVersion(version);
+    if (rc) return fail(UAPIC_ECUDA, "ncclGetVersion failed: %s", a->GetErrorString(rc));
+    return UAPIC_OK;
+}
+
+static void session_drop_nccl(uapic_session *s) {
+    if (s->nccl_comm && s->nccl_owned) { NcclApi *a = nccl_api(); if (a->h) a->CommDestroy(s->nccl_comm); }
+    s->nccl_comm = nullptr; s->nccl_owned = false; s->nccl_rank = 0; s->nccl_nranks = 1;
+}
+
+int uapic_session_init_nccl(uapic_session_t *s, const void *id128, int nranks, int rank) {
+    if (!s || !id128) return fail(UAPIC_EINVAL, "uapic_session_init_nccl: null pointer");
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(UAPIC_EINVAL, "uapic_session_init_nccl: rank %d of %d", rank, nranks);
+    NcclApi *a = nullptr;
+    TRY(nccl_need(&a));
+    TRY(session_bind(s));
+    session_drop_nccl(s);
+    NcclId id;
+    memcpy(id.internal, id128, sizeof(id.internal));
+    void *comm = nullptr;
+    const int rc = a->CommInitRank(&comm, nranks, id, rank);
+    if (rc) return fail(UAPIC_ECUDA, "ncclCommInitRank(rank %d of %d) failed: %s", rank, nranks, a->GetErrorString(rc));
+    s->nccl_comm = comm; s->nccl_owned = true; s->nccl_rank = rank; s->nccl_nranks = nranks;
+    return UAPIC_OK;
+}
+
+int uapic_session_set_nccl_comm(uapic_session_t *s, void *comm) {
+    if (!s) return fail(UAPIC_EINVAL, "session is null");
+    if (comm) { NcclApi *a = nullptr; TRY(nccl_need(&a)); }
+    session_drop_nccl(s);
+    s->nccl_comm = comm; s->nccl_owned = false;
     return UAPIC_OK;
 }
 
@@ -766,6 +923,7 @@ int uapic_session_init_fields(uapic_session_t *s) {
     if (!s->have_particles) return fail(UAPIC_ESTATE, "upload or generate particles before uapic_session_init_fields");
     TRY(session_bind(s));
     s->n_energy = 0;
+    TRY(session_reserve_energy(s, 1));
     TRY(session_clear_raw(s));
     CU(launch_deposit(s->lc, s->m, s->cfg.nbpart, s->x.as<double>(), s->cfg.weight, s->acc, s->cfg.wrap, s->cfg.scheme));   // bupdate.F90:89
     TRY(session_field_solve(s));                                                                              // :91
@@ -779,8 +937,13 @@ int uapic_session_step(uapic_session_t *s, int nsteps) {
     if (!s->fields_ready) return fail(UAPIC_ESTATE, "call uapic_session_init_fields before uapic_session_step");
     if (nsteps < 0) return fail(UAPIC_EINVAL, "nsteps must be >= 0");
     TRY(session_bind(s));
+    TRY(session_reserve_energy(s, 2 * (int64_t)nsteps));
     for (int it = 0; it < nsteps; ++it) {
-        if (s->sort_interval > 0 && s->steps_done % s->sort_interval == 0) TRY(session_sort(s));
+        if (s->sort_interval > 0 && s->steps_done % s->sort_interval == 0) {
+            bool sort_on = false;
+            TRY(session_want_sort(s, &sort_on));
+            if (sort_on) TRY(session_sort(s));
+        }
         s->steps_done++;
         const PhaseParams p = session_params(s);
         OnepassParams op = s->onepass ? session_onepass_params(s) : OnepassParams{};
@@ -852,7 +1015,9 @@ int uapic_session_step_host(uapic_session_t *s, const double *x_in, const double
         s->ep.swap(s->ep2);
     }
     s->permuted = false;
-    TRY(session_alloc_sort_buffers(s));
+    TRY(session_reserve_energy(s, 2));
+    bool sort = false;
+    TRY(session_want_sort(s, &sort));
     cudaStream_t cs = s->lc.stream;
     cudaEvent_t ev_start = s->chunk_ev[2 * kMaxChunks], ev_done = s->chunk_ev[2 * kMaxChunks + 1];
     CU(cudaEventRecord(ev_start, cs));                       // earlier work on the session stream (previous step) is finished
@@ -862,7 +1027,6 @@ int uapic_session_step_host(uapic_session_t *s, const double *x_in, const double
     const int64_t per = ((np + kChunks - 1) / kChunks + 255) / 256 * 256;
     OnepassParams op = session_onepass_params(s);
     const size_t stride = onepass_store_bytes_per_particle(op.ntau, op.full);
-    const bool sort = s->sort_interval > 0;
     // ---- uploads || reorder + phase A, chunk by chunk ----
     for (int c = 0; c < kChunks; ++c) {
         const int64_t lo = (int64_t)c * per, n = std::min(per, np - lo);
@@ -968,7 +1132,7 @@ int uapic_session_energy_history(uapic_session_t *s, double *out, int64_t capaci
 int uapic_session_sum_v(uapic_session_t *s, double *sumv2) {
     if (!s || !sumv2) return fail(UAPIC_EINVAL, "null pointer");
     TRY(session_bind(s));
-    CU(launch_sum_v(s->lc, s->cfg.nbpart, s->v.as<double>(), s->sumv.as<double>()));
+    CU(launch_sum_v(s->lc, s->cfg.nbpart, s->v.as<double>(), s->sumv.as<double>() + 2, s->sumv.as<double>()));
     CU(cudaMemcpyAsync(sumv2, s->sumv.p, 16, cudaMemcpyDeviceToHost, s->lc.stream));
     CU(cudaStreamSynchronize(s->lc.stream));
     return UAPIC_OK;

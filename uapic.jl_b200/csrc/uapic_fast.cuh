@@ -106,6 +106,54 @@ DEVINL void gather_tiled(const MeshDev &m, const double2 *__restrict__ ehalo, co
     e1 = s1; e2 = s2;
 }
 
+// ---- the same gather with 256-bit loads (sm_100a: LDG.E.256) -----------------------------------------------------
+// In the 2 x 4 tiling the two nodes (I, J), (I+1, J) with I even are 32 contiguous, 32-byte-aligned bytes, so one
+// ld.global.nc.v4.f64 fetches a PAIR of taps.  The L1 data pipe spends one wavefront per distinct 128-byte line an
+// instruction touches, whatever the access width (B300_MICROARCH.md, "L1tex wavefront queue"), and both nodes of a pair
+// sit in the same line: a row of 6 taps costs 3 pair loads (+ one predicated 16-byte load of the 7th node when the
+// stencil starts on an odd node) instead of 6 loads -- 21 load instructions per gather on average instead of 36, at the
+// same number of lines per instruction.  The 6 weights are shifted into a 7-wide window by the parity of c.i.
+DEVINL void ldg256(const double2 *p, double2 &a, double2 &b) {
+    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a.x), "=d"(a.y), "=d"(b.x), "=d"(b.y) : "l"(p));
+}
+
+DEVINL void gather_tiled_pairs(const MeshDev &m, const double2 *__restrict__ ehalo, const Cell &c, double &e1, double &e2) {
+    double cx[6], cy[6];
+    m6_weights_fast(c.dpx, cx);
+    m6_weights_fast(c.dpy, cy);
+    const int ntx8 = halo_tiled_ntx(m) << 3;
+    const bool odd = c.i & 1;
+    double w[7];
+    w[0] = odd ? 0.0 : cx[0];
+#pragma unroll
+    for (int a = 1; a < 6; ++a) w[a] = odd ? cx[a - 1] : cx[a];
+    w[6] = odd ? cx[5] : 0.0;
+    int q = c.j & 3;
+    int roff = (c.j >> 2) * ntx8 + (q << 1) + ((c.i >> 1) << 3);           // even node (i-2 or i-3, j-2)
+    double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+    for (int b = 0; b < 6; ++b) {
+        const double2 *r = ehalo + roff;
+        double2 n0, n1, n2, n3, n4, n5, n6 = make_double2(0.0, 0.0);
+        ldg256(r, n0, n1);
+        ldg256(r + 8, n2, n3);
+        ldg256(r + 16, n4, n5);
+        if (odd) n6 = __ldg(r + 24);
+        double r1 = w[0] * n0.x, r2 = w[0] * n0.y;
+        r1 = fma(w[1], n1.x, r1); r2 = fma(w[1], n1.y, r2);
+        r1 = fma(w[2], n2.x, r1); r2 = fma(w[2], n2.y, r2);
+        r1 = fma(w[3], n3.x, r1); r2 = fma(w[3], n3.y, r2);
+        r1 = fma(w[4], n4.x, r1); r2 = fma(w[4], n4.y, r2);
+        r1 = fma(w[5], n5.x, r1); r2 = fma(w[5], n5.y, r2);
+        r1 = fma(w[6], n6.x, r1); r2 = fma(w[6], n6.y, r2);
+        s1 = fma(cy[b], r1, s1);
+        s2 = fma(cy[b], r2, s2);
+        roff += (q == 3) ? ntx8 - 6 : 2;
+        q = (q + 1) & 3;
+    }
+    e1 = s1; e2 = s2;
+}
+
 // ---- CIC (bilinear), BUILD-DEFINED: the reference has no 2D CIC deposit and no CIC in the UA loop.
 // Weights of performance/test_cic.F90:73-76 (= 2D restriction of fortran/compute_rho_cic.f90:46-53) on nodes (i,j), (i+1,j),
 // (i+1,j+1), (i,j+1); wrap, ghost copy, /(dx dy) and neutralisation as on the M6 path.  oracle/uapic_oracle.c states the same.

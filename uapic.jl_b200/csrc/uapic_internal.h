@@ -113,6 +113,8 @@ cudaError_t launch_unpermute(const LaunchCtx &c, int64_t np, const uint32_t *per
 // ---- loaders / diagnostics --------------------------------------------------------------------------------------
 cudaError_t launch_generate(const LaunchCtx &c, const MeshDev &m, int kind, uint64_t seed, int64_t first, int64_t stride, int64_t np,
                             int64_t np_global, double alpha, double kx, double *x, double *v);
-cudaError_t launch_sum_v(const LaunchCtx &c, int64_t np, const double *v, double *out2);
+size_t sum_v_scratch_bytes();
+cudaError_t launch_sum_v(const LaunchCtx &c, int64_t np, const double *v, double *scratch, double *out2);
+cudaError_t probe_fp64_peak(const LaunchCtx &c, int launches, double *dfma_per_s, double *ms_per_launch);
 
 }  // namespace uapic

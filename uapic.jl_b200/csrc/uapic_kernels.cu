@@ -604,14 +604,44 @@ __global__ void __launch_bounds__(kBlock) k_generate(MeshDev m, int kind, uint64
     }
 }
 
-// sum(v[1,:]), sum(v[2,:])  (bupdate.F90:125) -- fixed-order single-CTA reduction
-__global__ void __launch_bounds__(kMeshBlock) k_sum_v(int64_t np, const double2 *__restrict__ v, double *out2) {
+// sum(v[1,:]), sum(v[2,:])  (bupdate.F90:125) -- two-level reduction in a FIXED order that does not depend on the GPU:
+// kSumParts CTAs each reduce one contiguous slice (per-thread strided partial, then the fixed tree of block_sum), a second
+// single-CTA launch reduces the kSumParts partials the same way.  bupdate prints this number every step, so at 1e8 particles
+// the old single-CTA kernel (1.6 GB through one SM) would have dominated a faithful driver loop.
+constexpr int kSumParts = 1024;
+__global__ void __launch_bounds__(kMeshBlock) k_sum_v_partial(int64_t np, const double2 *__restrict__ v, double2 *__restrict__ part) {
     __shared__ double sh[kMeshBlock];
+    const int64_t per = (np + kSumParts - 1) / kSumParts;
+    const int64_t lo = (int64_t)blockIdx.x * per, hi = lo + per < np ? lo + per : np;
     double a = 0.0, b = 0.0;
-    for (int64_t k = threadIdx.x; k < np; k += blockDim.x) { const double2 vv = v[k]; a += vv.x; b += vv.y; }
+    for (int64_t k = lo + threadIdx.x; k < hi; k += blockDim.x) { const double2 vv = v[k]; a += vv.x; b += vv.y; }
     const double sa = block_sum(a, sh);
     const double sb = block_sum(b, sh);
+    if (threadIdx.x == 0) part[blockIdx.x] = make_double2(sa, sb);
+}
+__global__ void __launch_bounds__(kMeshBlock) k_sum_v_final(const double2 *__restrict__ part, double *out2) {
+    __shared__ double sh[kMeshBlock];
+    const double2 p = threadIdx.x < kSumParts ? part[threadIdx.x] : make_double2(0.0, 0.0);
+    const double sa = block_sum(p.x, sh);
+    const double sb = block_sum(p.y, sh);
     if (threadIdx.x == 0) { out2[0] = sa; out2[1] = sb; }
+}
+
+// fp64 pipe probe: kProbeChains independent DFMA chains per thread, nothing else in the loop (uapic_probe_fp64_peak)
+constexpr int kProbeChains = 8;
+__global__ void __launch_bounds__(256) k_probe_dfma(int iters, double seed, double *sink) {
+    double a[kProbeChains];
+#pragma unroll
+    for (int i = 0; i < kProbeChains; ++i) a[i] = seed + (double)(threadIdx.x + i);
+    const double m = 0.999999999, c = 1e-9 * seed;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < kProbeChains; ++i) a[i] = fma(a[i], m, c);
+    }
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < kProbeChains; ++i) t += a[i];
+    if (t == 12345.678) *sink = t;      // never true: keeps the chains alive
 }
 
 }  // namespace
@@ -752,6 +782,16 @@ cudaError_t launch_poisson(const LaunchCtx &c, const MeshDev &m, const PoissonWo
     const int ty = m.ny >= 512 ? 256 : (m.ny >= 128 ? 128 : 64);
     const size_t shx = sizeof(double2) * (size_t)m.nx * 3;
     const size_t shy = sizeof(double2) * (size_t)m.ny * 5;
+    // above the 48 KB default (ny = 1024 needs 80 KB, nx = 1024 exactly 48 KB) the kernels must opt in
+    if (shx > 48 * 1024 - 256) {
+        cudaError_t e = cudaFuncSetAttribute(k_poisson_rows_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shx);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_poisson_rows_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shx);
+        if (e != cudaSuccess) return e;
+    }
+    if (shy > 48 * 1024 - 256) {
+        cudaError_t e = cudaFuncSetAttribute(k_poisson_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shy);
+        if (e != cudaSuccess) return e;
+    }
     k_poisson_rows_fwd<<<m.ny, tx, shx, c.stream>>>(m, rho, w.rk);
     k_poisson_cols<<<m.nx / 2 + 1, ty, shy, c.stream>>>(m, w.rk, w.ek);
     k_poisson_rows_bwd<<<dim3(m.ny, 2), tx, shx, c.stream>>>(m, w.ek, emesh);
@@ -787,9 +827,36 @@ cudaError_t launch_extend_emesh_tiled(const LaunchCtx &c, const MeshDev &m, cons
     return cudaGetLastError();
 }
 
-cudaError_t launch_sum_v(const LaunchCtx &c, int64_t np, const double *v, double *out2) {
-    k_sum_v<<<1, kMeshBlock, 0, c.stream>>>(np, reinterpret_cast<const double2 *>(v), out2);
-    count(c);
+size_t sum_v_scratch_bytes() { return sizeof(double2) * (size_t)kSumParts; }
+
+cudaError_t launch_sum_v(const LaunchCtx &c, int64_t np, const double *v, double *scratch, double *out2) {
+    k_sum_v_partial<<<kSumParts, kMeshBlock, 0, c.stream>>>(np, reinterpret_cast<const double2 *>(v), reinterpret_cast<double2 *>(scratch));
+    k_sum_v_final<<<1, kMeshBlock, 0, c.stream>>>(reinterpret_cast<const double2 *>(scratch), out2);
+    count(c, 2);
+    return cudaGetLastError();
+}
+
+// DFMA issue rate of the whole chip: `launches` back-to-back launches of a pure DFMA loop, timed with CUDA events
+cudaError_t probe_fp64_peak(const LaunchCtx &c, int launches, double *dfma_per_s, double *ms_per_launch) {
+    double *sink = nullptr;
+    cudaError_t e = cudaMalloc(&sink, 8);
+    if (e != cudaSuccess) return e;
+    const int iters = 1 << 16, grid = c.sm_count * 8, block = 256;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    k_probe_dfma<<<grid, block, 0, c.stream>>>(iters, 1.0, sink);          // warm-up
+    cudaEventRecord(e0, c.stream);
+    for (int l = 0; l < launches; ++l) k_probe_dfma<<<grid, block, 0, c.stream>>>(iters, 1.0 + l, sink);
+    cudaEventRecord(e1, c.stream);
+    e = cudaEventSynchronize(e1);
+    float ms = 0.f;
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(sink);
+    if (e != cudaSuccess) return e;
+    const double n = (double)grid * block * kProbeChains * (double)iters * launches;
+    if (dfma_per_s) *dfma_per_s = n / (ms * 1e-3);
+    if (ms_per_launch) *ms_per_launch = ms / launches;
     return cudaGetLastError();
 }
 

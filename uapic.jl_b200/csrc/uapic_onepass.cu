@@ -75,6 +75,14 @@ namespace {
 #ifndef UAPIC_OP_BLOCK_B
 #define UAPIC_OP_BLOCK_B 256
 #endif
+#ifndef UAPIC_OP_PAIR_LOADS
+#define UAPIC_OP_PAIR_LOADS 1     // M6 gathers fetch two taps per 256-bit load (gather_tiled_pairs, uapic_fast.cuh); 0: 36 LDG.128
+#endif
+#if UAPIC_OP_PAIR_LOADS
+#define OP_GATHER_M6 gather_tiled_pairs
+#else
+#define OP_GATHER_M6 gather_tiled
+#endif
 constexpr int kOpBlockA = UAPIC_OP_BLOCK_A, kOpBlockB = UAPIC_OP_BLOCK_B;      // threads per CTA of the two kernels
 constexpr int kGatherUnroll = UAPIC_OP_GATHER_UNROLL;
 #ifndef UAPIC_OP_TWIDDLE_TABLE
@@ -427,7 +435,7 @@ __global__ void __launch_bounds__(kOpBlockA, UAPIC_OP_MINB_A) k_onepass_a(OpDev 
             const double2 pos = gx[row * kRow + col];
             double xw, yw, e1, e2;
             const Cell cell = cell_fast(P.m, D.f, pos.x, pos.y, P.wrap, xw, yw);
-            if (SCHEME == kSchemeCic) gather_cic_tiled(P.m, P.ehalo, cell, e1, e2); else gather_tiled(P.m, P.ehalo, cell, e1, e2);
+            if (SCHEME == kSchemeCic) gather_cic_tiled(P.m, P.ehalo, cell, e1, e2); else OP_GATHER_M6(P.m, P.ehalo, cell, e1, e2);
             gx[row * kRow + col] = make_double2(e1, e2);
             sps[row * kRow + col] = sin(pos.x) * sin(pos.y);
         }
@@ -631,6 +639,10 @@ __global__ void __launch_bounds__(kOpBlockA, UAPIC_OP_MINB_A) k_onepass_a(OpDev 
         }
 #define rho_p_sel rp
 #define rho_c_sel rc
+#ifndef UAPIC_OP_NO_DEPOSIT     // measurement only (profiles/README.md): phase A without its 72 deposit atomics per particle
+#define UAPIC_OP_NO_DEPOSIT 0
+#endif
+#if !UAPIC_OP_NO_DEPOSIT
         const Cell cp = cell_fast(P.m, D.f, posp1, posp2, P.wrap, xw, yw);
         if (SCHEME == kSchemeCic) {
             if (valid) {
@@ -649,6 +661,11 @@ __global__ void __launch_bounds__(kOpBlockA, UAPIC_OP_MINB_A) k_onepass_a(OpDev 
         } else {
             deposit_split<G>(P.m, rho_c_sel, cc, P.weight, g, valid);          // (corrector)
         }
+#else
+        const Cell cp = cell_fast(P.m, D.f, posp1, posp2, P.wrap, xw, yw);
+        const Cell cc = cell_fast(P.m, D.f, posc1, posc2, P.wrap, xw, yw);
+        if (cp.i + cc.i == -12345) rho_add(rp, 0, xw);      // keeps the position sums alive
+#endif
         if (valid && g == 0) {
             if (P.out_perm) P.x_out[P.out_perm[ip]] = make_double2(xw, yw);
             else P.x[ip] = make_double2(xw, yw);                             // compute_rho_m6.F90:86-87
@@ -745,7 +762,7 @@ __global__ void __launch_bounds__(kOpBlockB, UAPIC_OP_MINB_B) k_onepass_b(OpDev 
             // ---- gather E_pred at the predicted samples (interpolation_m6.F90:83-189) ----
             double xw, yw, e1, e2;
             const Cell cell = cell_fast(P.m, D.f, xs.x, xs.y, P.wrap, xw, yw);
-            if (SCHEME == kSchemeCic) gather_cic_tiled(P.m, P.ehalo, cell, e1, e2); else gather_tiled(P.m, P.ehalo, cell, e1, e2);
+            if (SCHEME == kSchemeCic) gather_cic_tiled(P.m, P.ehalo, cell, e1, e2); else OP_GATHER_M6(P.m, P.ehalo, cell, e1, e2);
             cd gy1, gy2;
             fy_time(csn.x, csn.y, rb, iv, mk(ya.x, ya.y), mk(yb.x, yb.y), e1, e2, gy1, gy2);     // :177-183
             // terms of Re sum_n gy(tau_n) W_n: summed over n after the loop (one pass through shared memory instead of a

@@ -31,21 +31,47 @@ class _CudaView:
                                          "strides": None}
 
 
+def nccl_unique_id() -> bytes:
+    """128-byte NCCL unique id (uapic_nccl_unique_id): create on one rank, hand to the others"""
+    import ctypes as C
+    from ._lib import check, lib
+    buf = C.create_string_buffer(128)
+    check(lib().uapic_nccl_unique_id(buf))
+    return buf.raw
+
+
+def attach_nccl(session, group=None):
+    """the native multi-GPU path: the library owns an NCCL communicator and reduces by itself (no Python in the step).
+    torch.distributed (any backend) is used ONCE, to hand rank 0's unique id to the other ranks."""
+    import torch.distributed as dist
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    box = [nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    session.init_nccl(box[0], world, rank)
+
+
 def attach_torch_allreduce(session, group=None):
-    """make `session` sum its raw rho mesh over the ranks of `group` with torch.distributed (NCCL).
-    The session must run on torch's current CUDA stream so the collective is ordered with the kernels."""
+    """make `session` sum its raw rho mesh over the ranks of `group` with torch.distributed (NCCL), through the C ABI's
+    callback hook.  The collective is issued on the stream handle the library passes (the session's stream), whatever
+    torch's current stream is."""
     import torch
     import torch.distributed as dist
 
     cache = {}
+    device = torch.device("cuda", torch.cuda.current_device())
 
     def fn(ptr, count, dtype, stream):
         key = (ptr, count, dtype)
         t = cache.get(key)
         if t is None:
-            t = torch.as_tensor(_CudaView(ptr, count, "<f8" if dtype == 0 else "<i8"), device=torch.device("cuda", torch.cuda.current_device()))
+            t = torch.as_tensor(_CudaView(ptr, count, "<f8" if dtype == 0 else "<i8"), device=device)
             cache[key] = t
-        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        if stream and stream != torch.cuda.current_stream(device).cuda_stream:
+            with torch.cuda.stream(torch.cuda.ExternalStream(stream, device=device)):
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        else:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
         return 0
 
     session.set_allreduce(fn)

@@ -181,7 +181,15 @@ class Session:
         check(lib().uapic_session_device_bytes(self._h, C.byref(n)))
         return n.value
 
-    # ---- multi-GPU hook ----------------------------------------------------------------------------------
+    # ---- multi-GPU ---------------------------------------------------------------------------------------
+    def init_nccl(self, unique_id: bytes, nranks: int, rank: int):
+        """collective: create this session's NCCL communicator inside the library (uapic_session_init_nccl); from then on
+        the library itself sums the raw rho meshes with ncclAllReduce on the session's stream"""
+        if len(unique_id) != 128:
+            raise ValueError("the NCCL unique id is 128 bytes")
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        check(lib().uapic_session_init_nccl(self._h, buf, C.c_int(nranks), C.c_int(rank)))
+
     def set_allreduce(self, fn):
         """fn(buf_ptr: int, count: int, dtype: int, stream: int) -> int ; dtype 0 = float64, 1 = int64"""
         if fn is None:
