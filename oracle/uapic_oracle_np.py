@@ -14,7 +14,36 @@ use ``order='F'`` buffers when exchanging memory with the C oracle / the CUDA li
 """
 from __future__ import annotations
 
+import contextlib
+
 import numpy as np
+
+# Working precision.  float64 is the twin of the reference.  "longdouble" (x87 80-bit, 64-bit mantissa, eps 1.1e-19) turns
+# this file into the EXTENDED-PRECISION REFEREE of tests/golden/make_referee.py: the same formulas evaluated from the same
+# double inputs with 2000x smaller rounding, which tells which of two double implementations (C oracle, CUDA kernels) is
+# closer to the exact result when they disagree -- at small eps every rounding of b(x) is multiplied by t/eps in the phase
+# l*t/eps (ua_steps.F90:64,224,258,297).  numpy's pocketfft, sin/cos/exp and mod all run in long double for these dtypes.
+REAL = np.float64
+CPLX = np.complex128
+
+
+def set_precision(name: str):
+    global REAL, CPLX
+    REAL, CPLX = {"double": (np.float64, np.complex128), "longdouble": (np.longdouble, np.clongdouble)}[name]
+
+
+@contextlib.contextmanager
+def precision(name: str):
+    old = "double" if REAL is np.float64 else "longdouble"
+    set_precision(name)
+    try:
+        yield
+    finally:
+        set_precision(old)
+
+
+def _pi():
+    return np.pi if REAL is np.float64 else REAL(4) * np.arctan(REAL(1))
 
 
 # ----------------------------------------------------------------------------------------------
@@ -22,17 +51,17 @@ import numpy as np
 # ----------------------------------------------------------------------------------------------
 class Mesh:
     def __init__(self, xmin, xmax, nx, ymin, ymax, ny):
-        self.xmin, self.xmax, self.nx = float(xmin), float(xmax), int(nx)
-        self.ymin, self.ymax, self.ny = float(ymin), float(ymax), int(ny)
+        self.xmin, self.xmax, self.nx = REAL(xmin), REAL(xmax), int(nx)
+        self.ymin, self.ymax, self.ny = REAL(ymin), REAL(ymax), int(ny)
         self.dx = (self.xmax - self.xmin) / self.nx      # meshfields.jl:16
         self.dy = (self.ymax - self.ymin) / self.ny      # meshfields.jl:17
 
 
 def ua_tables(ntau):
     """tau[i] = i*2pi/ntau ; ltau = [0:ntau/2-1 ; -ntau/2:-1]      src/ua_type.jl:19-25"""
-    dtau = 2 * np.pi / ntau
-    ltau = np.concatenate([np.arange(0, ntau // 2), np.arange(-ntau // 2, 0)]).astype(np.float64)
-    tau = np.array([i * dtau for i in range(ntau)], dtype=np.float64)
+    dtau = 2 * _pi() / ntau
+    ltau = np.concatenate([np.arange(0, ntau // 2), np.arange(-ntau // 2, 0)]).astype(REAL)
+    tau = np.array([i * dtau for i in range(ntau)], dtype=REAL)
     return tau, ltau
 
 
@@ -40,7 +69,7 @@ def ua_tables(ntau):
 # M6                                                        src/compute_rho.jl:10-25
 # ----------------------------------------------------------------------------------------------
 def f_m6(q):
-    q = np.asarray(q, dtype=np.float64)
+    q = np.asarray(q, dtype=REAL)
     a = (3 - q) ** 5
     b = (2 - q) ** 5
     c = (1 - q) ** 5
@@ -83,8 +112,8 @@ def _cell_weights(mesh, x, y):
 
 def _gather(mesh, e, ix, jy, cx, cy):
     """49-term sum, same order as src/interpolation.jl:66-116 (x offset outer, y offset inner)"""
-    s1 = np.zeros(ix.shape[1:], dtype=np.float64)
-    s2 = np.zeros(ix.shape[1:], dtype=np.float64)
+    s1 = np.zeros(ix.shape[1:], dtype=REAL)
+    s2 = np.zeros(ix.shape[1:], dtype=REAL)
     for a in range(7):
         for b in range(7):
             w = cx[a] * cy[b]
@@ -147,10 +176,10 @@ def compute_rho_m6_tau(mesh, rho, x, w, xt, t, eps):
 class Poisson:
     def __init__(self, mesh):
         nx, ny = mesh.nx, mesh.ny
-        kx0 = 2 * np.pi / (mesh.xmax - mesh.xmin)
-        ky0 = 2 * np.pi / (mesh.ymax - mesh.ymin)
-        kx = np.zeros((nx // 2 + 1, ny))
-        ky = np.zeros((nx // 2 + 1, ny))
+        kx0 = 2 * _pi() / (mesh.xmax - mesh.xmin)
+        ky0 = 2 * _pi() / (mesh.ymax - mesh.ymin)
+        kx = np.zeros((nx // 2 + 1, ny), dtype=REAL)
+        ky = np.zeros((nx // 2 + 1, ny), dtype=REAL)
         for ik in range(nx // 2 + 1):
             kx[ik, :] = ik * kx0
         for jk in range(ny // 2):
@@ -189,8 +218,8 @@ def preparation(ntau, eps, dt, x, v, ep):
     b = 1 + 0.5 * np.sin(x1) * np.sin(x2)                                        # :20
     t = dt * b                                                                   # :21
     npart = x.shape[1]
-    pl = np.zeros((ntau, npart), dtype=np.complex128)
-    ql = np.zeros((ntau, npart), dtype=np.complex128)
+    pl = np.zeros((ntau, npart), dtype=CPLX)
+    ql = np.zeros((ntau, npart), dtype=CPLX)
     pl[0] = t                                                                    # :23
     ql[0] = t ** 2 / 2                                                           # :24
     l = ltau[1:, None]
@@ -205,18 +234,18 @@ def preparation(ntau, eps, dt, x, v, ep):
     h2 = eps * (st * vyb + ct * vxb)                                             # :44
     xt1 = x1 + h1 + eps * vyb                                                    # :46
     xt2 = x2 + h2 - eps * vxb                                                    # :47
-    xt = np.zeros((ntau, 2, npart), dtype=np.complex128)
+    xt = np.zeros((ntau, 2, npart), dtype=CPLX)
     xt[:, 0, :], xt[:, 1, :] = xt1, xt2
     interv = (1 + 0.5 * np.sin(xt1) * np.sin(xt2) - b) / eps                     # :52
     exb = ((ct * vy - st * vx) * interv + ex) / b                                # :54
     eyb = ((-ct * vx - st * vy) * interv + ey) / b                               # :55
-    r = np.zeros((ntau, 2, npart), dtype=np.complex128)
+    r = np.zeros((ntau, 2, npart), dtype=CPLX)
     r[:, 0, :] = ct * exb - st * eyb                                             # :57
     r[:, 1, :] = st * exb + ct * eyb                                             # :58
     rt = np.fft.fft(r, axis=0)                                                   # :62
     rt[1:] = -1j * rt[1:] / ltau[1:, None, None]                                 # :64-67
     r = np.fft.ifft(rt, axis=0)                                                  # :69
-    yt = np.zeros((ntau, 2, npart), dtype=np.complex128)
+    yt = np.zeros((ntau, 2, npart), dtype=CPLX)
     yt[:, 0, :] = vx + (r[:, 0, :] - r[0, 0, :]) * eps                           # :72
     yt[:, 1, :] = vy + (r[:, 1, :] - r[0, 1, :]) * eps                           # :73
     return b, t, pl, ql, xt, yt
@@ -275,11 +304,11 @@ def compute_v(eps, t, yt_fourier):
 # ----------------------------------------------------------------------------------------------
 def run_bupdate(mesh, ntau, eps, dt, nstep, x, v, w):
     """returns (x, v, energy[1+2*nstep], sumv[nstep,2]); x, v are (2,np) arrays, modified copies returned"""
-    x = np.array(x, dtype=np.float64, copy=True)
-    v = np.array(v, dtype=np.float64, copy=True)
+    x = np.array(x, dtype=REAL, copy=True)
+    v = np.array(v, dtype=REAL, copy=True)
     nx, ny = mesh.nx, mesh.ny
-    rho = np.zeros((nx + 1, ny + 1))
-    e = np.zeros((2, nx + 1, ny + 1))
+    rho = np.zeros((nx + 1, ny + 1), dtype=REAL)
+    e = np.zeros((2, nx + 1, ny + 1), dtype=REAL)
     ep = np.zeros_like(x)
     poisson = Poisson(mesh)
     energy = []
@@ -287,7 +316,7 @@ def run_bupdate(mesh, ntau, eps, dt, nstep, x, v, w):
     compute_rho_m6(mesh, rho, x, w)                                              # :63
     energy.append(poisson(rho, e))                                               # :65
     interpol_eb_m6(mesh, e, x, ep)                                               # :67
-    et = np.zeros((ntau, 2, x.shape[1]))
+    et = np.zeros((ntau, 2, x.shape[1]), dtype=REAL)
     for _ in range(nstep):
         b, t, pl, ql, xt, yt = preparation(ntau, eps, dt, x, v, ep)              # :71
         interpol_eb_m6_tau(mesh, e, xt, et)                                      # :73

@@ -492,6 +492,8 @@ struct uapic_session {
     int64_t np_global = 0;
     DevBuf x, v, ep, store, tb, raw, rho, emesh, ehalo, rk, ek, energy, sumv;
     DevBuf rec, emesh_p, ehalo_p;     // one-pass modes: per-particle record, predictor field
+    DevBuf rho_p, rk2, ek2, solve_scratch;   // second work set + scratch of the batched one-launch field solve (k_field_solve)
+    bool split_solve = false;          // $UAPIC_SPLIT_SOLVE=1: the six separate kernels per solve (A/B measurement, stage-API kernels)
     RhoAcc acc{};
     RhoAcc acc_c{};                    // one-pass modes: corrector deposit mesh (second half of raw)
     bool onepass = false;
@@ -549,26 +551,9 @@ int session_clear_raw(uapic_session *s) {
     return UAPIC_OK;
 }
 
-// sum the raw deposit mesh(es) over the ranks (the only exchange of the scheme)
-int session_reduce(uapic_session *s, int nmesh) {
-    if (s->onepass && nmesh == 2) CU(launch_fold_raw(s->lc, s->acc, 2 * (int64_t)s->m.ld * (s->m.ny + 1), UAPIC_RAW_COPIES));
-    if (s->nccl_comm) {
-        // in-library collective on the session's stream: no host callback, capturable in a CUDA graph
-        NcclApi *a = nccl_api();
-        const size_t n = (size_t)s->m.ld * (s->m.ny + 1) * nmesh;
-        const int rc = a->AllReduce(s->raw.p, s->raw.p, n, s->acc.i64 ? 4 /* ncclInt64 */ : 8 /* ncclFloat64 */, 0 /* ncclSum */,
-                                    s->nccl_comm, s->lc.stream);
-        if (rc) return fail(UAPIC_ECUDA, "ncclAllReduce failed: %s", a->GetErrorString(rc));
-    } else if (s->reduce) {
-        const int64_t n = (int64_t)s->m.ld * (s->m.ny + 1) * nmesh;
-        int rc = s->reduce(s->reduce_ctx, s->raw.p, n, s->acc.i64 ? 1 : 0, (void *)s->lc.stream);
-        if (rc) return fail(UAPIC_ECUDA, "allreduce callback failed with code %d", rc);
-    }
-    return UAPIC_OK;
-}
-
 // summed raw deposits -> neutralised rho -> E (+ halo copy), energy appended      compute_rho_m6.F90:191-200 + poisson_2d.f90:85-111
-int session_solve(uapic_session *s, const RhoAcc &acc, DevBuf &emesh, DevBuf &ehalo) {
+// (the six separate kernels; kept for $UAPIC_SPLIT_SOLVE=1 and as the cross-check of k_field_solve)
+int session_solve_split(uapic_session *s, const RhoAcc &acc, DevBuf &emesh, DevBuf &ehalo) {
     CU(launch_rho_epilogue(s->lc, s->m, acc, s->rho.as<double>(), nullptr));
     if (s->n_energy >= s->cap_energy) return fail(UAPIC_ESTATE, "energy history full (%lld entries): session_reserve_energy was not called", (long long)s->cap_energy);
     PoissonWork pw{s->rk.as<double2>(), s->ek.as<double2>()};
@@ -579,10 +564,57 @@ int session_solve(uapic_session *s, const RhoAcc &acc, DevBuf &emesh, DevBuf &eh
     return UAPIC_OK;
 }
 
-int session_field_solve(uapic_session *s) {
-    TRY(session_reduce(s, 1));
-    return session_solve(s, s->acc, s->emesh, s->ehalo);
+// the field barrier of a step: sum the raw deposit mesh(es) over the ranks (the only exchange of the scheme), then ONE
+// cooperative launch takes all `nmesh` meshes from raw deposits to E, halo copy and energy (k_field_solve).
+// nmesh = 2 (one-pass kernels): predictor mesh -> emesh_p / ehalo_p, corrector mesh -> emesh / ehalo, energies in this order.
+int session_field_barrier(uapic_session *s, int nmesh) {
+    if (s->n_energy + nmesh > s->cap_energy) return fail(UAPIC_ESTATE, "energy history full (%lld entries): session_reserve_energy was not called", (long long)s->cap_energy);
+    const size_t nrho = (size_t)s->m.ld * (s->m.ny + 1);
+    const bool copies = s->onepass && nmesh == 2;
+    const bool exchange = s->nccl_comm || s->reduce;
+    int fold_in_kernel = 1;
+    if (copies) {
+        if (exchange || s->split_solve) CU(launch_fold_raw(s->lc, s->acc, 2 * (int64_t)nrho, UAPIC_RAW_COPIES));
+        else fold_in_kernel = UAPIC_RAW_COPIES;        // single GPU: the solve kernel folds the copies while it scales them
+    }
+    if (s->nccl_comm) {
+        // in-library collective on the session's stream: no host callback, capturable in a CUDA graph
+        NcclApi *a = nccl_api();
+        const int rc = a->AllReduce(s->raw.p, s->raw.p, nrho * nmesh, s->acc.i64 ? 4 /* ncclInt64 */ : 8 /* ncclFloat64 */, 0 /* ncclSum */,
+                                    s->nccl_comm, s->lc.stream);
+        if (rc) return fail(UAPIC_ECUDA, "ncclAllReduce failed: %s", a->GetErrorString(rc));
+    } else if (s->reduce) {
+        int rc = s->reduce(s->reduce_ctx, s->raw.p, (int64_t)nrho * nmesh, s->acc.i64 ? 1 : 0, (void *)s->lc.stream);
+        if (rc) return fail(UAPIC_ECUDA, "allreduce callback failed with code %d", rc);
+    }
+    if (s->split_solve) {
+        if (nmesh == 2) {
+            TRY(session_solve_split(s, s->acc, s->emesh_p, s->ehalo_p));
+            return session_solve_split(s, s->acc_c, s->emesh, s->ehalo);
+        }
+        return session_solve_split(s, s->acc, s->emesh, s->ehalo);
+    }
+    SolveBatch B{};
+    B.nb = nmesh;
+    B.partial = s->solve_scratch.as<double>();
+    B.halo_tiled = s->onepass ? 1 : 0;
+    B.fold_copies = fold_in_kernel;
+    B.fold_stride = 2 * nrho;
+    if (nmesh == 2) {
+        B.acc[0] = s->acc;   B.rho[0] = s->rho_p.as<double>(); B.emesh[0] = s->emesh_p.as<double2>(); B.ehalo[0] = s->ehalo_p.as<double2>();
+        B.rk[0] = s->rk2.as<double2>(); B.ek[0] = s->ek2.as<double2>(); B.energy[0] = s->energy.as<double>() + s->n_energy;
+        B.acc[1] = s->acc_c; B.rho[1] = s->rho.as<double>();   B.emesh[1] = s->emesh.as<double2>();   B.ehalo[1] = s->ehalo.as<double2>();
+        B.rk[1] = s->rk.as<double2>();  B.ek[1] = s->ek.as<double2>();  B.energy[1] = s->energy.as<double>() + s->n_energy + 1;
+    } else {
+        B.acc[0] = s->acc;   B.rho[0] = s->rho.as<double>();   B.emesh[0] = s->emesh.as<double2>();   B.ehalo[0] = s->ehalo.as<double2>();
+        B.rk[0] = s->rk.as<double2>();  B.ek[0] = s->ek.as<double2>();  B.energy[0] = s->energy.as<double>() + s->n_energy;
+    }
+    CU(launch_field_solve(s->lc, s->m, B));
+    s->n_energy += nmesh;
+    return UAPIC_OK;
 }
+
+int session_field_solve(uapic_session *s) { return session_field_barrier(s, 1); }
 
 OnepassParams session_onepass_params(uapic_session *s) {
     OnepassParams p;
@@ -741,6 +773,13 @@ int uapic_session_create(const uapic_config_t *cfg, uapic_session_t **out) {
     if (!rc) rc = session_alloc(s, s->ehalo, 16 * (onepass ? ehalo_tiled_nodes(s->m) : ehalo_nodes(s->m)));
     if (!rc) rc = session_alloc(s, s->rk, 16 * nk);
     if (!rc) rc = session_alloc(s, s->ek, 32 * nk);
+    if (!rc) rc = session_alloc(s, s->solve_scratch, field_solve_scratch_bytes());
+    if (onepass) {
+        if (!rc) rc = session_alloc(s, s->rho_p, 8 * nrho);
+        if (!rc) rc = session_alloc(s, s->rk2, 16 * nk);
+        if (!rc) rc = session_alloc(s, s->ek2, 32 * nk);
+    }
+    { const char *e = getenv("UAPIC_SPLIT_SOLVE"); s->split_solve = e && *e == '1'; }
     if (!rc) rc = session_alloc(s, s->energy, 8 * (size_t)s->cap_energy);
     if (!rc) rc = session_alloc(s, s->sumv, 16 + sum_v_scratch_bytes());
     if (rc) { delete s; return rc; }
@@ -959,9 +998,7 @@ int uapic_session_step(uapic_session_t *s, int nsteps) {
             op.ehalo = s->ehalo.as<double2>();
             CU(launch_onepass_a(s->lc, op));                               // bupdate.F90:97-106, :112-117 (x part)
             if (s->timing) CU(cudaEventRecord(e4[1], s->lc.stream));
-            TRY(session_reduce(s, 2));
-            TRY(session_solve(s, s->acc, s->emesh_p, s->ehalo_p));         // :108  predictor field
-            TRY(session_solve(s, s->acc_c, s->emesh, s->ehalo));           // :119  field of the next step
+            TRY(session_field_barrier(s, 2));      // :108 predictor field and :119 field of the next step, one exchange + one launch
             if (s->timing) CU(cudaEventRecord(e4[2], s->lc.stream));
             op.ehalo = s->ehalo_p.as<double2>();
             CU(launch_onepass_b(s->lc, op));                               // :110-115 (y part), :123
@@ -1055,9 +1092,7 @@ int uapic_session_step_host(uapic_session_t *s, const double *x_in, const double
         CU(launch_onepass_a(s->lc, pc));
     }
     // ---- the one field barrier ----
-    TRY(session_reduce(s, 2));
-    TRY(session_solve(s, s->acc, s->emesh_p, s->ehalo_p));
-    TRY(session_solve(s, s->acc_c, s->emesh, s->ehalo));
+    TRY(session_field_barrier(s, 2));
     // ---- phase B (+ undo the reordering) || downloads, chunk by chunk ----
     for (int c = 0; c < kChunks; ++c) {
         const int64_t lo = (int64_t)c * per, n = std::min(per, np - lo);

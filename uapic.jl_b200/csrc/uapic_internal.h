@@ -50,6 +50,23 @@ struct PoissonWork { double2 *rk; double2 *ek; };   // rk: (nx/2+1)*ny ; ek: 2*(
 cudaError_t launch_poisson(const LaunchCtx &c, const MeshDev &m, const PoissonWork &w, const double *rho, double *emesh,
                            double *energy);
 bool poisson_size_supported(int n);
+// the session's field solve in one cooperative launch for nb <= 2 meshes at once (k_field_solve, uapic_kernels.cu):
+// fold of `fold_copies` raw copies (copy k of mesh b at acc[b] + k*fold_stride) -> rho epilogue -> Poisson -> energy -> halo copy
+struct SolveBatch {
+    int nb;
+    RhoAcc acc[2];         // summed raw deposits (fp64 or fixed point)
+    double *rho[2];        // (nx+1)*(ny+1) out
+    double2 *emesh[2];     // (nx+1)*(ny+1) out
+    double2 *ehalo[2];     // halo copy out (may be null)
+    double *energy[2];     // 1 double out (may be null)
+    double2 *rk[2], *ek[2];   // Poisson work: (nx/2+1)*ny and 2*(nx/2+1)*ny
+    double *partial;       // field_solve_scratch_bytes()
+    int halo_tiled;        // 1: 2 x 4-node tiled halo (one-pass kernels); 0: linear halo (two-barrier kernels)
+    int fold_copies;       // >= 1
+    size_t fold_stride;    // elements between copies
+};
+size_t field_solve_scratch_bytes();
+cudaError_t launch_field_solve(const LaunchCtx &c, const MeshDev &m, const SolveBatch &B);
 // periodic halo copy of the E mesh for the fused gathers: node (i,j), i in [-2,nx+3], j in [-2,ny+3], holds E(i mod nx, j mod ny)
 inline size_t ehalo_nodes(const MeshDev &m) { return (size_t)(m.nx + 6) * (size_t)(m.ny + 6); }
 cudaError_t launch_extend_emesh(const LaunchCtx &c, const MeshDev &m, const double *emesh, double2 *ehalo);

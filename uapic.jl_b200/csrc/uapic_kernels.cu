@@ -6,6 +6,8 @@
 //  4. loaders / diagnostics
 //
 // Reference citations are to /root/reference (fortran/*.F90, src/*.jl); see DESIGN.md for the mapping.
+#include <cooperative_groups.h>
+
 #include "uapic_internal.h"
 
 namespace uapic {
@@ -537,6 +539,240 @@ __global__ void __launch_bounds__(kMeshBlock) k_energy(MeshDev m, const double2 
     if (threadIdx.x == 0) *energy = tot * m.dx * m.dy;
 }
 
+
+// =================================================================================================
+// 2b. the whole field solve of the session path in ONE cooperative launch, for up to two meshes at once
+// =================================================================================================
+// raw deposits (already summed over the ranks) -> fold of the CTA-private copies -> /(dx dy), mean, ghosts
+// (compute_rho_m6.F90:191-200) -> r2c along x, FFT along y, -i k/k^2, two inverse FFTs, c2r along x (poisson_2d.f90:85-111)
+// -> ghost copies, 1/(nx ny) -> electric energy (src/poisson.jl:80-81) -> tiled / linear halo copy for the gathers.
+// The separate kernels above did this in 6 launches per mesh, two of them single-CTA (9.7 + 5.2 us); a one-pass step needs
+// two solves back to back, i.e. 12 launches and ~150 us of fixed cost -- 7 % of a BASELINE config-2 step.  Here the phases
+// are separated by grid.sync() and both meshes of a step go through together.  All sums run over kSolveParts FIXED chunks in
+// a fixed order, so the result does not depend on the grid size (same bits on any GPU, any SM count).
+constexpr int kSolveParts = 64;
+constexpr int kSolveBlock = 256;
+
+DEVINL double block_sum_256(double v, double *sh) {      // fixed tree over kSolveBlock threads, valid on every thread
+    const int tid = threadIdx.x;
+    __syncthreads();
+    sh[tid] = v;
+    __syncthreads();
+    for (int s = kSolveBlock / 2; s > 0; s >>= 1) {
+        if (tid < s) sh[tid] += sh[tid + s];
+        __syncthreads();
+    }
+    return sh[0];
+}
+DEVINL long long block_isum_256(long long v, long long *sh) {
+    const int tid = threadIdx.x;
+    __syncthreads();
+    sh[tid] = v;
+    __syncthreads();
+    for (int s = kSolveBlock / 2; s > 0; s >>= 1) {
+        if (tid < s) sh[tid] += sh[tid + s];
+        __syncthreads();
+    }
+    return sh[0];
+}
+
+__global__ void __launch_bounds__(kSolveBlock) k_field_solve(MeshDev m, SolveBatch B) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ double2 smem_raw[];
+    __shared__ double shd[kSolveBlock];
+    long long *shi = reinterpret_cast<long long *>(shd);
+    cd *buf = reinterpret_cast<cd *>(smem_raw);
+    const int nx = m.nx, ny = m.ny, ld = m.ld, nh = nx / 2 + 1, nb = B.nb;
+    const double dxdy = m.dx * m.dy;
+    const int ncell = nx * ny, per = (ncell + kSolveParts - 1) / kSolveParts;
+
+    // ---- phase 0: fold the copies, scale, partial sums over fixed chunks ----
+    for (int task = blockIdx.x; task < nb * kSolveParts; task += gridDim.x) {
+        const int b = task / kSolveParts, c = task - b * kSolveParts;
+        const RhoAcc acc = B.acc[b];
+        const double inv_scale = acc.i64 ? 1.0 / acc.scale : 1.0;
+        const int lo = c * per, hi = min(lo + per, ncell);
+        double part = 0.0;
+        long long ipart = 0;
+        for (int idx = lo + threadIdx.x; idx < hi; idx += kSolveBlock) {
+            const int j = idx / nx, i = idx - j * nx, q = i + ld * j;
+            double raw;
+            if (acc.i64) {
+                unsigned long long t = acc.i64[q];
+                for (int k = 1; k < B.fold_copies; ++k) t += acc.i64[(size_t)k * B.fold_stride + q];
+                ipart += (long long)t;
+                raw = (double)(long long)t * inv_scale;
+            } else {
+                double t = acc.f64[q];
+                for (int k = 1; k < B.fold_copies; ++k) t += acc.f64[(size_t)k * B.fold_stride + q];
+                raw = t;
+            }
+            const double val = raw / dxdy;
+            B.rho[b][q] = val;
+            part += val;
+        }
+        if (acc.i64) {
+            const long long tot = block_isum_256(ipart, shi);
+            if (threadIdx.x == 0) reinterpret_cast<long long *>(B.partial)[task] = tot;
+        } else {
+            const double tot = block_sum_256(part, shd);
+            if (threadIdx.x == 0) B.partial[task] = tot;
+        }
+    }
+    grid.sync();
+
+    // ---- phase 1: subtract the mean, ghosts of rho, r2c along x ----
+    {
+        cd *a = buf, *tmp = a + nx, *tw = tmp + nx;
+        line_twiddles(tw, nx);
+        double sub[2] = {0.0, 0.0};
+        for (int b = 0; b < nb; ++b) {
+            double total;
+            if (B.acc[b].i64) {
+                long long t = 0;
+                for (int c = 0; c < kSolveParts; ++c) t += reinterpret_cast<const long long *>(B.partial)[b * kSolveParts + c];
+                total = (double)t / B.acc[b].scale;                // sum(rho)*dx*dy == sum(raw) exactly in fixed point
+            } else {
+                double t = 0.0;
+                for (int c = 0; c < kSolveParts; ++c) t += B.partial[b * kSolveParts + c];
+                total = t * m.dx * m.dy;
+            }
+            sub[b] = total / m.dimx / m.dimy;
+        }
+        for (int task = blockIdx.x; task < nb * ny; task += gridDim.x) {
+            const int b = task / ny, j = task - b * ny;
+            double *rho = B.rho[b];
+            __syncthreads();
+            for (int i = threadIdx.x; i < nx; i += kSolveBlock) {
+                const double val = rho[i + ld * j] - sub[b];
+                rho[i + ld * j] = val;
+                if (j == 0) rho[i + ld * ny] = val;                 // ghost row
+                if (i == 0) { rho[nx + ld * j] = val; if (j == 0) rho[nx + ld * ny] = val; }   // ghost column, corner
+                a[i] = mk(val, 0.0);
+            }
+            line_fft(a, tmp, tw, nx, -1);
+            for (int i = threadIdx.x; i < nh; i += kSolveBlock) B.rk[b][i + (size_t)nh * j] = make_double2(a[i].re, a[i].im);
+        }
+    }
+    grid.sync();
+
+    // ---- phase 2: along y, multiply by -i k / k^2, back along y for both components ----
+    {
+        cd *a = buf, *bx = a + ny, *by = bx + ny, *tmp = by + ny, *tw = tmp + ny;
+        const double pi = 3.14159265358979323846;
+        const double kx0 = 2.0 * pi / m.dimx, ky0 = 2.0 * pi / m.dimy;
+        __syncthreads();
+        line_twiddles(tw, ny);
+        for (int task = blockIdx.x; task < nb * nh; task += gridDim.x) {
+            const int b = task / nh, ik = task - b * nh;
+            __syncthreads();
+            for (int jk = threadIdx.x; jk < ny; jk += kSolveBlock) {
+                const double2 r = B.rk[b][ik + (size_t)nh * jk];
+                a[jk] = mk(r.x, r.y);
+            }
+            line_fft(a, tmp, tw, ny, -1);
+            for (int jk = threadIdx.x; jk < ny; jk += kSolveBlock) {
+                double kx = (double)ik * kx0;
+                const double ky = (jk < ny / 2) ? (double)jk * ky0 : (double)(jk - ny) * ky0;
+                if (ik == 0 && jk == 0) kx = 1.0;
+                const double k2 = kx * kx + ky * ky;
+                const double kkx = kx / k2, kky = ky / k2;
+                const cd r = a[jk];
+                bx[jk] = mk(kkx * r.im, -kkx * r.re);
+                by[jk] = mk(kky * r.im, -kky * r.re);
+            }
+            line_fft(bx, tmp, tw, ny, +1);
+            line_fft(by, tmp, tw, ny, +1);
+            const size_t plane = (size_t)nh * ny;
+            for (int jk = threadIdx.x; jk < ny; jk += kSolveBlock) {
+                B.ek[b][ik + (size_t)nh * jk] = make_double2(bx[jk].re, bx[jk].im);
+                B.ek[b][plane + ik + (size_t)nh * jk] = make_double2(by[jk].re, by[jk].im);
+            }
+        }
+    }
+    grid.sync();
+
+    // ---- phase 3: c2r along x (FFTW semantics), ghosts, 1/(nx ny) ----
+    {
+        cd *a = buf, *tmp = a + nx, *tw = tmp + nx;
+        __syncthreads();
+        line_twiddles(tw, nx);
+        const double sc = 1.0 / (double)(nx * ny);
+        for (int task = blockIdx.x; task < nb * 2 * ny; task += gridDim.x) {
+            const int b = task / (2 * ny), r = task - b * 2 * ny, comp = r / ny, j = r - comp * ny;
+            const double2 *src = B.ek[b] + (size_t)comp * nh * ny + (size_t)nh * j;
+            double *emesh = reinterpret_cast<double *>(B.emesh[b]);
+            __syncthreads();
+            for (int i = threadIdx.x; i < nx; i += kSolveBlock) {
+                cd z;
+                if (i < nh) {
+                    z = mk(src[i].x, src[i].y);
+                    if (i == 0 || (2 * i == nx)) z.im = 0.0;
+                } else {
+                    z = mk(src[nx - i].x, -src[nx - i].y);
+                }
+                a[i] = z;
+            }
+            line_fft(a, tmp, tw, nx, +1);
+            for (int i = threadIdx.x; i <= nx; i += kSolveBlock) {
+                const double val = a[i == nx ? 0 : i].re * sc;
+                emesh[comp + 2 * ((size_t)i + (size_t)ld * j)] = val;
+                if (j == 0) emesh[comp + 2 * ((size_t)i + (size_t)ld * ny)] = val;
+            }
+        }
+    }
+    grid.sync();
+
+    // ---- phase 4: energy partials over fixed chunks; halo copies ----
+    {
+        const int n = ld * (ny + 1), eper = (n + kSolveParts - 1) / kSolveParts;
+        for (int task = blockIdx.x; task < nb * kSolveParts; task += gridDim.x) {
+            const int b = task / kSolveParts, c = task - b * kSolveParts;
+            const int lo = c * eper, hi = min(lo + eper, n);
+            double part = 0.0;
+            for (int q = lo + threadIdx.x; q < hi; q += kSolveBlock) {
+                const double2 ev = B.emesh[b][q];
+                part += ev.x * ev.x + ev.y * ev.y;
+            }
+            const double tot = block_sum_256(part, shd);
+            if (threadIdx.x == 0) B.partial[2 * kSolveParts + task] = tot;
+        }
+        for (int b = 0; b < nb; ++b) {
+            const double2 *emesh = B.emesh[b];
+            double2 *ehalo = B.ehalo[b];
+            if (!ehalo) continue;
+            if (B.halo_tiled) {
+                const int ntx = (nx + 6 + 1) >> 1, nty = (ny + 6 + 3) >> 2, nn = ntx * nty * 8;
+                for (int q = blockIdx.x * kSolveBlock + threadIdx.x; q < nn; q += gridDim.x * kSolveBlock) {
+                    const int tile = q >> 3, w = q & 7;
+                    const int tj = tile / ntx, ti = tile - tj * ntx;
+                    int i = 2 * ti + (w & 1) - 2, j = 4 * tj + (w >> 1) - 2;
+                    i %= nx; i += (i < 0) ? nx : 0;
+                    j %= ny; j += (j < 0) ? ny : 0;
+                    ehalo[q] = emesh[i + ld * j];
+                }
+            } else {
+                const int lx = nx + 6, ly = ny + 6;
+                for (int q = blockIdx.x * kSolveBlock + threadIdx.x; q < lx * ly; q += gridDim.x * kSolveBlock) {
+                    const int je = q / lx, ie = q - je * lx;
+                    int i = ie - 2, j = je - 2;
+                    i += (i < 0) ? nx : 0; i -= (i >= nx) ? nx : 0;
+                    j += (j < 0) ? ny : 0; j -= (j >= ny) ? ny : 0;
+                    ehalo[q] = emesh[i + ld * j];
+                }
+            }
+        }
+    }
+    grid.sync();
+    if (blockIdx.x == 0 && threadIdx.x < nb) {
+        const int b = threadIdx.x;
+        double t = 0.0;
+        for (int c = 0; c < kSolveParts; ++c) t += B.partial[2 * kSolveParts + b * kSolveParts + c];
+        if (B.energy[b]) *B.energy[b] = t * m.dx * m.dy;
+    }
+}
+
 // =================================================================================================
 // 4. loaders / diagnostics
 // =================================================================================================
@@ -800,6 +1036,35 @@ cudaError_t launch_poisson(const LaunchCtx &c, const MeshDev &m, const PoissonWo
         k_energy<<<1, kMeshBlock, 0, c.stream>>>(m, reinterpret_cast<const double2 *>(emesh), energy);
         count(c);
     }
+    return cudaGetLastError();
+}
+
+size_t field_solve_scratch_bytes() { return sizeof(double) * 4 * kSolveParts; }
+
+cudaError_t launch_field_solve(const LaunchCtx &c, const MeshDev &m, const SolveBatch &B) {
+    if (B.nb < 1 || B.nb > 2) return cudaErrorInvalidValue;
+    if (!poisson_size_supported(m.nx) || !poisson_size_supported(m.ny) || m.nx < 4 || m.ny < 4) return cudaErrorInvalidValue;
+    const size_t smem = sizeof(double2) * (size_t)max(3 * m.nx, 5 * m.ny);
+    static size_t smem_set = 0;
+    cudaError_t e;
+    if (smem > 48 * 1024 - 4096 && smem > smem_set) {
+        e = cudaFuncSetAttribute(k_field_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        smem_set = smem;
+    }
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_field_solve, kSolveBlock, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    const int want = B.nb * 2 * m.ny;                      // the phase with the most tasks
+    int grid = c.sm_count * (per_sm > 2 ? 2 : per_sm);
+    if (grid > want) grid = want;
+    MeshDev mm = m;
+    SolveBatch bb = B;
+    void *args[] = {&mm, &bb};
+    e = cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(k_field_solve), dim3(grid), dim3(kSolveBlock), args, smem, c.stream);
+    if (e != cudaSuccess) return e;
+    count(c);
     return cudaGetLastError();
 }
 

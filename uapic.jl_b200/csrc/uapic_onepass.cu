@@ -76,7 +76,9 @@ namespace {
 #define UAPIC_OP_BLOCK_B 256
 #endif
 #ifndef UAPIC_OP_PAIR_LOADS
-#define UAPIC_OP_PAIR_LOADS 1     // M6 gathers fetch two taps per 256-bit load (gather_tiled_pairs, uapic_fast.cuh); 0: 36 LDG.128
+#define UAPIC_OP_PAIR_LOADS 0     // 1: M6 gathers fetch two taps per 256-bit load (gather_tiled_pairs). MEASURED SLOWER (profiles/README.md r2a):
+                                  // an LDG.256 costs 11.7 data-pipe wavefronts against 5.3 for an LDG.128 -- the pipe is bound by the 128 B/clk
+                                  // register write-back, not by the number of lines touched
 #endif
 #if UAPIC_OP_PAIR_LOADS
 #define OP_GATHER_M6 gather_tiled_pairs
