@@ -220,3 +220,23 @@ def test_gnuplot_dump_layout(tmp_path):
     rec = [float(t) for t in lines[4].split()]            # i = 1, j = 0
     assert rec == [m.dx, 0.0, 1.5, -2.0, 3.0]
     assert lines[0].count("  ") == 4
+
+
+# ---- both double oracles against the extended-precision referee (tests/golden/make_referee.py) -----------------------------
+import glob as _glob  # noqa: E402
+
+from referee_util import dist_to_referee, referee_cases  # noqa: E402
+
+
+@pytest.mark.parametrize("path", referee_cases(), ids=lambda p: p.split("referee_")[-1][:-4])
+def test_c_oracle_vs_extended_precision_referee(corc, path):
+    """the C oracle (Fortran operation order, double) must sit where make_referee.py found it: x and the energy history within
+    1e-13 of the long-double evaluation, v within 4.2e-14 * (0.1/eps) * 10 -- the eps-amplified rounding of b(x)"""
+    g = np.load(path)
+    om = oracle.mesh(0, 4 * np.pi, int(g["nx"]), 0, 2 * np.pi, int(g["ny"]))
+    x, v = g["x0"].copy(order="F"), g["v0"].copy(order="F")
+    en, _, _, _ = corc.run_bupdate(om, int(g["ntau"]), float(g["eps"]), float(g["dt"]), int(g["nstep"]), x, v, float(g["w"]))
+    dx, dv, de = dist_to_referee(g, x, v, en)
+    assert dx < 1e-13 and de < 1e-13
+    assert dv < 5e-13 * (0.1 / float(g["eps"]))
+    assert dv < 2.0 * float(g["c_oracle_dist"][1]) + 1e-15      # and has not moved since the vectors were made

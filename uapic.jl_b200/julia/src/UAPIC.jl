@@ -18,7 +18,8 @@ export preparation!, update_particles_e!, update_particles_x!, compute_f!, ua_st
 export fft_tau!, ifft_tau!
 export integrate, gnuplot, errors
 export Session, upload_particles!, init_fields!, step!, step_host!, generate_particles!, set_sort!, download_particles, download_fields, energy_history
-export STORE_FULL, STORE_HYBRID, STORE_ONEPASS, STORE_ONEPASS_LEAN
+export STORE_FULL, STORE_HYBRID, STORE_ONEPASS, STORE_ONEPASS_LEAN, SCHEME_M6, SCHEME_CIC
+export nccl_unique_id, init_nccl!, sum_v
 export UAPICError
 
 const libuapic = get(ENV, "UAPIC_B200_LIB", joinpath(@__DIR__, "..", "..", "libuapic_b200.so"))
@@ -27,6 +28,8 @@ const WRAP_FORTRAN = Cint(0)
 const WRAP_JULIA   = Cint(1)
 const DEPOSIT_FP64_ATOMIC = Cint(0)
 const DEPOSIT_FIXED_POINT = Cint(1)
+const SCHEME_M6  = Cint(0)           # quintic spline: what the reference ships
+const SCHEME_CIC = Cint(1)           # bilinear, build-defined (include/uapic_b200.h); STORE_ONEPASS_LEAN only
 const STORE_FULL         = Cint(0)   # two field barriers per step, 128 B per particle-tau between them
 const STORE_HYBRID       = Cint(1)   # ... 16 B, predictor recomputed
 const STORE_ONEPASS      = Cint(2)   # one field barrier per step, 72 B per particle-tau across it
@@ -361,14 +364,35 @@ mutable struct Session
     # STORE_FULL (the literal two-barrier sequence, 128 B) otherwise; see include/uapic_b200.h
     function Session(mesh::Mesh, ntau, ε, dt, nbpart; weight = (mesh.xmax - mesh.xmin) * (mesh.ymax - mesh.ymin) / nbpart,
                      nbpart_global = nbpart, wrap = WRAP_JULIA, deposit_mode = DEPOSIT_FP64_ATOMIC, device = 0,
-                     storage_mode = ntau in (8, 16, 32) ? STORE_ONEPASS_LEAN : STORE_FULL)
-        cfg = CConfig(CMesh(mesh), ntau, wrap, deposit_mode, 0, storage_mode, device, ε, dt, nbpart, weight, weight * nbpart_global, C_NULL)
+                     scheme = SCHEME_M6, storage_mode = ntau in (8, 16, 32) ? STORE_ONEPASS_LEAN : STORE_FULL)
+        cfg = CConfig(CMesh(mesh), ntau, wrap, deposit_mode, scheme, storage_mode, device, ε, dt, nbpart, weight, weight * nbpart_global, C_NULL)
         h = Ref{Ptr{Cvoid}}(C_NULL)
         check(ccall((:uapic_session_create, libuapic), Cint, (Ref{CConfig}, Ref{Ptr{Cvoid}}), cfg, h))
         s = new(h[], mesh, nbpart)
         finalizer(x -> (x.handle != C_NULL && ccall((:uapic_session_destroy, libuapic), Cint, (Ptr{Cvoid},), x.handle); x.handle = C_NULL), s)
         s
     end
+end
+
+# ---- several GPUs, one Julia process per GPU ------------------------------------------------------------------------
+# The library binds libnccl.so.2 itself (dlopen) and sums the raw ρ meshes with ncclAllReduce on the session's stream; the
+# caller only has to hand rank 0's 128-byte id to the other ranks (MPI.jl: `MPI.Bcast!(id, 0, comm)`; or a shared file):
+#     id = rank == 0 ? nccl_unique_id() : zeros(UInt8, 128);  MPI.Bcast!(id, 0, comm)
+#     s  = Session(mesh, ntau, ε, dt, n_local; nbpart_global = n_global, device = local_rank)
+#     init_nccl!(s, id, nranks, rank)
+function nccl_unique_id()
+    id = zeros(UInt8, 128)
+    check(ccall((:uapic_nccl_unique_id, libuapic), Cint, (Ptr{UInt8},), id))
+    id
+end
+init_nccl!(s::Session, id::Vector{UInt8}, nranks, rank) =
+    (length(id) == 128 || error("the NCCL unique id is 128 bytes");
+     check(ccall((:uapic_session_init_nccl, libuapic), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Cint, Cint), s.handle, id, nranks, rank)))
+# sum(v[1,:]), sum(v[2,:]) of this shard -- what test/bupdate.jl:112 prints every step
+function sum_v(s::Session)
+    out = zeros(2)
+    check(ccall((:uapic_session_sum_v, libuapic), Cint, (Ptr{Cvoid}, Ptr{Cdouble}), s.handle, out))
+    out
 end
 
 # reorder the device copies of the particle arrays by coarse mesh bin every `interval` steps (0 = never); uploads and
