@@ -35,7 +35,10 @@ DIMX, DIMY = 4 * np.pi, 2 * np.pi
 
 
 def _compare(xg, vg, eng, xo, vo, eno, eps, tol=1e-10):
-    tolv = tol * max(1.0, 0.1 / eps)
+    # measured (profiles/r2b_small_eps_parity.json): GPU-vs-oracle distance of v is 3.4e-14 at eps = 0.1 and grows like 1/eps
+    # (3.1e-10 at 1e-5) -- both sit within 2e-10 of the extended-precision referee there.  30x that, instead of round 1's
+    # 1e-10 * 0.1/eps (which was 1e-6 at eps = 1e-5).
+    tolv = min(tol, 1e-12) * max(1.0, 0.1 / eps)
     assert periodic_diff(xg[0], xo[0], DIMX).max() < tol * DIMX
     assert periodic_diff(xg[1], xo[1], DIMY).max() < tol * DIMY
     assert np.abs(vg - vo).max() < tolv * np.abs(vo).max()

@@ -260,7 +260,7 @@ def test_stage_chain_vs_oracle(corc, ntau, eps):
     ub.ua_step(jl2, yf, ua, p, np.asfortranarray(fy * ntau), np.asfortranarray(gy * ntau))
     v_ref = np.zeros((2, npart), order="F")
     corc.compute_v(eps, t, yt_c, v_ref)
-    tolv = tol * max(1.0, 0.1 / eps)
+    tolv = min(tol, 1e-12) * max(1.0, 0.1 / eps)      # 30x the measured GPU-vs-oracle distance (profiles/r2b_small_eps_parity.json)
     ub.compute_v(jl2, p, ua, yt_is_fourier=True)                      # Julia: Fourier coefficients (unnormalised)
     assert np.abs(p.v - v_ref).max() < tolv * np.abs(v_ref).max()
     ub.compute_v(yt_c, p, ua, yt_is_fourier=False)                    # Fortran: time domain

@@ -430,7 +430,7 @@ int uapic_compute_v(int ntau, double eps, int64_t nbpart, const double *t, const
 // ================================================================================================
 
 #ifndef UAPIC_HOST_CHUNKS
-#define UAPIC_HOST_CHUNKS 32     // particle chunks of uapic_session_step_host (copies of a chunk overlap the kernels of its neighbours)
+#define UAPIC_HOST_CHUNKS 64     // most particle chunks of uapic_session_step_host (copies of a chunk overlap the kernels of its neighbours)
 #endif
 #ifndef UAPIC_RAW_COPIES
 #define UAPIC_RAW_COPIES 8      // CTA-private copies of the two raw deposit meshes of the one-pass kernels (measured: -2 % on phase A)
@@ -1035,12 +1035,12 @@ int uapic_session_step_host(uapic_session_t *s, const double *x_in, const double
         return uapic_session_download_particles(s, x_out, v_out);
     }
     constexpr int kMaxChunks = UAPIC_HOST_CHUNKS;
-    // chunks of at least 2^20 particles: smaller ones cost more in launch tails than their overlap hides
-    const int kChunks = (int)std::min<int64_t>(kMaxChunks, std::max<int64_t>(2, np >> 20));
+    // chunks of at least 2^18 particles (smaller ones cost more in launch tails than their overlap hides), at least 2
+    const int kChunks = (int)std::min<int64_t>(kMaxChunks, std::max<int64_t>(2, np >> 18));
     if (!s->up_stream) {
         CU(cudaStreamCreateWithFlags(&s->up_stream, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithFlags(&s->down_stream, cudaStreamNonBlocking));
-        for (int q = 0; q < 2 * kMaxChunks + 2; ++q) {
+        for (int q = 0; q < 3 * kMaxChunks + 2; ++q) {
             cudaEvent_t e;
             CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
             s->chunk_ev.push_back(e);
@@ -1056,7 +1056,7 @@ int uapic_session_step_host(uapic_session_t *s, const double *x_in, const double
     bool sort = false;
     TRY(session_want_sort(s, &sort));
     cudaStream_t cs = s->lc.stream;
-    cudaEvent_t ev_start = s->chunk_ev[2 * kMaxChunks], ev_done = s->chunk_ev[2 * kMaxChunks + 1];
+    cudaEvent_t ev_start = s->chunk_ev[3 * kMaxChunks], ev_done = s->chunk_ev[3 * kMaxChunks + 1];
     CU(cudaEventRecord(ev_start, cs));                       // earlier work on the session stream (previous step) is finished
     CU(cudaStreamWaitEvent(s->up_stream, ev_start, 0));
     CU(cudaStreamWaitEvent(s->down_stream, ev_start, 0));
@@ -1090,6 +1090,11 @@ int uapic_session_step_host(uapic_session_t *s, const double *x_in, const double
         pc.rec = op.rec + 8 * lo;
         pc.ehalo = s->ehalo.as<double2>();
         CU(launch_onepass_a(s->lc, pc));
+        // the new x is final after phase A (corrector deposit position, compute_rho_m6.F90:86-87) and already in the caller's
+        // order: send it down now, while the device-to-host direction of the link is idle -- only v has to wait for phase B
+        CU(cudaEventRecord(s->chunk_ev[2 * kMaxChunks + c], cs));
+        CU(cudaStreamWaitEvent(s->down_stream, s->chunk_ev[2 * kMaxChunks + c], 0));
+        CU(cudaMemcpyAsync(x_out + 2 * lo, s->x.as<double2>() + lo, 16 * (size_t)n, cudaMemcpyDeviceToHost, s->down_stream));
     }
     // ---- the one field barrier ----
     TRY(session_field_barrier(s, 2));
@@ -1108,7 +1113,6 @@ int uapic_session_step_host(uapic_session_t *s, const double *x_in, const double
         CU(launch_onepass_b(s->lc, pc));
         CU(cudaEventRecord(s->chunk_ev[kMaxChunks + c], cs));
         CU(cudaStreamWaitEvent(s->down_stream, s->chunk_ev[kMaxChunks + c], 0));
-        CU(cudaMemcpyAsync(x_out + 2 * lo, s->x.as<double2>() + lo, 16 * (size_t)n, cudaMemcpyDeviceToHost, s->down_stream));
         CU(cudaMemcpyAsync(v_out + 2 * lo, s->v.as<double2>() + lo, 16 * (size_t)n, cudaMemcpyDeviceToHost, s->down_stream));
     }
     CU(cudaEventRecord(ev_done, s->down_stream));
