@@ -167,7 +167,7 @@ def run_peaks(args):
     for d in ("profiles", "gpurun_out"):
         with open(os.path.join(ROOT, d, "fp64_peak.json"), "w") as f:
             json.dump(out, f, indent=1)
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 def run_reference(args):
@@ -192,7 +192,26 @@ def run_reference(args):
                          "sample": f"{min(sample, np_global)} particles x ntau={ntau} x {args.steps} steps of the same workload (Fortran-faithful: 3 gathers/step)"},
         "e2e": {"value": rate, "unit": "particle-tau updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """the contract is ONE JSON line on stdout: libraries that print there from C (NCCL's "NCCL version ..." banner when a
+    communicator is created under NCCL_DEBUG=VERSION/WARN) are sent to stderr; emit() writes the line to the real stdout"""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
@@ -220,6 +239,7 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    quiet_stdout()
 
     if args.impl == "reference":
         run_reference(args)
@@ -409,7 +429,7 @@ def main():
             line["cpu_baseline"] = cpu_baseline_block(args.workload, np_global, eps, args.cpu_sample or (100_000 if world == 1 else 50_000))
         else:
             line["cpu_baseline"] = None
-        print(json.dumps(line), flush=True)
+        emit(line)
     s.close()
     if dist is not None:
         dist.barrier()

@@ -15,12 +15,13 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.skipif(ub.device_count() < 2, reason="needs at least 2 GPUs")
-def test_sharded_run_matches_single_gpu(tmp_path):
-    world = min(ub.device_count(), 4)
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_run_matches_single_gpu(tmp_path, world):
+    if ub.device_count() < world:
+        pytest.skip(f"needs {world} GPUs, this box has {ub.device_count()}")
     out = tmp_path / "multi.json"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
-           "--master-port", "29611", os.path.join(ROOT, "tests", "multi_gpu_worker.py"), str(out)]
+           "--master-port", str(29611 + world), os.path.join(ROOT, "tests", "multi_gpu_worker.py"), str(out)]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     res = json.load(open(out))
