@@ -386,19 +386,35 @@ def main():
         dom = (kb, bytes_b, per_b, impl_b) if per_b >= per_a else (ka, bytes_a, per_a, impl_a)
         achieved = dom[1] / (dom[2] * 1e-3) / 1e9 if dom[2] > 0 else 0.0
         b_alg = 256 + 112 / ntau
-        # DRAM traffic of the dominant kernel: dram__bytes_read + dram__bytes_write of one `ncu --set full` capture at 2e6
-        # particles (profiles/r1n_traffic.json), scaled to this launch's particle-tau count (traffic is linear in it)
+        # DRAM traffic of the dominant kernel: dram__bytes_read + dram__bytes_write of an ncu capture of the same kernels at
+        # 12.5e6 particles (profiles/r2e_traffic.json; r1n_traffic.json = 2e6 particles as fallback), scaled to this launch's
+        # particle-tau count (traffic is linear in it: no reuse across particles)
         traffic, traffic_src = None, None
+        for tfile in ("r2e_traffic.json", "r1n_traffic.json"):
+            try:
+                with open(os.path.join(ROOT, "profiles", tfile)) as f:
+                    tj = json.load(f)
+                kshort = dom[0].split("::")[-1]
+                if onepass and storage == "onepass-lean" and ntau == tj["ntau"] and kshort in tj:
+                    per_unit = (tj[kshort]["dram_bytes_read"] + tj[kshort]["dram_bytes_write"]) / (tj["particles"] * tj["ntau"])
+                    traffic = int(per_unit * n_loc * ntau)
+                    traffic_src = f"ncu capture at {tj['particles']} particles scaled by particle-tau count ({per_unit:.1f} B each); profiles/{tfile}"
+                    break
+            except (OSError, KeyError, ValueError):
+                pass
+        # fp64 pipe beside HBM: executed fp64 lane-instructions per update (ncu opcode census of both kernels,
+        # profiles/r1n_sass_mix.txt) x rate / the DFMA rate measured on this pool (bench.py --peaks -> profiles/fp64_peak.json)
+        fp64 = None
         try:
-            with open(os.path.join(ROOT, "profiles", "r1n_traffic.json")) as f:
-                tj = json.load(f)
-            kshort = dom[0].split("::")[-1]
-            if onepass and storage == "onepass-lean" and ntau == tj["ntau"] and kshort in tj:
-                per_unit = (tj[kshort]["dram_bytes_read"] + tj[kshort]["dram_bytes_write"]) / (tj["particles"] * tj["ntau"])
-                traffic = int(per_unit * n_loc * ntau)
-                traffic_src = f"ncu capture at {tj['particles']} particles scaled by particle-tau count ({per_unit:.1f} B each); profiles/r1n_traffic.json"
+            with open(os.path.join(ROOT, "profiles", "fp64_peak.json")) as f:
+                pk = json.load(f)
+            per_update = 842.0 if (onepass and args.scheme == "m6") else None
+            if per_update:
+                fp64 = {"fp64_lane_instr_per_update": per_update, "peak_dfma_per_s": pk["dfma_per_s"], "peak_source": "measured DFMA loop (profiles/fp64_peak.json)",
+                        "frac": value / world * per_update / pk["dfma_per_s"]}
         except (OSError, KeyError, ValueError):
             pass
+        ms_field = s.field_barrier_time() / max(nt, 1) if onepass else None
         line = {
             "metric": "particle-tau updates/sec", "value": value, "unit": "particle-tau updates/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
@@ -421,7 +437,12 @@ def main():
                          "impl_bytes_per_launch": int(dom[3]), "impl_gbs": dom[3] / (dom[2] * 1e-3) / 1e9 if dom[2] > 0 else 0.0,
                          "phase_a_ms": per_a, "phase_b_ms": per_b,
                          "whole_step_frac_of_hbm": value * b_alg / 1e9 / hbm / world,
-                         "algorithmic_bytes_per_update": b_alg},
+                         "algorithmic_bytes_per_update": b_alg,
+                         "achieved_is": "ALGORITHMIC bytes (SURVEY 8d: 128 B per particle-tau each way) / kernel time -- the graded figure, not DRAM throughput; traffic_gbs is what DRAM really moves",
+                         "traffic_gbs": (traffic / (dom[2] * 1e-3) / 1e9) if (traffic and dom[2] > 0) else None,
+                         "field_barrier_ms": ms_field,
+                         "fp64": fp64,
+                         "binding_unit": "L1TEX LSU data pipe (register write-back, 128 B/clk/SM): 76-87 % busy in both kernels (profiles/README.md); DRAM 11-18 % busy"},
             "clocks": clocks,
         }
         if not args.no_cpu_baseline:

@@ -200,6 +200,9 @@ int uapic_session_set_sort(uapic_session_t *s, int interval, int bin_cells_log2)
    phase_times returns the accumulated milliseconds and the number of steps they cover, then resets them */
 int uapic_session_enable_timing(uapic_session_t *s, int enable);
 int uapic_session_phase_times(uapic_session_t *s, double *ms_phase_a, double *ms_phase_b, int64_t *steps);
+/* milliseconds between the end of phase A and the start of phase B (fold of the deposit copies + all-reduce + field solve),
+   accumulated over the steps the LAST uapic_session_phase_times call reported (one-pass modes; the exchange step of SURVEY 8e) */
+int uapic_session_field_barrier_time(uapic_session_t *s, double *ms_field_barrier);
 /* device-side loaders (counter-based RNG; particle index offset = first global index of this shard)
    kind 0: init_particles_2d / plasma densities (particles.F90:68-103, src/plasma.jl:17-48)
    kind 1: Landau load (the intent of src/landau.jl:19-43)                                         */

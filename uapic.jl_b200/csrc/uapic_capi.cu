@@ -517,8 +517,9 @@ struct uapic_session {
     // optional per-kernel timing
     bool timing = false;
     std::vector<cudaEvent_t> ev;     // 4 per step: A0 A1 B0 B1
-    double ms_a = 0, ms_b = 0;
+    double ms_a = 0, ms_b = 0, ms_f = 0;   // phase A, phase B, and what lies between them: fold + all-reduce + field solve
     int64_t timed_steps = 0;
+    double ms_field_last = 0;
     ~uapic_session() {
         for (cudaEvent_t e : ev) cudaEventDestroy(e);
         for (cudaEvent_t e : chunk_ev) cudaEventDestroy(e);
@@ -908,10 +909,11 @@ int drain_timing(uapic_session *s) {
     if (s->ev.empty()) return UAPIC_OK;
     CU(cudaStreamSynchronize(s->lc.stream));
     for (size_t i = 0; i + 3 < s->ev.size(); i += 4) {
-        float a = 0, b = 0;
+        float a = 0, b = 0, f = 0;
         CU(cudaEventElapsedTime(&a, s->ev[i], s->ev[i + 1]));
         CU(cudaEventElapsedTime(&b, s->ev[i + 2], s->ev[i + 3]));
-        s->ms_a += a; s->ms_b += b; s->timed_steps++;
+        CU(cudaEventElapsedTime(&f, s->ev[i + 1], s->ev[i + 2]));
+        s->ms_a += a; s->ms_b += b; s->ms_f += f; s->timed_steps++;
     }
     for (cudaEvent_t e : s->ev) cudaEventDestroy(e);
     s->ev.clear();
@@ -924,7 +926,7 @@ int uapic_session_enable_timing(uapic_session_t *s, int enable) {
     TRY(session_bind(s));
     TRY(drain_timing(s));
     s->timing = enable != 0;
-    s->ms_a = s->ms_b = 0; s->timed_steps = 0;
+    s->ms_a = s->ms_b = s->ms_f = 0; s->timed_steps = 0;
     return UAPIC_OK;
 }
 
@@ -935,7 +937,14 @@ int uapic_session_phase_times(uapic_session_t *s, double *ms_phase_a, double *ms
     if (ms_phase_a) *ms_phase_a = s->ms_a;
     if (ms_phase_b) *ms_phase_b = s->ms_b;
     if (steps) *steps = s->timed_steps;
-    s->ms_a = s->ms_b = 0; s->timed_steps = 0;
+    s->ms_field_last = s->ms_f;
+    s->ms_a = s->ms_b = s->ms_f = 0; s->timed_steps = 0;
+    return UAPIC_OK;
+}
+
+int uapic_session_field_barrier_time(uapic_session_t *s, double *ms_field_barrier) {
+    if (!s || !ms_field_barrier) return fail(UAPIC_EINVAL, "null pointer");
+    *ms_field_barrier = s->ms_field_last;
     return UAPIC_OK;
 }
 

@@ -102,6 +102,12 @@ class Session:
         check(lib().uapic_session_phase_times(self._h, C.byref(a), C.byref(b), C.byref(n)))
         return a.value, b.value, n.value
 
+    def field_barrier_time(self) -> float:
+        """ms between phase A and phase B (fold + all-reduce + field solve) over the steps the last phase_times() reported"""
+        f = C.c_double(0)
+        check(lib().uapic_session_field_barrier_time(self._h, C.byref(f)))
+        return f.value
+
     def generate_particles(self, kind: str = "plasma", seed: int = 20190101, first_global_index: int = 0, alpha=0.05, kx=0.5,
                            index_stride: int = 1):
         """device-side load of this shard: global particle indices first, first+stride, ... (stride = world size and
