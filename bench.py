@@ -403,12 +403,14 @@ def main():
             except (OSError, KeyError, ValueError):
                 pass
         # fp64 pipe beside HBM: executed fp64 lane-instructions per update (ncu opcode census of both kernels,
-        # profiles/r1n_sass_mix.txt) x rate / the DFMA rate measured on this pool (bench.py --peaks -> profiles/fp64_peak.json)
+        # profiles/r2e_sass_mix.txt -> profiles/fp64_instr.json) x rate / the DFMA rate measured on this pool (bench.py --peaks -> profiles/fp64_peak.json)
         fp64 = None
         try:
             with open(os.path.join(ROOT, "profiles", "fp64_peak.json")) as f:
                 pk = json.load(f)
-            per_update = 842.0 if (onepass and args.scheme == "m6") else None
+            with open(os.path.join(ROOT, "profiles", "fp64_instr.json")) as f:
+                fi = json.load(f)
+            per_update = fi["fp64_lane_instr_per_update"] if (onepass and args.scheme == "m6" and ntau == fi["ntau"]) else None
             if per_update:
                 fp64 = {"fp64_lane_instr_per_update": per_update, "peak_dfma_per_s": pk["dfma_per_s"], "peak_source": "measured DFMA loop (profiles/fp64_peak.json)",
                         "frac": value / world * per_update / pk["dfma_per_s"]}
