@@ -77,6 +77,19 @@ DEVINL int halo_tiled_ntx(const MeshDev &m) { return (m.nx + 6 + 1) >> 1; }
 DEVINL int halo_tiled_nty(const MeshDev &m) { return (m.ny + 6 + 3) >> 2; }
 DEVINL int halo_tiled_index(int ntx, int I, int J) { return (((J >> 2) * ntx + (I >> 1)) << 3) + ((J & 3) << 1) + (I & 1); }
 
+#ifndef UAPIC_OP_TAP_EVICT_LAST
+#define UAPIC_OP_TAP_EVICT_LAST 0     // 1: the taps ask L1 to keep their lines (ld.global.nc.L1::evict_last)
+#endif
+DEVINL double2 ldg_tap(const double2 *p) {
+#if UAPIC_OP_TAP_EVICT_LAST
+    double2 r;
+    asm("ld.global.nc.L1::evict_last.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+    return r;
+#else
+    return __ldg(p);
+#endif
+}
+
 DEVINL void gather_tiled(const MeshDev &m, const double2 *__restrict__ ehalo, const Cell &c, double &e1, double &e2) {
     double cx[6], cy[6];
     m6_weights_fast(c.dpx, cx);
@@ -94,7 +107,7 @@ DEVINL void gather_tiled(const MeshDev &m, const double2 *__restrict__ ehalo, co
         double r1 = 0.0, r2 = 0.0;
 #pragma unroll
         for (int a = 0; a < 6; ++a) {
-            const double2 ev = __ldg(((a & 1) ? ro : re) + 8 * (a >> 1));
+            const double2 ev = ldg_tap(((a & 1) ? ro : re) + 8 * (a >> 1));
             r1 = fma(cx[a], ev.x, r1);
             r2 = fma(cx[a], ev.y, r2);
         }

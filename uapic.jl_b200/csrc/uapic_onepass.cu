@@ -80,10 +80,35 @@ namespace {
                                   // an LDG.256 costs 11.7 data-pipe wavefronts against 5.3 for an LDG.128 -- the pipe is bound by the 128 B/clk
                                   // register write-back, not by the number of lines touched
 #endif
-#if UAPIC_OP_PAIR_LOADS
+#if UAPIC_OP_NO_GATHER
+DEVINL void gather_none(const MeshDev &, const double2 *, const Cell &c, double &e1, double &e2) { e1 = c.dpx * 1e-3; e2 = c.dpy * 1e-3; }
+#define OP_GATHER_M6 gather_none
+#elif UAPIC_OP_PAIR_LOADS
 #define OP_GATHER_M6 gather_tiled_pairs
 #else
 #define OP_GATHER_M6 gather_tiled
+#endif
+#ifndef UAPIC_OP_STREAM_HINTS
+#define UAPIC_OP_STREAM_HINTS 2   // 1: the once-only streams (store, records, particle arrays) use ld/st.global.cs so that they do not
+#endif                            //    displace the E-halo lines the gathers live on in L1; 2: ld.global.L1::no_allocate for them
+                                  //    (measured, profiles/README.md r2g/r2h: 1 = +-0, 2 = phase B -2.8 %)
+#ifndef UAPIC_OP_NO_GATHER        // measurement only: skip the 36 tap loads (E := position-dependent dummy) to count their wavefronts
+#define UAPIC_OP_NO_GATHER 0
+#endif
+#if UAPIC_OP_STREAM_HINTS == 2       // loads of the once-only streams do not allocate in L1 at all
+DEVINL double2 ld_noalloc(const double2 *p) {
+    double2 r;
+    asm volatile("ld.global.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+    return r;
+}
+#define OP_LDS(p) ld_noalloc(p)
+#define OP_STS(p, v) __stcs(p, v)
+#elif UAPIC_OP_STREAM_HINTS
+#define OP_LDS(p) __ldcs(p)
+#define OP_STS(p, v) __stcs(p, v)
+#else
+#define OP_LDS(p) (*(p))
+#define OP_STS(p, v) (*(p) = (v))
 #endif
 constexpr int kOpBlockA = UAPIC_OP_BLOCK_A, kOpBlockB = UAPIC_OP_BLOCK_B;      // threads per CTA of the two kernels
 constexpr int kGatherUnroll = UAPIC_OP_GATHER_UNROLL;
@@ -528,7 +553,7 @@ __global__ void __launch_bounds__(kOpBlockA, UAPIC_OP_MINB_A) k_onepass_a(OpDev 
         char *sbase = P.store + (size_t)ip * SM::stride;
         if (valid) {
 #pragma unroll
-            for (int s = 0; s < 8; ++s) SM::xtr(sbase)[g + G * s] = make_double2(X1[s].re, X2[s].re);
+            for (int s = 0; s < 8; ++s) OP_STS(SM::xtr(sbase) + g + G * s, make_double2(X1[s].re, X2[s].re));
             if (FULL) {
 #pragma unroll
                 for (int s = 0; s < 8; ++s)
@@ -607,8 +632,8 @@ __global__ void __launch_bounds__(kOpBlockA, UAPIC_OP_MINB_A) k_onepass_a(OpDev 
         if (valid) {
 #pragma unroll
             for (int s = 0; s < 8; ++s) {
-                SM::yt1(sbase)[g + G * s] = make_double2(y1[s].re, y1[s].im);
-                SM::yt2(sbase)[g + G * s] = make_double2(y2[s].re, y2[s].im);
+                OP_STS(SM::yt1(sbase) + g + G * s, make_double2(y1[s].re, y1[s].im));
+                OP_STS(SM::yt2(sbase) + g + G * s, make_double2(y2[s].re, y2[s].im));
             }
         }
         if (FULL) {
@@ -625,7 +650,7 @@ __global__ void __launch_bounds__(kOpBlockA, UAPIC_OP_MINB_A) k_onepass_a(OpDev 
         {   // next tile of this warp (clamped like the current one)
             const int64_t kn = kraw + nwarps * PW;
             const int64_t in = (tile + nwarps < t_end && kn < P.np) ? kn : P.np - 1;
-            xx_n = P.x[in]; vv_n = P.v[in]; ee_n = P.ep[in];
+            xx_n = OP_LDS(P.x + in); vv_n = OP_LDS(P.v + in); ee_n = OP_LDS(P.ep + in);
         }
         // ---- both deposit positions, deposits, per-particle record ----
         posp1 = grp_sum<G>(posp1); posp2 = grp_sum<G>(posp2);
@@ -736,7 +761,7 @@ __global__ void __launch_bounds__(kOpBlockB, UAPIC_OP_MINB_B) k_onepass_b(OpDev 
             const int64_t kraw = tile * PW + pp;
             const bool valid = kraw < P.np;
             const int64_t ip = valid ? kraw : P.np - 1;
-            const double2 r0 = *reinterpret_cast<const double2 *>(P.rec + 8 * ip);
+            const double2 r0 = OP_LDS(reinterpret_cast<const double2 *>(P.rec + 8 * ip));
             const double b = r0.x, rb = r0.y;
             char *sbase = P.store + (size_t)ip * SM::stride;
 #if UAPIC_OP_PREFETCH_B
@@ -751,7 +776,7 @@ __global__ void __launch_bounds__(kOpBlockB, UAPIC_OP_MINB_B) k_onepass_b(OpDev 
                 }
             }
 #endif
-            const double2 xs = SM::xtr(sbase)[n], ya = SM::yt1(sbase)[n], yb = SM::yt2(sbase)[n];
+            const double2 xs = OP_LDS(SM::xtr(sbase) + n), ya = OP_LDS(SM::yt1(sbase) + n), yb = OP_LDS(SM::yt2(sbase) + n);
             double2 wn;
             double iv;
             if (FULL) {
