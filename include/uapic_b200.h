@@ -196,6 +196,11 @@ int uapic_session_upload_particle_e(uapic_session_t *s, const double *ep);
    and downloads are always in the caller's particle order.  Default: every step with 8 x 8-cell bins for the one-pass
    storage modes, off for the others.  Not in the reference (particles there are processed in array order). */
 int uapic_session_set_sort(uapic_session_t *s, int interval, int bin_cells_log2);
+/* Phase fusion (UAPIC_STORE_ONEPASS_LEAN): phase B of step n (gather of the predictor field, compute_v) runs inside the first
+   kernel of step n+1 instead of as a kernel of its own; results are identical to the unfused sequence (same arithmetic, same
+   order).  The pending phase B of the last step runs on its own as soon as something needs v (downloads, sum_v) or reorders the
+   particles; with fusion on, reordering happens every 4 steps by default (uapic_session_set_sort changes it). */
+int uapic_session_set_fusion(uapic_session_t *s, int enable);
 /* per-kernel device timing: when enabled, CUDA events bracket the two fused phase kernels of every step;
    phase_times returns the accumulated milliseconds and the number of steps they cover, then resets them */
 int uapic_session_enable_timing(uapic_session_t *s, int enable);

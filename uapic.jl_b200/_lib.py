@@ -29,7 +29,7 @@ EXPORTS = [
     "uapic_ua_step2", "uapic_compute_rho_m6_tau", "uapic_compute_v",
     "uapic_session_create", "uapic_session_destroy", "uapic_session_set_allreduce", "uapic_nccl_unique_id", "uapic_nccl_version",
     "uapic_session_init_nccl", "uapic_session_set_nccl_comm", "uapic_session_upload_particles", "uapic_session_upload_particle_e",
-    "uapic_session_enable_timing", "uapic_session_phase_times", "uapic_session_field_barrier_time", "uapic_session_set_sort",
+    "uapic_session_set_fusion", "uapic_session_enable_timing", "uapic_session_phase_times", "uapic_session_field_barrier_time", "uapic_session_set_sort",
     "uapic_session_generate_particles", "uapic_session_generate_particles_strided", "uapic_session_init_fields", "uapic_session_step", "uapic_session_step_host", "uapic_session_synchronize",
     "uapic_session_download_particles", "uapic_session_download_particle_e", "uapic_session_download_fields",
     "uapic_session_energy_history", "uapic_session_sum_v", "uapic_session_launch_count", "uapic_session_device_bytes",

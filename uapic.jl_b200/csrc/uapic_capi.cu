@@ -432,6 +432,12 @@ int uapic_compute_v(int ntau, double eps, int64_t nbpart, const double *t, const
 #ifndef UAPIC_HOST_CHUNKS
 #define UAPIC_HOST_CHUNKS 64     // most particle chunks of uapic_session_step_host (copies of a chunk overlap the kernels of its neighbours)
 #endif
+#ifndef UAPIC_FUSE_DEFAULT
+#define UAPIC_FUSE_DEFAULT 0            // phase B of step n inside phase A of step n+1 (uapic_session_set_fusion); $UAPIC_FUSE_BA overrides
+#endif
+#ifndef UAPIC_FUSE_SORT_INTERVAL
+#define UAPIC_FUSE_SORT_INTERVAL 4      // fused mode: the particles can only be reordered where the store is dead, every this many steps
+#endif
 #ifndef UAPIC_RAW_COPIES
 #define UAPIC_RAW_COPIES 8      // CTA-private copies of the two raw deposit meshes of the one-pass kernels (measured: -2 % on phase A)
 #endif
@@ -500,6 +506,8 @@ struct uapic_session {
     // spatial reordering (uapic_sort.cu): alternate buffers, slot -> original index, scratch; allocated at the first sort
     DevBuf x2, v2, ep2, perm, perm2, binid, hist;
     bool permuted = false;             // device arrays are in sorted order, perm is valid
+    bool fuse = false;                 // run phase B of step n inside phase A of step n+1 (k_onepass_a<..., FUSEB>; lean layout)
+    bool pending_b = false;            // fused mode: phase B of the last step has not run yet (v on the device is one step old)
     bool sort_bufs_ready = false;      // the whole set of alternate buffers exists (all-or-nothing)
     int sort_interval = 0, sort_shift = 3;
     int64_t steps_done = 0;
@@ -625,8 +633,19 @@ OnepassParams session_onepass_params(uapic_session *s) {
     p.ehalo = s->ehalo.as<double2>();
     p.store = s->store.as<char>(); p.rec = s->rec.as<double>();
     p.rho_p = s->acc; p.rho_c = s->acc_c; p.rho_copies = UAPIC_RAW_COPIES;
-    p.out_perm = nullptr; p.x_out = nullptr; p.v_out = nullptr;
+    p.out_perm = nullptr; p.x_out = nullptr; p.v_out = nullptr; p.ehalo_b = nullptr; p.fuse_b = 0;
     return p;
+}
+
+// fused mode leaves phase B of the last step pending (it runs inside the next step's first kernel); everything that reads or
+// replaces v, or reorders the particles, runs it on its own first
+int session_flush_b(uapic_session *s) {
+    if (!s->pending_b) return UAPIC_OK;
+    OnepassParams op = session_onepass_params(s);
+    op.ehalo = s->ehalo_p.as<double2>();
+    CU(launch_onepass_b(s->lc, op));
+    s->pending_b = false;
+    return UAPIC_OK;
 }
 
 // reorder x, v, ep by coarse mesh bin; callers never see the order (downloads undo it)
@@ -781,6 +800,8 @@ int uapic_session_create(const uapic_config_t *cfg, uapic_session_t **out) {
         if (!rc) rc = session_alloc(s, s->ek2, 32 * nk);
     }
     { const char *e = getenv("UAPIC_SPLIT_SOLVE"); s->split_solve = e && *e == '1'; }
+    { const char *e = getenv("UAPIC_FUSE_BA"); s->fuse = (e ? *e == '1' : UAPIC_FUSE_DEFAULT) && cfg->storage_mode == UAPIC_STORE_ONEPASS_LEAN;
+      const char *k = getenv("UAPIC_FUSE_SORT"); if (s->fuse) s->sort_interval = k ? atoi(k) : UAPIC_FUSE_SORT_INTERVAL; }
     if (!rc) rc = session_alloc(s, s->energy, 8 * (size_t)s->cap_energy);
     if (!rc) rc = session_alloc(s, s->sumv, 16 + sum_v_scratch_bytes());
     if (rc) { delete s; return rc; }
@@ -863,9 +884,22 @@ int uapic_session_set_nccl_comm(uapic_session_t *s, void *comm) {
     return UAPIC_OK;
 }
 
+int uapic_session_set_fusion(uapic_session_t *s, int enable) {
+    if (!s) return fail(UAPIC_EINVAL, "session is null");
+    if (enable && s->cfg.storage_mode != UAPIC_STORE_ONEPASS_LEAN)
+        return fail(UAPIC_EUNSUPPORTED, "phase fusion exists for storage_mode UAPIC_STORE_ONEPASS_LEAN only");
+    TRY(session_bind(s));
+    if (!enable) TRY(session_flush_b(s));
+    if (enable && !s->fuse && s->sort_interval == 1) s->sort_interval = UAPIC_FUSE_SORT_INTERVAL;   // see the header
+    if (!enable && s->fuse && s->sort_interval == UAPIC_FUSE_SORT_INTERVAL) s->sort_interval = 1;
+    s->fuse = enable != 0;
+    return UAPIC_OK;
+}
+
 int uapic_session_upload_particles(uapic_session_t *s, const double *x, const double *v) {
     if (!s || !x || !v) return fail(UAPIC_EINVAL, "uapic_session_upload_particles: null pointer");
     TRY(session_bind(s));
+    s->pending_b = false;          // v is replaced: the pending compute_v of the old particles has no reader
     const size_t n = 16 * (size_t)s->cfg.nbpart;
     CU(cudaMemcpyAsync(s->x.p, x, n, cudaMemcpyHostToDevice, s->lc.stream));
     CU(cudaMemcpyAsync(s->v.p, v, n, cudaMemcpyHostToDevice, s->lc.stream));
@@ -883,6 +917,7 @@ int uapic_session_upload_particles(uapic_session_t *s, const double *x, const do
 int uapic_session_upload_particle_e(uapic_session_t *s, const double *ep) {
     if (!s || !ep) return fail(UAPIC_EINVAL, "uapic_session_upload_particle_e: null pointer");
     TRY(session_bind(s));
+    TRY(session_flush_b(s));
     if (s->permuted) {
         // the device arrays are in sorted order: undo it for x and v so that everything is in the caller's order again
         CU(launch_unpermute(s->lc, s->cfg.nbpart, s->perm.as<uint32_t>(), s->x.as<double2>(), s->x2.as<double2>()));
@@ -954,6 +989,7 @@ int uapic_session_generate_particles_strided(uapic_session_t *s, int kind, uint6
     if (kind != 0 && kind != 1) return fail(UAPIC_EINVAL, "unknown load kind %d", kind);
     if (index_stride < 1 || first_global_index < 0) return fail(UAPIC_EINVAL, "bad particle index range");
     TRY(session_bind(s));
+    s->pending_b = false;
     CU(launch_generate(s->lc, s->m, kind, seed, first_global_index, index_stride, s->cfg.nbpart, s->np_global, alpha, kx,
                        s->x.as<double>(), s->v.as<double>()));
     s->permuted = false;
@@ -990,7 +1026,10 @@ int uapic_session_step(uapic_session_t *s, int nsteps) {
         if (s->sort_interval > 0 && s->steps_done % s->sort_interval == 0) {
             bool sort_on = false;
             TRY(session_want_sort(s, &sort_on));
-            if (sort_on) TRY(session_sort(s));
+            if (sort_on) {
+                TRY(session_flush_b(s));      // the store is in the old order: its phase B has to run before the particles move
+                TRY(session_sort(s));
+            }
         }
         s->steps_done++;
         const PhaseParams p = session_params(s);
@@ -1005,12 +1044,20 @@ int uapic_session_step(uapic_session_t *s, int nsteps) {
             // one field barrier per step: both deposits come out of the first kernel (uapic_onepass.cu)
             if (s->timing) CU(cudaEventRecord(e4[0], s->lc.stream));
             op.ehalo = s->ehalo.as<double2>();
+            op.ehalo_b = s->ehalo_p.as<double2>();
+            op.fuse_b = s->pending_b ? 1 : 0;                              // phase B of the previous step rides along
             CU(launch_onepass_a(s->lc, op));                               // bupdate.F90:97-106, :112-117 (x part)
+            s->pending_b = false;
             if (s->timing) CU(cudaEventRecord(e4[1], s->lc.stream));
             TRY(session_field_barrier(s, 2));      // :108 predictor field and :119 field of the next step, one exchange + one launch
             if (s->timing) CU(cudaEventRecord(e4[2], s->lc.stream));
-            op.ehalo = s->ehalo_p.as<double2>();
-            CU(launch_onepass_b(s->lc, op));                               // :110-115 (y part), :123
+            if (s->fuse) {
+                s->pending_b = true;                                       // :110-115 (y part), :123 run inside the next kernel
+            } else {
+                op.ehalo = s->ehalo_p.as<double2>();
+                op.fuse_b = 0;
+                CU(launch_onepass_b(s->lc, op));                           // :110-115 (y part), :123
+            }
             if (s->timing) CU(cudaEventRecord(e4[3], s->lc.stream));
             continue;
         }
@@ -1035,6 +1082,7 @@ int uapic_session_step_host(uapic_session_t *s, const double *x_in, const double
     if (!s || !x_in || !v_in || !x_out || !v_out) return fail(UAPIC_EINVAL, "uapic_session_step_host: null pointer");
     if (!s->fields_ready) return fail(UAPIC_ESTATE, "call uapic_session_init_fields before uapic_session_step_host");
     TRY(session_bind(s));
+    s->pending_b = false;          // x, v (and e) come from the caller: nothing on the device is carried over
     const int64_t np = s->cfg.nbpart;
     if (!s->onepass || np < (1 << 16)) {
         // two-barrier kernels / tiny problems: nothing to overlap
@@ -1141,6 +1189,7 @@ int uapic_session_synchronize(uapic_session_t *s) {
 int uapic_session_download_particles(uapic_session_t *s, double *x, double *v) {
     if (!s) return fail(UAPIC_EINVAL, "session is null");
     TRY(session_bind(s));
+    TRY(session_flush_b(s));
     if (x) TRY(session_download_pairs(s, s->x, s->x2, x));
     if (v) TRY(session_download_pairs(s, s->v, s->v2, v));
     CU(cudaStreamSynchronize(s->lc.stream));
@@ -1180,6 +1229,7 @@ int uapic_session_energy_history(uapic_session_t *s, double *out, int64_t capaci
 int uapic_session_sum_v(uapic_session_t *s, double *sumv2) {
     if (!s || !sumv2) return fail(UAPIC_EINVAL, "null pointer");
     TRY(session_bind(s));
+    TRY(session_flush_b(s));
     CU(launch_sum_v(s->lc, s->cfg.nbpart, s->v.as<double>(), s->sumv.as<double>() + 2, s->sumv.as<double>()));
     CU(cudaMemcpyAsync(sumv2, s->sumv.p, 16, cudaMemcpyDeviceToHost, s->lc.stream));
     CU(cudaStreamSynchronize(s->lc.stream));

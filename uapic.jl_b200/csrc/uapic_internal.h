@@ -108,6 +108,8 @@ struct OnepassParams {
     double2 *v;            // (2,np): read by A, written by B
     const double2 *ep;     // (2,np): particles.e, frozen after init
     const double2 *ehalo;  // TILED periodic halo copy of the field to gather: E_n for A, E_pred for B
+    const double2 *ehalo_b; // fuse_b: E_pred of the PREVIOUS step (phase B part of the fused kernel)
+    int fuse_b;            // launch_onepass_a only: 1 = run phase B of the previous step inside it (lean layout)
     char *store;           // np * onepass_store_bytes_per_particle(ntau, full)
     double *rec;           // np * 8 doubles: t, b, 1/b, bracket sums (2), cos(t/eps), sin(t/eps), unused
     RhoAcc rho_p, rho_c;   // raw accumulation meshes of the predictor and the corrector deposit (A only)

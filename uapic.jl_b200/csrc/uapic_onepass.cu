@@ -386,7 +386,12 @@ template <int N, bool FULL> struct StoreMap {
 };
 
 // =================================================================================================
-template <int G, bool FULL, int SCHEME>
+// FUSEB (lean layout only): the tile first runs phase B of the PREVIOUS step on its particles (gather of E_pred at the stored
+// predicted samples, gy, the tau* sums, compute_v) and hands the new v straight to this step's preparation -- k_onepass_b and
+// k_onepass_a of consecutive steps in one kernel.  Phase A alone leaves the LSU data pipe at 60 % and the fp64 pipe at 46 %
+// outside its own gather (measured with the tap loads compiled out), phase B alone is bound by its 36 tap loads: in one
+// kernel B's loads overlap A's transforms the way A's own gather already does.
+template <int G, bool FULL, int SCHEME, bool FUSEB>
 __global__ void __launch_bounds__(kOpBlockA, UAPIC_OP_MINB_A) k_onepass_a(OpDev D) {
     constexpr int N = 8 * G, PW = 32 / G, PPI = 32 / N;     // particles per warp tile / per gather iteration
     constexpr int kOpWarps = kOpBlockA / 32;
@@ -427,7 +432,71 @@ __global__ void __launch_bounds__(kOpBlockA, UAPIC_OP_MINB_A) k_onepass_a(OpDev 
         const int64_t kraw = tile * PW + pin;
         const bool valid = tile < t_end && kraw < P.np;
         const int64_t ip = valid ? kraw : P.np - 1;
-        const double2 xx = xx_n, vv = vv_n, ee = ee_n;
+        const double2 xx = xx_n, ee = ee_n;
+        double2 vv = vv_n;
+        if (FUSEB && !FULL) {
+            // ================= phase B of the previous step for this tile (k_onepass_b, same arithmetic) =================
+            double2 *wx = gx, *red = yhs;              // the exchange rows / the yhat stash are free until the preparation
+            {
+                const double2 *rec = reinterpret_cast<const double2 *>(P.rec + 8 * ip);
+                const double tb = OP_LDS(rec + 1).x, rtb = 1.0 / tb;
+                const double2 rc2 = OP_LDS(rec + 2), rc3 = OP_LDS(rec + 3);
+                const cd e1b = mk(rc2.y, -rc3.x);
+                cd eltb[8], wv[8];
+                elt_modes<G>(L, tb, eps, e1b, eltb);
+#pragma unroll
+                for (int k1 = 0; k1 < 8; ++k1) {
+                    cd pl, qt;
+                    pl_qt<G>(L, k1, tb, rtb, eps, eltb[k1], pl, qt);
+                    const cd w = cmulc(qt, eltb[k1]);
+                    wv[k1] = mk(invN * w.re, -invN * w.im);
+                }
+                bwdN<G>(wv, L);
+                __syncwarp();
+#pragma unroll
+                for (int s = 0; s < 8; ++s) wx[s * kRow + lane] = make_double2(wv[s].re, -wv[s].im);
+                __syncwarp();
+            }
+            {
+                const int n = lane & (N - 1);
+                const double2 csn = L.cs[n];
+#pragma unroll (kGatherUnrollB)
+                for (int j = 0; j < 8; ++j) {
+                    const int pp = j * PPI + lane / N;
+                    const int64_t kb = tile * PW + pp;
+                    const int64_t ib = (tile < t_end && kb < P.np) ? kb : P.np - 1;
+                    const double2 r0 = OP_LDS(reinterpret_cast<const double2 *>(P.rec + 8 * ib));
+                    const double bb = r0.x, rbb = r0.y;
+                    char *sb = P.store + (size_t)ib * SM::stride;
+                    const double2 xs = OP_LDS(SM::xtr(sb) + n), ya = OP_LDS(SM::yt1(sb) + n), yb = OP_LDS(SM::yt2(sb) + n);
+                    const double2 wn = wx[(n / G) * kRow + pp * G + (n & (G - 1))];
+                    const double iv = (1.0 + 0.5 * sin(xs.x) * sin(xs.y) - bb) * inv_eps;      // ua_steps.F90:177
+                    double xwb, ywb, eb1, eb2;
+                    const Cell cell = cell_fast(P.m, D.f, xs.x, xs.y, P.wrap, xwb, ywb);
+                    if (SCHEME == kSchemeCic) gather_cic_tiled(P.m, P.ehalo_b, cell, eb1, eb2); else OP_GATHER_M6(P.m, P.ehalo_b, cell, eb1, eb2);
+                    cd gy1, gy2;
+                    fy_time(csn.x, csn.y, rbb, iv, mk(ya.x, ya.y), mk(yb.x, yb.y), eb1, eb2, gy1, gy2);     // :177-183
+                    red[pp * N + (n & ~7) + (((n & 7) + (n >> 3) + 4 * (pp & 1)) & 7)] =
+                        make_double2(fma(gy1.re, wn.x, -gy1.im * wn.y), fma(gy2.re, wn.x, -gy2.im * wn.y));
+                }
+            }
+            __syncwarp();
+            {
+                double sx = 0.0, sy = 0.0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const double2 q = red[pin * N + 8 * g + ((i + g + 4 * (pin & 1)) & 7)];
+                    sx += q.x; sy += q.y;
+                }
+                sx = grp_sum<G>(sx); sy = grp_sum<G>(sy);
+                const double2 *rec = reinterpret_cast<const double2 *>(P.rec + 8 * ip);
+                const double2 r1 = OP_LDS(rec + 1), r2 = OP_LDS(rec + 2), r3 = OP_LDS(rec + 3);
+                const double px = r1.y + sx, py = r2.x + sy, cs = r2.y, sn = r3.x;
+                vv = make_double2(cs * px + sn * py, cs * py - sn * px);                           // :302-303, every lane of the particle
+                if (valid && g == 0) { if (P.out_perm) P.v_out[P.out_perm[ip]] = vv; else P.v[ip] = vv; }
+            }
+            OP_SYNC(0);        // the exchange rows are reused by the preparation below
+        }
         const double x1 = xx.x, x2 = xx.y, vx = vv.x, vy = vv.y;
 #if UAPIC_OP_PREFETCH
         {   // the CTA's next tiles: their particle data would otherwise be a cold HBM access all warps of the CTA wait on together
@@ -854,16 +923,18 @@ template <typename K> cudaError_t op_launch(K kernel, const LaunchCtx &c, const 
 bool onepass_ntau_supported(int ntau) { return ntau == 8 || ntau == 16 || ntau == 32; }
 size_t onepass_store_bytes_per_particle(int ntau, int full) { return (size_t)(full ? 72 : 48) * (size_t)ntau; }
 
-#define UAPIC_OP_LAUNCH(KERNEL, GG, MINB, BLOCK, SMEM)                                                                       \
-    (p.scheme == kSchemeCic ? op_launch(KERNEL<GG, false, kSchemeCic>, c, D, op_grid(c, p.np, 8 * GG, MINB, BLOCK), BLOCK, SMEM)     \
-     : p.full             ? op_launch(KERNEL<GG, true, kSchemeM6>, c, D, op_grid(c, p.np, 8 * GG, MINB, BLOCK), BLOCK, SMEM)       \
-                          : op_launch(KERNEL<GG, false, kSchemeM6>, c, D, op_grid(c, p.np, 8 * GG, MINB, BLOCK), BLOCK, SMEM))
-#define UAPIC_OP_DISPATCH(KERNEL, MINB, BLOCK, SMEM)                  \
+#define COMMA_TRUE , true
+#define COMMA_FALSE , false
+#define UAPIC_OP_LAUNCH(KERNEL, GG, MINB, BLOCK, SMEM, ...)                                                                       \
+    (p.scheme == kSchemeCic ? op_launch(KERNEL<GG, false, kSchemeCic __VA_ARGS__>, c, D, op_grid(c, p.np, 8 * GG, MINB, BLOCK), BLOCK, SMEM)     \
+     : p.full             ? op_launch(KERNEL<GG, true, kSchemeM6 __VA_ARGS__>, c, D, op_grid(c, p.np, 8 * GG, MINB, BLOCK), BLOCK, SMEM)       \
+                          : op_launch(KERNEL<GG, false, kSchemeM6 __VA_ARGS__>, c, D, op_grid(c, p.np, 8 * GG, MINB, BLOCK), BLOCK, SMEM))
+#define UAPIC_OP_DISPATCH(KERNEL, MINB, BLOCK, SMEM, ...)                  \
     if (p.scheme == kSchemeCic && p.full) return cudaErrorInvalidValue; \
     switch (p.ntau) {                                                 \
-        case 8:  return UAPIC_OP_LAUNCH(KERNEL, 1, MINB, BLOCK, SMEM); \
-        case 16: return UAPIC_OP_LAUNCH(KERNEL, 2, MINB, BLOCK, SMEM); \
-        case 32: return UAPIC_OP_LAUNCH(KERNEL, 4, MINB, BLOCK, SMEM); \
+        case 8:  return UAPIC_OP_LAUNCH(KERNEL, 1, MINB, BLOCK, SMEM, __VA_ARGS__); \
+        case 16: return UAPIC_OP_LAUNCH(KERNEL, 2, MINB, BLOCK, SMEM, __VA_ARGS__); \
+        case 32: return UAPIC_OP_LAUNCH(KERNEL, 4, MINB, BLOCK, SMEM, __VA_ARGS__); \
         default: return cudaErrorInvalidValue;                        \
     }
 
@@ -872,7 +943,11 @@ cudaError_t launch_onepass_a(const LaunchCtx &c, const OnepassParams &p) {
     if (p.m.nx < 4 || p.m.ny < 4) return cudaErrorInvalidValue;
     const OpDev D = make_opdev(p);
     const size_t smem = sizeof(double2) * (size_t)(kTab + (kOpBlockA / 32) * kWarpSmA);
-    UAPIC_OP_DISPATCH(k_onepass_a, UAPIC_OP_MINB_A, kOpBlockA, smem)
+    if (p.fuse_b) {
+        if (p.full || !p.ehalo_b) return cudaErrorInvalidValue;      // the fused kernel exists for the lean layout only
+        UAPIC_OP_DISPATCH(k_onepass_a, UAPIC_OP_MINB_A, kOpBlockA, smem, COMMA_TRUE)
+    }
+    UAPIC_OP_DISPATCH(k_onepass_a, UAPIC_OP_MINB_A, kOpBlockA, smem, COMMA_FALSE)
 }
 
 cudaError_t launch_onepass_b(const LaunchCtx &c, const OnepassParams &p) {
@@ -880,7 +955,7 @@ cudaError_t launch_onepass_b(const LaunchCtx &c, const OnepassParams &p) {
     if (p.m.nx < 4 || p.m.ny < 4) return cudaErrorInvalidValue;
     const OpDev D = make_opdev(p);
     const size_t smem = sizeof(double2) * (size_t)(kTab + (kOpBlockB / 32) * kWarpSmB);
-    UAPIC_OP_DISPATCH(k_onepass_b, UAPIC_OP_MINB_B, kOpBlockB, smem)
+    UAPIC_OP_DISPATCH(k_onepass_b, UAPIC_OP_MINB_B, kOpBlockB, smem, )
 }
 
 }  // namespace uapic

@@ -93,6 +93,10 @@ class Session:
         """reorder the particle arrays by coarse mesh bin every `interval` steps (0 = never); invisible to the caller"""
         check(lib().uapic_session_set_sort(self._h, C.c_int(interval), C.c_int(bin_cells_log2)))
 
+    def set_fusion(self, enable: bool = True):
+        """run phase B of a step inside the first kernel of the next one (lean one-pass layout); results do not change"""
+        check(lib().uapic_session_set_fusion(self._h, C.c_int(int(enable))))
+
     def enable_timing(self, enable: bool = True):
         check(lib().uapic_session_enable_timing(self._h, C.c_int(int(enable))))
 
