@@ -15,7 +15,9 @@
  *    uapic_last_error() gives the message of the last failure on the calling thread.
  *  - there is NO CPU fallback: without a CUDA device every compute entry point fails with
  *    UAPIC_ENODEVICE.
- *  - ntau must be a power of two in [2, 32] (one tau sample per lane of a warp).
+ *  - ntau: any even number in [2, 256], as in the reference (ua_type.F90:32-76).  Powers of two <= 32 run on the fast kernels
+ *    (one tau sample per lane; 8, 16, 32 also on the one-pass kernels); every other even ntau runs on general kernels
+ *    (one warp per particle, direct DFTs) behind the same entry points -- complete, not fast; sessions need UAPIC_STORE_FULL.
  *  - stage functions are synchronous (H2D, kernel, D2H inside the call); the session API keeps
  *    all state resident in HBM and is the performance path.
  */
@@ -151,7 +153,7 @@ typedef struct uapic_session uapic_session_t;
 
 typedef struct uapic_config {
     uapic_mesh_t mesh;
-    int32_t ntau;            /* power of two, 2..32 */
+    int32_t ntau;            /* even, 2..256; powers of two <= 32 are the fast ones */
     int32_t wrap;            /* UAPIC_WRAP_*          */
     int32_t deposit_mode;    /* UAPIC_DEPOSIT_*       */
     int32_t scheme;          /* UAPIC_SCHEME_*        */

@@ -191,3 +191,31 @@ def test_phase_fusion_then_step_host():
     a, b = run(False), run(True)
     for u, w in zip(a, b):
         assert np.array_equal(u, w)
+
+
+@pytest.mark.parametrize("ntau,eps,wrap", [(12, 0.1, "fortran"), (64, 0.1, "fortran"), (20, 1e-3, "julia"), (6, 0.1, "fortran")])
+def test_any_even_ntau_session_vs_oracle(corc, ntau, eps, wrap):
+    """the reference takes any even ntau (FFTW plans, ua_type.F90:32-76): sessions with ntau outside {2, 4, 8, 16, 32} run the
+    literal call sequence of bupdate.F90:97-123 on the general kernels (uapic_generic.cu) -- same 1e-10 parity"""
+    npart, nstep = 3001, 4
+    om, x0, v0 = seeded_load(npart, nx=64, ny=32, seed=40 + ntau)
+    mesh = ub.Mesh(0, DIMX, 64, 0, DIMY, 32)
+    w = DIMX * DIMY / npart
+    ow, gw = (oracle.WRAP_JULIA, ub.WRAP_JULIA) if wrap == "julia" else (oracle.WRAP_FORTRAN, ub.WRAP_FORTRAN)
+    xo, vo = x0.copy(order="F"), v0.copy(order="F")
+    eno, _, _, emo = corc.run_bupdate(om, ntau, eps, DT, nstep, xo, vo, w, wrap=ow)
+    x, v, en, em = ub.run_bupdate(mesh, ntau, eps, DT, nstep, x0, v0, w, wrap=gw)
+    assert np.abs(np.mod(x[0] - xo[0] + DIMX / 2, DIMX) - DIMX / 2).max() < 1e-10 * DIMX
+    assert np.abs(np.mod(x[1] - xo[1] + DIMY / 2, DIMY) - DIMY / 2).max() < 1e-10 * DIMY
+    assert np.abs(v - vo).max() < 1e-12 * max(1.0, 0.1 / eps) * np.abs(vo).max()
+    assert np.abs(en - eno).max() < 1e-10 * np.abs(eno).max()
+    assert np.abs(em - emo).max() < 1e-10 * np.abs(emo).max()
+
+
+def test_unsupported_ntau_fails_loudly():
+    mesh = ub.Mesh(0, DIMX, 32, 0, DIMY, 32)
+    for bad in (7, 258, 0):
+        with pytest.raises((ub.UapicError, ValueError)):
+            ub.Session(mesh, bad, 0.1, DT, 100)
+    with pytest.raises(ub.UapicError):                    # general kernels exist for the two-barrier storage only
+        ub.Session(mesh, 12, 0.1, DT, 100, storage_mode=ub.STORE_ONEPASS_LEAN)

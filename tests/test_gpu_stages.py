@@ -178,7 +178,8 @@ def test_fft_tau(corc, ntau):
     assert np.abs(b - a).max() < 1e-14
 
 
-@pytest.mark.parametrize("ntau,eps", [(16, 0.1), (32, 0.1), (8, 0.1), (16, 1e-3)])
+@pytest.mark.parametrize("ntau,eps", [(16, 0.1), (32, 0.1), (8, 0.1), (16, 1e-3),
+                                      (6, 0.1), (12, 0.1), (20, 1e-2), (48, 0.1), (64, 0.1), (250, 0.1)])    # general kernels (uapic_generic.cu)
 def test_stage_chain_vs_oracle(corc, ntau, eps):
     """preparation -> gather -> compute_f -> ua_step1 x2 -> deposit -> gather -> compute_f -> ua_step2 x2 -> deposit -> compute_v,
     each GPU stage fed with the ORACLE's inputs so errors do not accumulate across stages"""

@@ -84,8 +84,8 @@ class UA:
     """src/ua_type.jl:3-41 (the FFTW plans are replaced by the library's warp-shuffle FFT)"""
 
     def __init__(self, ntau: int, eps: float, nbpart: int, wrap=_lib.WRAP_JULIA, deposit_mode=_lib.DEPOSIT_FP64_ATOMIC):
-        if ntau not in (2, 4, 8, 16, 32):
-            raise ValueError("ntau must be a power of two in [2, 32]")
+        if ntau % 2 or not 2 <= ntau <= 256:
+            raise ValueError("ntau must be even and in [2, 256] (powers of two <= 32 run on the fast kernels)")
         self.ntau = int(ntau)
         self.eps = float(eps)
         dtau = 2 * np.pi / ntau

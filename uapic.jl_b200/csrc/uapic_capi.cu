@@ -75,7 +75,8 @@ MeshDev make_mesh(const uapic_mesh_t *mesh) {
 }
 
 int check_ntau(int ntau) {
-    if (!ntau_supported(ntau)) return fail(UAPIC_EINVAL, "ntau must be a power of two in [2,32] (got %d)", ntau);
+    if (!ntau_supported(ntau) && !generic_ntau_supported(ntau))
+        return fail(UAPIC_EINVAL, "ntau must be even and in [2,%d] (got %d)", kGenericMaxNtau, ntau);
     return UAPIC_OK;
 }
 
@@ -498,6 +499,8 @@ struct uapic_session {
     int64_t np_global = 0;
     DevBuf x, v, ep, store, tb, raw, rho, emesh, ehalo, rk, ek, energy, sumv;
     DevBuf rec, emesh_p, ehalo_p;     // one-pass modes: per-particle record, predictor field
+    DevBuf gb, gt, gpl, gql, gxt, gyt, gxf, gyf, gfx, gfy, ggx, ggy, get;   // generic-ntau sessions: the reference's own arrays (uapic_generic.cu)
+    bool generic = false;
     DevBuf rho_p, rk2, ek2, solve_scratch;   // second work set + scratch of the batched one-launch field solve (k_field_solve)
     bool split_solve = false;          // $UAPIC_SPLIT_SOLVE=1: the six separate kernels per solve (A/B measurement, stage-API kernels)
     RhoAcc acc{};
@@ -749,6 +752,9 @@ int uapic_session_create(const uapic_config_t *cfg, uapic_session_t **out) {
     const bool onepass = cfg->storage_mode == UAPIC_STORE_ONEPASS || cfg->storage_mode == UAPIC_STORE_ONEPASS_LEAN;
     if (cfg->storage_mode != UAPIC_STORE_FULL && cfg->storage_mode != UAPIC_STORE_HYBRID && !onepass) return fail(UAPIC_EINVAL, "unknown storage_mode %d", cfg->storage_mode);
     if (onepass && !onepass_ntau_supported(cfg->ntau)) return fail(UAPIC_EUNSUPPORTED, "the one-pass storage modes need ntau = 8, 16 or 32 (got %d)", cfg->ntau);
+    const bool generic = !ntau_supported(cfg->ntau);
+    if (generic && (cfg->storage_mode != UAPIC_STORE_FULL || cfg->scheme != UAPIC_SCHEME_M6))
+        return fail(UAPIC_EUNSUPPORTED, "ntau = %d runs on the general one-warp-per-particle kernels: UAPIC_STORE_FULL and UAPIC_SCHEME_M6 only", cfg->ntau);
     if (cfg->wrap != UAPIC_WRAP_FORTRAN && cfg->wrap != UAPIC_WRAP_JULIA) return fail(UAPIC_EINVAL, "unknown wrap %d", cfg->wrap);
     if (!poisson_size_supported(cfg->mesh.nx) || !poisson_size_supported(cfg->mesh.ny) || cfg->mesh.nx < 4 || cfg->mesh.ny < 4)
         return fail(UAPIC_EUNSUPPORTED, "session mesh %d x %d unsupported (need 4 <= n, powers of two <= 1024 or any n <= 512)", cfg->mesh.nx, cfg->mesh.ny);
@@ -779,9 +785,21 @@ int uapic_session_create(const uapic_config_t *cfg, uapic_session_t **out) {
     s->sort_interval = onepass ? 1 : 0;
     s->sort_shift = 3;
     while (sort_bins(s->m, s->sort_shift) > 4096) s->sort_shift++;
-    if (!rc && !onepass) rc = session_alloc(s, s->tb, 16 * (np ? np : 1));
+    s->generic = generic;
+    if (!rc && !onepass && !generic) rc = session_alloc(s, s->tb, 16 * (np ? np : 1));
     const size_t per_tau = onepass ? (cfg->storage_mode == UAPIC_STORE_ONEPASS ? 72 : 48) : (cfg->storage_mode == UAPIC_STORE_HYBRID ? 16 : 128);
-    if (!rc) rc = session_alloc(s, s->store, per_tau * N * (np ? np : 1));
+    if (!rc && !generic) rc = session_alloc(s, s->store, per_tau * N * (np ? np : 1));
+    if (generic) {
+        // the reference's own working set (bupdate.F90:79-87): b, t, pl, ql, xt, xf, yt, yf, fx, fy, gx, gy, et
+        const size_t n1 = np ? np : 1, big = 32 * N * n1;
+        if (!rc) rc = session_alloc(s, s->gb, 8 * n1);
+        if (!rc) rc = session_alloc(s, s->gt, 8 * n1);
+        if (!rc) rc = session_alloc(s, s->gpl, 16 * N * n1);
+        if (!rc) rc = session_alloc(s, s->gql, 16 * N * n1);
+        for (DevBuf *b : {&s->gxt, &s->gyt, &s->gxf, &s->gyf, &s->gfx, &s->gfy, &s->ggx, &s->ggy})
+            if (!rc) rc = session_alloc(s, *b, big);
+        if (!rc) rc = session_alloc(s, s->get, 16 * N * n1);
+    }
     if (!rc) rc = session_alloc(s, s->raw, 8 * nrho * (onepass ? 2 * UAPIC_RAW_COPIES : 1));
     if (onepass) {
         if (!rc) rc = session_alloc(s, s->rec, 64 * (np ? np : 1));
@@ -1059,6 +1077,35 @@ int uapic_session_step(uapic_session_t *s, int nsteps) {
                 CU(launch_onepass_b(s->lc, op));                           // :110-115 (y part), :123
             }
             if (s->timing) CU(cudaEventRecord(e4[3], s->lc.stream));
+            continue;
+        }
+        if (s->generic) {
+            // any even ntau: the literal call sequence of bupdate.F90:97-123 on the reference-shaped arrays (uapic_generic.cu)
+            const int N = s->cfg.ntau;
+            const double eps = s->cfg.eps;
+            const int64_t np = s->cfg.nbpart;
+            double *b = s->gb.as<double>(), *t = s->gt.as<double>(), *pl = s->gpl.as<double>(), *ql = s->gql.as<double>();
+            double *xt = s->gxt.as<double>(), *yt = s->gyt.as<double>(), *xf = s->gxf.as<double>(), *yf = s->gyf.as<double>();
+            double *fx = s->gfx.as<double>(), *fy = s->gfy.as<double>(), *gx = s->ggx.as<double>(), *gy = s->ggy.as<double>(), *et = s->get.as<double>();
+            if (s->timing) CU(cudaEventRecord(e4[0], s->lc.stream));
+            CU(launch_preparation(s->lc, N, eps, s->cfg.dt, np, s->x.as<double>(), s->v.as<double>(), s->ep.as<double>(), b, t, pl, ql, xt, yt));   // :97
+            CU(launch_gather_tau(s->lc, s->m, s->emesh.as<double>(), N, np, xt, et, s->cfg.wrap));                                   // :99
+            CU(launch_compute_f(s->lc, N, eps, np, b, xt, yt, et, fx, fy, 1));                                                      // :101
+            CU(launch_step_fortran(s->lc, N, eps, np, t, pl, nullptr, xt, xf, fx, nullptr, 0));                                     // :103
+            CU(launch_step_fortran(s->lc, N, eps, np, t, pl, nullptr, yt, yf, fy, nullptr, 0));                                     // :104
+            CU(launch_deposit_tau(s->lc, s->m, N, eps, np, xt, t, s->cfg.weight, s->acc, s->x.as<double>(), s->cfg.wrap));          // :106
+            if (s->timing) CU(cudaEventRecord(e4[1], s->lc.stream));
+            TRY(session_field_solve(s));                                                                                            // :108
+            TRY(session_clear_raw(s));
+            if (s->timing) CU(cudaEventRecord(e4[2], s->lc.stream));
+            CU(launch_gather_tau(s->lc, s->m, s->emesh.as<double>(), N, np, xt, et, s->cfg.wrap));                                   // :110
+            CU(launch_compute_f(s->lc, N, eps, np, b, xt, yt, et, gx, gy, 1));                                                      // :112
+            CU(launch_step_fortran(s->lc, N, eps, np, t, pl, ql, xt, xf, fx, gx, 1));                                               // :114
+            CU(launch_step_fortran(s->lc, N, eps, np, t, pl, ql, yt, yf, fy, gy, 1));                                               // :115
+            CU(launch_deposit_tau(s->lc, s->m, N, eps, np, xt, t, s->cfg.weight, s->acc, s->x.as<double>(), s->cfg.wrap));          // :117
+            CU(launch_compute_v(s->lc, N, eps, np, t, yt, 0, s->v.as<double>()));                                                   // :123 (needs no field)
+            if (s->timing) CU(cudaEventRecord(e4[3], s->lc.stream));
+            TRY(session_field_solve(s));                                                                                            // :119
             continue;
         }
         if (s->timing) CU(cudaEventRecord(e4[0], s->lc.stream));

@@ -14,7 +14,21 @@ struct LaunchCtx {
     int64_t *launches;   // host counter, may be null
 };
 
-inline bool ntau_supported(int ntau) { return ntau == 2 || ntau == 4 || ntau == 8 || ntau == 16 || ntau == 32; }
+inline bool ntau_supported(int ntau) { return ntau == 2 || ntau == 4 || ntau == 8 || ntau == 16 || ntau == 32; }   // the fast lane-per-sample kernels
+// any other even ntau up to this goes to the one-warp-per-particle kernels of uapic_generic.cu (direct DFTs): complete, not fast
+constexpr int kGenericMaxNtau = 256;
+bool generic_ntau_supported(int ntau);
+cudaError_t launch_preparation_generic(const LaunchCtx &c, int ntau, double eps, double dt, int64_t np, const double *x, const double *v,
+                                       const double *e, double *b, double *t, double *pl, double *ql, double *xt, double *yt);
+cudaError_t launch_compute_f_generic(const LaunchCtx &c, int ntau, double eps, int64_t np, const double *b, const double *xt, const double *yt,
+                                     const double *et, double *fx, double *fy, int normalise);
+cudaError_t launch_fft_tau_generic(const LaunchCtx &c, int ntau, int64_t nvec, const double *in, double *out, int sign, int normalise);
+cudaError_t launch_step_fortran_generic(const LaunchCtx &c, int ntau, double eps, int64_t np, const double *t, const double *pl,
+                                        const double *ql, double *xt, double *xf, const double *fx, const double *gx, int corrector);
+cudaError_t launch_deposit_tau_generic(const LaunchCtx &c, const MeshDev &m, int ntau, double eps, int64_t np, const double *xt,
+                                       const double *t, double w, const RhoAcc &acc, double *x, int wrap);
+cudaError_t launch_compute_v_generic(const LaunchCtx &c, int ntau, double eps, int64_t np, const double *t, const double *yt,
+                                     int yt_is_fourier, double *v);
 
 // ---- stage kernels (reference-shaped arrays, natural-order Fourier arrays) ----------------------------------
 cudaError_t launch_preparation(const LaunchCtx &c, int ntau, double eps, double dt, int64_t np, const double *x,

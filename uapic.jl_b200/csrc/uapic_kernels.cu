@@ -890,6 +890,7 @@ cudaError_t launch_preparation(const LaunchCtx &c, int ntau, double eps, double 
                                const double *v, const double *e, double *b, double *t, double *pl, double *ql,
                                double *xt, double *yt) {
     if (np <= 0) return cudaSuccess;
+    if (!ntau_supported(ntau)) return generic_ntau_supported(ntau) ? launch_preparation_generic(c, ntau, eps, dt, np, x, v, e, b, t, pl, ql, xt, yt) : cudaErrorInvalidValue;
     UAPIC_DISPATCH_N(ntau, (k_preparation<N><<<grid_for(c, np, (kBlock / 32) * (32 / N)), kBlock, 0, c.stream>>>(
                                eps, dt, np, x, v, e, b, t, pl, ql, xt, yt)));
     count(c);
@@ -908,6 +909,7 @@ cudaError_t launch_gather_tau(const LaunchCtx &c, const MeshDev &m, const double
 cudaError_t launch_compute_f(const LaunchCtx &c, int ntau, double eps, int64_t np, const double *b, const double *xt,
                              const double *yt, const double *et, double *fx, double *fy, int normalise) {
     if (np <= 0) return cudaSuccess;
+    if (!ntau_supported(ntau)) return generic_ntau_supported(ntau) ? launch_compute_f_generic(c, ntau, eps, np, b, xt, yt, et, fx, fy, normalise) : cudaErrorInvalidValue;
     UAPIC_DISPATCH_N(ntau, (k_compute_f<N><<<grid_for(c, np, (kBlock / 32) * (32 / N)), kBlock, 0, c.stream>>>(
                                eps, np, b, xt, yt, et, fx, fy, normalise)));
     count(c);
@@ -917,6 +919,7 @@ cudaError_t launch_compute_f(const LaunchCtx &c, int ntau, double eps, int64_t n
 cudaError_t launch_fft_tau(const LaunchCtx &c, int ntau, int64_t nvec, const double *in, double *out, int sign,
                            int normalise) {
     if (nvec <= 0) return cudaSuccess;
+    if (!ntau_supported(ntau)) return generic_ntau_supported(ntau) ? launch_fft_tau_generic(c, ntau, nvec, in, out, sign, normalise) : cudaErrorInvalidValue;
     UAPIC_DISPATCH_N(ntau, (k_fft_tau<N><<<grid_for(c, nvec, (kBlock / 32) * (32 / N)), kBlock, 0, c.stream>>>(nvec, in, out, sign,
                                                                                                            normalise)));
     count(c);
@@ -936,6 +939,7 @@ cudaError_t launch_step_fortran(const LaunchCtx &c, int ntau, double eps, int64_
                                 const double *pl, const double *ql, double *xt, double *xf, const double *fx,
                                 const double *gx, int corrector) {
     if (np <= 0) return cudaSuccess;
+    if (!ntau_supported(ntau)) return generic_ntau_supported(ntau) ? launch_step_fortran_generic(c, ntau, eps, np, t, pl, ql, xt, xf, fx, gx, corrector) : cudaErrorInvalidValue;
     UAPIC_DISPATCH_N(ntau, (k_step_fortran<N><<<grid_for(c, np, (kBlock / 32) * (32 / N)), kBlock, 0, c.stream>>>(
                                eps, np, t, pl, ql, xt, xf, fx, gx, corrector)));
     count(c);
@@ -945,6 +949,7 @@ cudaError_t launch_step_fortran(const LaunchCtx &c, int ntau, double eps, int64_
 cudaError_t launch_deposit_tau(const LaunchCtx &c, const MeshDev &m, int ntau, double eps, int64_t np,
                                const double *xt, const double *t, double w, const RhoAcc &acc, double *x, int wrap) {
     if (np <= 0) return cudaSuccess;
+    if (!ntau_supported(ntau)) return generic_ntau_supported(ntau) ? launch_deposit_tau_generic(c, m, ntau, eps, np, xt, t, w, acc, x, wrap) : cudaErrorInvalidValue;
     UAPIC_DISPATCH_N(ntau, (k_deposit_tau<N><<<grid_for(c, np, (kBlock / 32) * (32 / N)), kBlock, 0, c.stream>>>(m, eps, np, xt, t, w,
                                                                                                            acc, x, wrap)));
     count(c);
@@ -954,6 +959,7 @@ cudaError_t launch_deposit_tau(const LaunchCtx &c, const MeshDev &m, int ntau, d
 cudaError_t launch_compute_v(const LaunchCtx &c, int ntau, double eps, int64_t np, const double *t, const double *yt,
                              int yt_is_fourier, double *v) {
     if (np <= 0) return cudaSuccess;
+    if (!ntau_supported(ntau)) return generic_ntau_supported(ntau) ? launch_compute_v_generic(c, ntau, eps, np, t, yt, yt_is_fourier, v) : cudaErrorInvalidValue;
     UAPIC_DISPATCH_N(ntau, (k_compute_v<N><<<grid_for(c, np, (kBlock / 32) * (32 / N)), kBlock, 0, c.stream>>>(eps, np, t, yt,
                                                                                                          yt_is_fourier, v)));
     count(c);
