@@ -40,6 +40,8 @@
 #include <omp.h>
 #endif
 
+#define ORC_MAX_NTAU 256   /* stack arrays of the per-particle tau loops */
+
 typedef struct { double re, im; } cplx;
 
 static inline cplx c_make(double re, double im) { cplx z = { re, im }; return z; }
@@ -455,7 +457,7 @@ static void dep_tau_body(int64_t k, double *rho, void *vctx)
 {
     dep_tau_ctx *c = (dep_tau_ctx *)vctx;
     const int N = c->ntau;
-    cplx ft[64];
+    cplx ft[ORC_MAX_NTAU];
     double pos[2];
     const double t = c->t[k];
     for (int comp = 0; comp < 2; comp++) {
@@ -478,8 +480,8 @@ static void dep_tau_body(int64_t k, double *rho, void *vctx)
 double orc_compute_rho_m6_tau(const orc_mesh *m, int ntau, double eps, int64_t np, const double *xt,
                               const double *t, double w, double *rho, double *x, int wrap)
 {
-    double tau[64], ltau[64];
-    if (ntau > 64) return NAN;
+    double tau[ORC_MAX_NTAU], ltau[ORC_MAX_NTAU];
+    if (ntau > ORC_MAX_NTAU) return NAN;
     orc_ua_tables(ntau, tau, ltau);
     orc_fft_plan *plan = orc_fft_new(ntau);
     dep_tau_ctx c = { m, ntau, eps, (const cplx *)xt, t, x, w, wrap, ltau, plan, mesh_dx(m), mesh_dy(m) };
@@ -569,14 +571,14 @@ void orc_preparation(int ntau, double eps, double dt, int64_t np, const double *
                      double *b_out, double *t_out, double *pl_, double *ql_, double *xt_, double *yt_)
 {
     const int N = ntau;
-    double tau[64], ltau[64];
+    double tau[ORC_MAX_NTAU], ltau[ORC_MAX_NTAU];
     orc_ua_tables(N, tau, ltau);
     cplx *PL = (cplx *)pl_, *QL = (cplx *)ql_, *XT = (cplx *)xt_, *YT = (cplx *)yt_;
 
     #pragma omp parallel if (g_threads > 1)
     {
     orc_fft_plan *plan = orc_fft_new(N);
-    cplx rt[2][64], rf[2][64];
+    cplx rt[2][ORC_MAX_NTAU], rf[2][ORC_MAX_NTAU];
     #pragma omp for schedule(static)
     for (int64_t m = 0; m < np; m++) {
         double x1 = x[2 * m], x2 = x[2 * m + 1];                                  /* :51-52 */
@@ -651,7 +653,7 @@ void orc_compute_f(int ntau, double eps, int64_t np, const double *b_, const dou
                    const double *et, double *fx_, double *fy_, int normalise)
 {
     const int N = ntau;
-    double tau[64], ltau[64];
+    double tau[ORC_MAX_NTAU], ltau[ORC_MAX_NTAU];
     orc_ua_tables(N, tau, ltau);
     const cplx *XT = (const cplx *)xt_, *YT = (const cplx *)yt_;
     cplx *FX = (cplx *)fx_, *FY = (cplx *)fy_;
@@ -696,14 +698,14 @@ void orc_ua_step1(int ntau, double eps, int64_t np, const double *t_, const doub
                   const double *fx_)
 {
     const int N = ntau;
-    double tau[64], ltau[64];
+    double tau[ORC_MAX_NTAU], ltau[ORC_MAX_NTAU];
     orc_ua_tables(N, tau, ltau);
     const cplx *PL = (const cplx *)pl_, *FX = (const cplx *)fx_;
     cplx *XT = (cplx *)xt_, *XF = (cplx *)xf_;
     #pragma omp parallel if (g_threads > 1)
     {
     orc_fft_plan *plan = orc_fft_new(N);
-    cplx rf[2][64];
+    cplx rf[2][ORC_MAX_NTAU];
     #pragma omp for schedule(static)
     for (int64_t m = 0; m < np; m++) {
         cplx *x1 = XT + (size_t)N * (0 + 2 * m), *x2 = XT + (size_t)N * (1 + 2 * m);
@@ -734,7 +736,7 @@ void orc_ua_step2(int ntau, double eps, int64_t np, const double *t_, const doub
                   double *xt_, const double *xf_, const double *fx_, const double *gx_)
 {
     const int N = ntau;
-    double tau[64], ltau[64];
+    double tau[ORC_MAX_NTAU], ltau[ORC_MAX_NTAU];
     orc_ua_tables(N, tau, ltau);
     const cplx *PL = (const cplx *)pl_, *QL = (const cplx *)ql_, *FX = (const cplx *)fx_, *GX = (const cplx *)gx_;
     const cplx *XF = (const cplx *)xf_;
@@ -742,7 +744,7 @@ void orc_ua_step2(int ntau, double eps, int64_t np, const double *t_, const doub
     #pragma omp parallel if (g_threads > 1)
     {
     orc_fft_plan *plan = orc_fft_new(N);
-    cplx rf[2][64];
+    cplx rf[2][ORC_MAX_NTAU];
     #pragma omp for schedule(static)
     for (int64_t m = 0; m < np; m++) {
         double t = t_[m];                                                         /* :254 */
@@ -772,7 +774,7 @@ void orc_ua_step2(int ntau, double eps, int64_t np, const double *t_, const doub
 void orc_compute_v(int ntau, double eps, int64_t np, const double *t_, const double *yt_, double *yf_, double *v)
 {
     const int N = ntau;
-    double tau[64], ltau[64];
+    double tau[ORC_MAX_NTAU], ltau[ORC_MAX_NTAU];
     orc_ua_tables(N, tau, ltau);
     const cplx *YT = (const cplx *)yt_;
     cplx *YF = (cplx *)yf_;
@@ -824,7 +826,7 @@ void orc_sim_destroy(orc_sim *s)
 orc_sim *orc_sim_create(const orc_mesh *m, int ntau, double eps, double dt, int64_t np, double w, double *x, double *v,
                         int wrap, int faithful)
 {
-    if (ntau > 64) return NULL;
+    if (ntau > ORC_MAX_NTAU) return NULL;
     orc_sim *s = (orc_sim *)calloc(1, sizeof(orc_sim));
     if (!s) return NULL;
     s->m = *m; s->ntau = ntau; s->eps = eps; s->dt = dt; s->w = w; s->np = np; s->wrap = wrap; s->faithful = faithful;

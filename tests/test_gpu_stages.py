@@ -271,7 +271,9 @@ def test_stage_chain_vs_oracle(corc, ntau, eps):
 def test_bad_arguments_fail_loudly():
     mesh = ub.Mesh(0, 1, 8, 0, 1, 8)
     with pytest.raises(ValueError):
-        ub.UA(12, 0.1, 10)
+        ub.UA(13, 0.1, 10)                  # odd
+    with pytest.raises(ValueError):
+        ub.UA(258, 0.1, 10)                 # beyond the general kernels
     p = ub.Particles(4, 1.0)
     ua = ub.UA(16, 0.1, 4)
     with pytest.raises(ValueError):
