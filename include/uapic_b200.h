@@ -247,6 +247,55 @@ int uapic_session_launch_count(uapic_session_t *s, int64_t *count);
 /* bytes of HBM the session holds */
 int uapic_session_device_bytes(uapic_session_t *s, int64_t *bytes);
 
+/* ------------------------------------------------------------------------------------------
+ * Sibling scheme: the 3D rotation-push PIC of fortran/uapic3d.f90 --
+ * CIC deposition (compute_rho_cic.f90:11-79), 3D periodic spectral Poisson solve (poisson_3d.f90:47-191),
+ * CIC interpolation (interpolation_cic.f90:10-66), the velocity rotation in the field b(x) of
+ * uapic3d.f90:103-121 and its multi-revolution composition (:131-204).  Arrays are column-major as the
+ * Fortran holds them: x, v, e_particles (3,nbpart); rho (nx+1,ny+1,nz+1); e (3,nx+1,ny+1,nz+1).
+ * The reference's quirks on this path are reproduced (uapic_mrc3d.cu lists them); no CPU fallback.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct uapic3d_mesh {
+    double  xmin[3], xmax[3];        /* meshfields.F90:80-107 */
+    int32_t n[3];
+} uapic3d_mesh_t;
+
+typedef struct uapic3d_config {
+    uapic3d_mesh_t mesh;
+    int64_t nbpart;                  /* particles of THIS session */
+    int64_t nbpart_global;           /* 0 = nbpart (bounds the fixed-point scale) */
+    double  weight;                  /* p%w = dimx*dimy*dimz/nbpart_global (particles.F90:133) */
+    double  ep;                      /* uapic3d.f90:19 (0.5**10) */
+    double  delta;                   /* uapic3d.f90:18 (3e-3): b(x) = (d2, -d1, 1)*delta-scaled / sqrt(1 + r^2 delta^2), centre (9, 9) */
+    int32_t deposit_mode;            /* UAPIC_DEPOSIT_* */
+    int32_t index_quirk;             /* 1: reproduce p%x(m,1) of uapic3d.f90:179,182 (the reference's behaviour); 0: x(1,m) */
+    int32_t device;
+    void   *stream;
+} uapic3d_config_t;
+
+typedef struct uapic3d_session uapic3d_session_t;
+
+int uapic3d_create(const uapic3d_config_t *cfg, uapic3d_session_t **out);
+int uapic3d_destroy(uapic3d_session_t *s);
+int uapic3d_upload_particles(uapic3d_session_t *s, const double *x, const double *v);
+/* init_particles_3d densities (particles.F90:152-190) from a counter-based stream keyed by first_global_index + k */
+int uapic3d_generate_particles(uapic3d_session_t *s, uint64_t seed, int64_t first_global_index);
+/* compute_rho_cic -> solve_poisson -> interpolate_eb_cic                         uapic3d.f90:76-83 */
+int uapic3d_init_fields(uapic3d_session_t *s);
+/* `count` sub-steps: push(dt/2) -> deposit -> Poisson -> interpolate -> rotate -> push(dt/2).
+   kind 0: uapic3d.f90:93-127 (coef unused); kind 1: :133-165, coef = alpha; kind 2: :167-200, coef = beta */
+int uapic3d_substep(uapic3d_session_t *s, int kind, double dt, double coef, int count);
+/* the time loop of uapic3d.f90:44-61, :91-206 (branch on N0mrc = nint(tfinal/ep/2pi/Nmrc)); max_outer > 0 caps the number of
+   outer iterations (steps of the first branch, istep of the MRC branch); *substeps = sub-steps performed */
+int uapic3d_run(uapic3d_session_t *s, int nmrc, int nmrcm, double tfinal, int max_outer, int64_t *substeps);
+int uapic3d_download_particles(uapic3d_session_t *s, double *x, double *v, double *e_particles);
+int uapic3d_download_fields(uapic3d_session_t *s, double *e, double *rho);
+int uapic3d_launch_count(uapic3d_session_t *s, int64_t *count);
+/* stage functions (host buffers, synchronous): the three module routines the Fortran tests call (test_pic_3d.f90, test_poisson_3d.f90) */
+int uapic3d_compute_rho_cic(const uapic3d_mesh_t *mesh, int64_t nbpart, const double *x, double w, double *rho);
+int uapic3d_poisson(const uapic3d_mesh_t *mesh, const double *rho, double *e);
+int uapic3d_interpolate_eb_cic(const uapic3d_mesh_t *mesh, const double *e, int64_t nbpart, const double *x, double *e_particles);
+
 #ifdef __cplusplus
 }
 #endif

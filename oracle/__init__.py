@@ -247,3 +247,61 @@ def corc() -> _COracle:
     if _corc is None:
         _corc = _COracle()
     return _corc
+
+
+# ---- sibling scheme: the 3D rotation-push PIC of fortran/uapic3d.f90 (uapic_oracle.c, orc3_*) ---------------------------
+class Orc3Mesh(C.Structure):
+    _fields_ = [("xmin", C.c_double * 3), ("xmax", C.c_double * 3), ("n", C.c_int32 * 3)]
+
+
+def mesh3(xmin, xmax, n) -> Orc3Mesh:
+    return Orc3Mesh((C.c_double * 3)(*map(float, xmin)), (C.c_double * 3)(*map(float, xmax)), (C.c_int32 * 3)(*map(int, n)))
+
+
+class _COracle3:
+    """arrays: x, v, e_part (3, np); rho (nx+1, ny+1, nz+1); e (3, nx+1, ny+1, nz+1), Fortran order"""
+
+    def __init__(self):
+        self.lib = corc().lib
+        self.lib.orc3_run.restype = C.c_int64
+
+    def compute_rho_cic(self, m, x, w):
+        rho = np.zeros((m.n[0] + 1, m.n[1] + 1, m.n[2] + 1), order="F")
+        self.lib.orc3_compute_rho_cic(C.byref(m), C.c_int64(x.shape[1]), _p(x), C.c_double(w), _p(rho))
+        return rho
+
+    def poisson(self, m, rho):
+        e = np.zeros((3, m.n[0] + 1, m.n[1] + 1, m.n[2] + 1), order="F")
+        self.lib.orc3_poisson(C.byref(m), _p(rho), _p(e))
+        return e
+
+    def interpolate_eb_cic(self, m, e, x):
+        ep = np.zeros((3, x.shape[1]), order="F")
+        self.lib.orc3_interpolate_eb_cic(C.byref(m), _p(e), C.c_int64(x.shape[1]), _p(x), _p(ep))
+        return ep
+
+    def generate(self, m, seed, npart, first=0):
+        x = np.zeros((3, npart), order="F")
+        v = np.zeros((3, npart), order="F")
+        self.lib.orc3_generate(C.byref(m), C.c_uint64(seed), C.c_int64(first), C.c_int64(npart), _p(x), _p(v))
+        return x, v
+
+    def run(self, m, x, v, w, ep, delta, nmrc, nmrcm, tfinal, max_outer=0, index_quirk=1):
+        """x, v updated in place; returns (substeps, e_part, e, rho)"""
+        npart = x.shape[1]
+        epart = np.zeros((3, npart), order="F")
+        e = np.zeros((3, m.n[0] + 1, m.n[1] + 1, m.n[2] + 1), order="F")
+        rho = np.zeros((m.n[0] + 1, m.n[1] + 1, m.n[2] + 1), order="F")
+        n = self.lib.orc3_run(C.byref(m), C.c_int64(npart), _p(x), _p(v), _p(epart), C.c_double(w), C.c_double(ep), C.c_double(delta),
+                              C.c_int(nmrc), C.c_int(nmrcm), C.c_double(tfinal), C.c_int(max_outer), C.c_int(index_quirk), _p(e), _p(rho))
+        return int(n), epart, e, rho
+
+
+_corc3 = None
+
+
+def corc3() -> _COracle3:
+    global _corc3
+    if _corc3 is None:
+        _corc3 = _COracle3()
+    return _corc3

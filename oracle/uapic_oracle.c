@@ -1014,3 +1014,236 @@ void orc_generate(const orc_mesh *m, int kind, uint64_t seed, int64_t first, int
         v[2 * k] = v1; v[2 * k + 1] = v2;
     }
 }
+
+/* ==================================================================================== */
+/* Sibling scheme: the 3D rotation-push PIC of fortran/uapic3d.f90 */
+/* Statement-by-statement restatement, quirks included (see uapic_mrc3d.cu's header).    */
+/* Arrays: x, v, e_part (3,np); rho (nx+1,ny+1,nz+1); e (3,nx+1,ny+1,nz+1), x fastest.    */
+/* ==================================================================================== */
+
+typedef struct { double xmin[3], xmax[3]; int32_t n[3]; } orc3_mesh;
+
+#define ORC3_NODE(i, j, k) ((size_t)(i) + (size_t)(nx + 1) * ((size_t)(j) + (size_t)(ny + 1) * (size_t)(k)))
+
+/* compute_rho_cic                                   fortran/compute_rho_cic.f90:11-79 */
+void orc3_compute_rho_cic(const orc3_mesh *m, int64_t np, const double *x, double w, double *rho)
+{
+    const int nx = m->n[0], ny = m->n[1], nz = m->n[2];
+    const double dx = (m->xmax[0] - m->xmin[0]) / (double)nx, dy = (m->xmax[1] - m->xmin[1]) / (double)ny, dz = (m->xmax[2] - m->xmin[2]) / (double)nz;
+    const size_t nn = (size_t)(nx + 1) * (ny + 1) * (nz + 1);
+    for (size_t q = 0; q < nn; q++) rho[q] = 0.0;                                   /* :28 */
+    const double vol = w / (dx * dy * dz);                                          /* :30 */
+    for (int64_t p = 0; p < np; p++) {
+        const double xp = x[3 * p] / dx, yp = x[3 * p + 1] / dy, zp = x[3 * p + 2] / dz;   /* :34-36 */
+        int ip = (int)floor(xp), jp = (int)floor(yp), kp = (int)floor(zp);
+        const double dxp = xp - (double)ip, dyp = yp - (double)jp, dzp = zp - (double)kp;
+        const double a1 = (1.0 - dxp) * (1.0 - dyp) * (1.0 - dzp), a2 = dxp * (1.0 - dyp) * (1.0 - dzp);
+        const double a3 = (1.0 - dxp) * dyp * (1.0 - dzp), a4 = dxp * dyp * (1.0 - dzp);
+        const double a5 = (1.0 - dxp) * (1.0 - dyp) * dzp, a6 = dxp * (1.0 - dyp) * dzp;
+        const double a7 = (1.0 - dxp) * dyp * dzp, a8 = dxp * dyp * dzp;
+        /* outside the box the reference is undefined; clamp the cell like the CUDA kernel does (memory safety only) */
+        if (ip < 0) ip = 0;
+        if (ip >= nx) ip = nx - 1;
+        if (jp < 0) jp = 0;
+        if (jp >= ny) jp = ny - 1;
+        if (kp < 0) kp = 0;
+        if (kp >= nz) kp = nz - 1;
+        rho[ORC3_NODE(ip, jp, kp)] += a1 * vol;          rho[ORC3_NODE(ip + 1, jp, kp)] += a2 * vol;          /* :58-65 */
+        rho[ORC3_NODE(ip, jp + 1, kp)] += a3 * vol;      rho[ORC3_NODE(ip + 1, jp + 1, kp)] += a4 * vol;
+        rho[ORC3_NODE(ip, jp, kp + 1)] += a5 * vol;      rho[ORC3_NODE(ip + 1, jp, kp + 1)] += a6 * vol;
+        rho[ORC3_NODE(ip, jp + 1, kp + 1)] += a7 * vol;  rho[ORC3_NODE(ip + 1, jp + 1, kp + 1)] += a8 * vol;
+    }
+    for (int k = 0; k <= nz; k++) for (int j = 0; j <= ny; j++) rho[ORC3_NODE(nx, j, k)] = rho[ORC3_NODE(0, j, k)];   /* :69 */
+    for (int k = 0; k <= nz; k++) for (int i = 0; i <= nx; i++) rho[ORC3_NODE(i, ny, k)] = rho[ORC3_NODE(i, 0, k)];   /* :70 */
+    for (int j = 0; j <= ny; j++) for (int i = 0; i <= nx; i++) rho[ORC3_NODE(i, j, nz)] = rho[ORC3_NODE(i, j, 0)];   /* :71 */
+}
+
+/* interpolate_eb_cic                                fortran/interpolation_cic.f90:10-66 */
+void orc3_interpolate_eb_cic(const orc3_mesh *m, const double *e, int64_t np, const double *x, double *ep)
+{
+    const int nx = m->n[0], ny = m->n[1], nz = m->n[2];
+    const double dx = (m->xmax[0] - m->xmin[0]) / (double)nx, dy = (m->xmax[1] - m->xmin[1]) / (double)ny, dz = (m->xmax[2] - m->xmin[2]) / (double)nz;
+    for (int64_t p = 0; p < np; p++) {
+        const double xp = x[3 * p] / dx, yp = x[3 * p + 1] / dy, zp = x[3 * p + 2] / dz;
+        int i = (int)floor(xp), j = (int)floor(yp), k = (int)floor(zp);
+        const double dxp = xp - (double)i, dyp = yp - (double)j, dzp = zp - (double)k;
+        const double a1 = (1.0 - dxp) * (1.0 - dyp) * (1.0 - dzp), a2 = dxp * (1.0 - dyp) * (1.0 - dzp);
+        const double a3 = (1.0 - dxp) * dyp * (1.0 - dzp), a4 = dxp * dyp * (1.0 - dzp);
+        const double a5 = (1.0 - dxp) * (1.0 - dyp) * dzp, a6 = dxp * (1.0 - dyp) * dzp;
+        const double a7 = (1.0 - dxp) * dyp * dzp, a8 = dxp * dyp * dzp;
+        if (i < 0) i = 0;
+        if (i >= nx) i = nx - 1;
+        if (j < 0) j = 0;
+        if (j >= ny) j = ny - 1;
+        if (k < 0) k = 0;
+        if (k >= nz) k = nz - 1;
+        for (int d = 0; d < 3; d++)                                                  /* :56-60 */
+            ep[3 * p + d] = a1 * e[d + 3 * ORC3_NODE(i, j, k)] + a2 * e[d + 3 * ORC3_NODE(i + 1, j, k)]
+                          + a3 * e[d + 3 * ORC3_NODE(i, j + 1, k)] + a4 * e[d + 3 * ORC3_NODE(i + 1, j + 1, k)]
+                          + a5 * e[d + 3 * ORC3_NODE(i, j, k + 1)] + a6 * e[d + 3 * ORC3_NODE(i + 1, j, k + 1)]
+                          + a7 * e[d + 3 * ORC3_NODE(i, j + 1, k + 1)] + a8 * e[d + 3 * ORC3_NODE(i + 1, j + 1, k + 1)];
+    }
+}
+
+static void orc3_fft3(cplx *a, int nx, int ny, int nz, int sign, orc_fft_plan *px, orc_fft_plan *py, orc_fft_plan *pz)
+{
+    for (int k = 0; k < nz; k++) for (int j = 0; j < ny; j++) { cplx *l = a + (size_t)nx * (j + (size_t)ny * k); orc_fft_exec(px, l, 1, l, 1, sign); }
+    for (int k = 0; k < nz; k++) for (int i = 0; i < nx; i++) { cplx *l = a + i + (size_t)nx * ny * k; orc_fft_exec(py, l, nx, l, nx, sign); }
+    for (int j = 0; j < ny; j++) for (int i = 0; i < nx; i++) { cplx *l = a + i + (size_t)nx * j; orc_fft_exec(pz, l, nx * ny, l, nx * ny, sign); }
+}
+
+/* solve_poisson                                     fortran/poisson_3d.f90:47-191 */
+void orc3_poisson(const orc3_mesh *m, const double *rho, double *e)
+{
+    const int nx = m->n[0], ny = m->n[1], nz = m->n[2];
+    const double pi = 4.0 * atan(1.0);
+    const double dimx = m->xmax[0] - m->xmin[0], dimy = m->xmax[1] - m->xmin[1], dimz = m->xmax[2] - m->xmin[2];
+    const size_t nc = (size_t)nx * ny * nz;
+    cplx *rhs = (cplx *)malloc(sizeof(cplx) * nc), *psi = (cplx *)malloc(sizeof(cplx) * nc);
+    orc_fft_plan *px = orc_fft_new(nx), *py = orc_fft_new(ny), *pz = orc_fft_new(nz);
+    for (int comp = 0; comp < 3; comp++) {
+        for (int k = 0; k < nz; k++) for (int j = 0; j < ny; j++) for (int i = 0; i < nx; i++)
+            rhs[i + (size_t)nx * (j + (size_t)ny * k)] = c_make(rho[ORC3_NODE(i, j, k)], 0.0);              /* :71, :98, :131 */
+        orc3_fft3(rhs, nx, ny, nz, -1, px, py, pz);
+        for (int k = 0; k < nz; k++) {
+            const int ind_z = (k + 1 <= nz / 2) ? k : -nz + k;                                              /* :75-79 */
+            const double kz = 2.0 * pi * (double)ind_z / dimz;
+            for (int j = 0; j < ny; j++) {
+                const int ind_y = (j + 1 <= ny / 2) ? j : -ny + j;
+                const double ky = 2.0 * pi * (double)ind_y / dimy;
+                for (int i = 0; i < nx; i++) {
+                    const int ind_x = (i + 1 <= nx / 2) ? i : -nx + i;
+                    const double kx = 2.0 * pi * (double)ind_x / dimx;
+                    cplx *r = &rhs[i + (size_t)nx * (j + (size_t)ny * k)];
+                    if (ind_x == 0 && ind_y == 0 && ind_z == 0) { *r = c_make(0.0, 0.0); continue; }
+                    const double kk = comp == 0 ? kx : (comp == 1 ? ky : kz), k2 = kx * kx + ky * ky + kz * kz;
+                    const cplx t = c_mul(c_make(-0.0, -kk), *r);                                             /* -cmplx(0,kk) * rhs */
+                    *r = c_make(t.re / k2, t.im / k2);
+                }
+            }
+        }
+        for (size_t q = 0; q < nc; q++) psi[q] = rhs[q];
+        orc3_fft3(psi, nx, ny, nz, +1, px, py, pz);
+        for (int k = 0; k < nz; k++) for (int j = 0; j < ny; j++) for (int i = 0; i < nx; i++)
+            e[comp + 3 * ORC3_NODE(i, j, k)] = psi[i + (size_t)nx * (j + (size_t)ny * k)].re;                /* :96, :129, :163 */
+    }
+    for (int d = 0; d < 3; d++) {                                                                             /* :184-186 */
+        for (int k = 0; k <= nz; k++) for (int j = 0; j <= ny; j++) e[d + 3 * ORC3_NODE(nx, j, k)] = e[d + 3 * ORC3_NODE(0, j, k)];
+    }
+    for (int d = 0; d < 3; d++) for (int k = 0; k <= nz; k++) for (int i = 0; i <= nx; i++) e[d + 3 * ORC3_NODE(i, ny, k)] = e[d + 3 * ORC3_NODE(i, 0, k)];
+    for (int d = 0; d < 3; d++) for (int j = 0; j <= ny; j++) for (int i = 0; i <= nx; i++) e[d + 3 * ORC3_NODE(i, j, nz)] = e[d + 3 * ORC3_NODE(i, j, 0)];
+    const size_t nn = (size_t)(nx + 1) * (ny + 1) * (nz + 1);
+    const double sc = (double)nx * (double)ny * (double)nz;
+    for (size_t q = 0; q < 3 * nn; q++) e[q] = e[q] / sc;                                                     /* :188 */
+    orc_fft_free(px); orc_fft_free(py); orc_fft_free(pz);
+    free(rhs); free(psi);
+}
+
+static double orc3_modulo(double a, double p) { double r = fmod(a, p); if (r != 0.0 && ((r < 0.0) != (p < 0.0))) r += p; return r; }
+
+static void orc3_push(const orc3_mesh *m, int64_t np, double *x, const double *v, double delta_t)          /* uapic3d.f90:224-242 */
+{
+    for (int64_t p = 0; p < np; p++)
+        for (int c = 0; c < 3; c++) {
+            const double d = delta_t * v[3 * p + c] - m->xmin[c];
+            x[3 * p + c] = m->xmin[c] + orc3_modulo(x[3 * p + c] + d, m->xmax[c] - m->xmin[c]);
+        }
+}
+
+static void orc3_rotate(int kind, int64_t np, const double *x, double *v, const double *ep, double dt, double eps, double coef, double delta,
+                        int index_quirk)
+{
+    for (int64_t p = 0; p < np; p++) {
+        const double x1 = x[3 * p], x2 = x[3 * p + 1];
+        const double xa = (kind == 2 && index_quirk) ? x[p] : x1;                   /* p%x(m,1), uapic3d.f90:179,182 */
+        double Bm[3], Ee[3], vv[3], vxB[3], ExB[3];
+        Bm[0] = (x2 - 9.0) * delta / sqrt(1.0 + ((xa - 9.0) * (xa - 9.0) + (x2 - 9.0) * (x2 - 9.0)) * delta * delta);
+        Bm[1] = -(x1 - 9.0) * delta / sqrt(1.0 + ((xa - 9.0) * (xa - 9.0) + (x2 - 9.0) * (x2 - 9.0)) * delta * delta);
+        Bm[2] = 1.0 / sqrt(1.0 + ((x1 - 9.0) * (x1 - 9.0) + (x2 - 9.0) * (x2 - 9.0)) * delta * delta);
+        for (int c = 0; c < 3; c++) { Ee[c] = ep[3 * p + c]; vv[c] = v[3 * p + c]; }
+        vxB[0] = vv[1] * Bm[2] - vv[2] * Bm[1]; vxB[1] = vv[2] * Bm[0] - vv[0] * Bm[2]; vxB[2] = vv[0] * Bm[1] - vv[1] * Bm[0];
+        ExB[0] = Ee[1] * Bm[2] - Ee[2] * Bm[1]; ExB[1] = Ee[2] * Bm[0] - Ee[0] * Bm[2]; ExB[2] = Ee[0] * Bm[1] - Ee[1] * Bm[0];
+        const double EB = Bm[0] * Ee[0] + Bm[1] * Ee[1] + Bm[2] * Ee[2], vB = Bm[0] * vv[0] + Bm[1] * vv[1] + Bm[2] * vv[2];
+        for (int c = 0; c < 3; c++) {
+            if (kind == 0)          /* :113-121 */
+                v[3 * p + c] = cos(dt / eps) * vv[c] + sin(dt / eps) * vxB[c] + eps * sin(dt / eps) * Ee[c] + (dt - eps * sin(dt / eps)) * EB * Bm[c]
+                             + (eps - eps * cos(dt / eps)) * ExB[c] + (1.0 - cos(dt / eps)) * vB * Bm[c];
+            else if (kind == 1)     /* :152-159 */
+                v[3 * p + c] = cos(dt) * vv[c] + sin(dt) * vxB[c] + coef * sin(dt) * Ee[c] + coef * (dt - sin(dt)) * EB * Bm[c]
+                             + coef * (1.0 - cos(dt)) * ExB[c] + (1.0 - cos(dt)) * vB * Bm[c];
+            else                    /* :187-194 */
+                v[3 * p + c] = cos(dt) * vv[c] + sin(-dt) * vxB[c] - coef * sin(-dt) * Ee[c] - coef * (-dt - sin(-dt)) * EB * Bm[c]
+                             - coef * (1.0 - cos(dt)) * ExB[c] + (1.0 - cos(dt)) * vB * Bm[c];
+        }
+    }
+}
+
+/* the program: uapic3d.f90:44-61 (parameters), :74-83 (initial fields), :91-206 (time loop).  max_outer > 0 caps the outer loop. */
+int64_t orc3_run(const orc3_mesh *m, int64_t np, double *x, double *v, double *ep_out, double w, double eps, double delta, int nmrc, int nmrcm,
+                 double tfinal, int max_outer, int index_quirk, double *e_out, double *rho_out)
+{
+    const int nx = m->n[0], ny = m->n[1], nz = m->n[2];
+    const size_t nn = (size_t)(nx + 1) * (ny + 1) * (nz + 1);
+    const double pi = 4.0 * atan(1.0);
+    double *rho = (double *)malloc(8 * nn), *e = (double *)malloc(24 * nn), *ep = (double *)malloc(24 * (size_t)(np ? np : 1));
+    int64_t done = 0;
+#define ORC3_FIELDS() do { orc3_compute_rho_cic(m, np, x, w, rho); orc3_poisson(m, rho, e); orc3_interpolate_eb_cic(m, e, np, x, ep); } while (0)
+    ORC3_FIELDS();                                                                   /* :76-83 */
+    const long n0 = lround(tfinal / eps / (2.0 * pi) / (double)nmrc);                /* :48 */
+    if (n0 == 0 || n0 == 1) {
+        const double dt = eps * (2.0 * pi) / (double)nmrc;
+        long nstep = lround(tfinal / dt);
+        if (max_outer > 0 && nstep > max_outer) nstep = max_outer;
+        for (long it = 0; it < nstep; it++) {
+            orc3_push(m, np, x, v, 0.5 * dt);
+            ORC3_FIELDS();
+            orc3_rotate(0, np, x, v, ep, dt, eps, 1.0, delta, index_quirk);
+            for (int64_t q = 0; q < 3 * np; q++) x[q] = x[q] + 0.5 * dt * v[q];      /* :123 (no wrap) */
+            done++;
+        }
+    } else {
+        const double alpha = 0.5 * (1.0 + 1.0 / (double)n0) * eps * (double)n0, beta = 0.5 * (1.0 - 1.0 / (double)n0) * eps * (double)n0;
+        const double dt = (2.0 * pi) / (double)nmrcm;
+        int outer = nmrc;
+        if (max_outer > 0 && outer > max_outer) outer = max_outer;
+        for (int istep = 0; istep < outer; istep++) {
+            for (int n = 0; n < nmrcm; n++) {
+                orc3_push(m, np, x, v, 0.5 * dt * alpha);
+                ORC3_FIELDS();
+                orc3_rotate(1, np, x, v, ep, dt, eps, alpha, delta, index_quirk);
+                orc3_push(m, np, x, v, 0.5 * dt * alpha);
+                done++;
+            }
+            for (int n = 0; n < nmrcm; n++) {
+                orc3_push(m, np, x, v, 0.5 * dt * beta);
+                ORC3_FIELDS();
+                orc3_rotate(2, np, x, v, ep, dt, eps, beta, delta, index_quirk);
+                orc3_push(m, np, x, v, 0.5 * dt * beta);
+                done++;
+            }
+        }
+    }
+    if (ep_out) memcpy(ep_out, ep, 24 * (size_t)np);
+    if (e_out) memcpy(e_out, e, 24 * nn);
+    if (rho_out) memcpy(rho_out, rho, 8 * nn);
+    free(rho); free(e); free(ep);
+    return done;
+}
+
+/* init_particles_3d densities (particles.F90:152-190) from the counter-based stream of k3_generate (uapic_mrc3d.cu) */
+void orc3_generate(const orc3_mesh *m, uint64_t seed, int64_t first, int64_t np, double *x, double *v)
+{
+    const double pi = 3.14159265358979323846;
+    for (int64_t p = 0; p < np; p++) {
+        const uint64_t id = (uint64_t)(first + p);
+        x[3 * p + 2] = m->xmin[2] + (m->xmax[2] - m->xmin[2]) * orc_uniform01(seed, id, 3, 0);
+        for (uint32_t d = 0;; d += 3) {
+            const double xi = 9.0 * orc_uniform01(seed, id, 4, d), yi = 2.0 * pi * orc_uniform01(seed, id, 4, d + 1), zi = (1.0 + 0.02) * orc_uniform01(seed, id, 4, d + 2);
+            if ((1.0 + 0.02 * cos(4.0 * yi)) * exp(-5.0 * (xi - 4.8) * (xi - 4.8)) >= zi) { x[3 * p] = cos(yi) * xi + 9.0; x[3 * p + 1] = sin(yi) * xi + 9.0; break; }
+        }
+        for (uint32_t d = 0;; d += 4) {
+            const double xi = (orc_uniform01(seed, id, 5, d) - 0.5) * 8.0, yi = (orc_uniform01(seed, id, 5, d + 1) - 0.5) * 8.0, wi = (orc_uniform01(seed, id, 5, d + 2) - 0.5) * 8.0;
+            if (exp(-2.0 * (xi * xi + yi * yi + wi * wi)) >= orc_uniform01(seed, id, 5, d + 3)) { v[3 * p] = xi; v[3 * p + 1] = yi; v[3 * p + 2] = wi; break; }
+        }
+    }
+}

@@ -1,0 +1,90 @@
+"""GPU parity of the reference's 3D path (fortran/uapic3d.f90; uapic3d_* in include/uapic_b200.h, csrc/uapic_mrc3d.cu) against
+the oracle's restatement, and the reference-owned programs test_poisson_3d.f90 / test_pic_3d.f90 on the GPU."""
+import numpy as np
+import pytest
+
+import oracle
+import uapic_b200 as ub
+
+pytestmark = pytest.mark.gpu
+
+
+def _meshes(xmax, n):
+    return ub.Mesh3D((0, 0, 0), xmax, n), oracle.mesh3((0, 0, 0), xmax, n)
+
+
+def test_poisson_3d_reference_program_on_gpu():
+    """fortran/test_poisson_3d.f90"""
+    nx, ny, nz = 32, 64, 128
+    mesh, om = _meshes((2 * np.pi, 4 * np.pi, 6 * np.pi), (nx, ny, nz))
+    x, y, z = (np.arange(k + 1) * d for k, d in zip(mesh.n, mesh.d))
+    sx, sy, sz = np.sin(x)[:, None, None], np.sin(y)[None, :, None], np.sin(z)[None, None, :]
+    f = ub.Fields3D(mesh)
+    f.rho[:] = -3 * sx * sy * sz
+    ub.mrc3d.solve_poisson(f)
+    assert np.abs(f.e[0] - np.cos(x)[:, None, None] * sy * sz).max() < 1e-13
+    assert np.abs(f.e[1] - sx * np.cos(y)[None, :, None] * sz).max() < 1e-13
+    assert np.abs(f.e[2] - sx * sy * np.cos(z)[None, None, :]).max() < 1e-13
+    rng = np.random.default_rng(3)
+    f.rho[:] = rng.standard_normal(f.rho.shape)
+    ub.mrc3d.solve_poisson(f)
+    eo = oracle.corc3().poisson(om, f.rho)
+    assert np.abs(f.e - eo).max() < 1e-12 * np.abs(eo).max()
+
+
+@pytest.mark.parametrize("n", [(64, 64, 4), (20, 12, 6)])
+def test_pic_3d_reference_program_on_gpu(n):
+    """fortran/test_pic_3d.f90: deposit, interpolation of (sin x, sin y, sin z); plus parity with the oracle (the interpolation
+    is bit-exact: same operation order, no contraction)"""
+    mesh, om = _meshes((18, 18, 1), n)
+    npart = 50001
+    o = oracle.corc3()
+    with ub.Session3D(mesh, npart) as s:
+        s.generate_particles(seed=11, first_global_index=5)
+        x, v, _ = s.download_particles()
+    xo, vo = o.generate(om, 11, npart, first=5)
+    assert np.abs(x - xo).max() < 1e-12 and np.abs(v - vo).max() < 1e-12
+    w = 18 * 18 / npart
+    f = ub.Fields3D(mesh)
+    ub.mrc3d.compute_rho_cic(f, xo, w)
+    rho_o = o.compute_rho_cic(om, xo, w)
+    assert np.abs(f.rho - rho_o).max() < 1e-12 * np.abs(rho_o).max()
+    X, Y, Z = (np.arange(k + 1) * d for k, d in zip(mesh.n, mesh.d))
+    f.e[0], f.e[1], f.e[2] = np.sin(X)[:, None, None], np.sin(Y)[None, :, None], np.sin(Z)[None, None, :]
+    ep = ub.mrc3d.interpolate_eb_cic(xo, f)
+    assert np.array_equal(ep, o.interpolate_eb_cic(om, f.e, xo))
+    assert np.abs(ep[0] - np.sin(xo[0])).mean() < mesh.d[0] ** 2
+
+
+@pytest.mark.parametrize("nmrc,nmrcm,tfinal,delta,quirk", [(8, 8, 0.05, 3e-3, 1),      # N0mrc = 1: the plain time loop, uapic3d.f90:93-127
+                                                            (8, 8, np.pi, 3e-3, 1),     # N0mrc = 64: multi-revolution composition, :131-204
+                                                            (4, 6, np.pi, 0.3, 1), (4, 6, np.pi, 0.3, 0)])
+def test_uapic3d_program_vs_oracle(nmrc, nmrcm, tfinal, delta, quirk):
+    mesh, om = _meshes((18, 18, 1), (16, 16, 4))
+    npart = 4000
+    o = oracle.corc3()
+    x0, v0 = o.generate(om, 99, npart)
+    w = 18 * 18 / npart
+    xo, vo = x0.copy(order="F"), v0.copy(order="F")
+    n_o, ep_o, e_o, rho_o = o.run(om, xo, vo, w, 0.5 ** 10, delta, nmrc, nmrcm, tfinal, index_quirk=quirk)
+    x, v, ep, f, n = ub.run_uapic3d(mesh, x0, v0, ep=0.5 ** 10, delta=delta, nmrc=nmrc, nmrcm=nmrcm, tfinal=tfinal, weight=w, index_quirk=bool(quirk))
+    assert n == n_o
+    per = np.array([18.0, 18.0, 1.0])[:, None]
+    dxp = np.abs(np.mod(x - xo + per / 2, per) - per / 2)
+    assert (dxp / per).max() < 1e-10
+    assert np.abs(v - vo).max() < 1e-10 * np.abs(vo).max()
+    assert np.abs(f.e - e_o).max() < 1e-10 * np.abs(e_o).max()
+    assert np.abs(f.rho - rho_o).max() < 1e-10 * np.abs(rho_o).max()
+
+
+def test_uapic3d_fixed_point_is_reproducible_and_errors_are_loud():
+    mesh, om = _meshes((18, 18, 1), (16, 16, 4))
+    npart = 3000
+    x0, v0 = oracle.corc3().generate(om, 5, npart)
+    runs = [ub.run_uapic3d(mesh, x0, v0, nmrc=4, nmrcm=4, tfinal=np.pi, deposit_mode=ub.DEPOSIT_FIXED_POINT) for _ in range(2)]
+    assert np.array_equal(runs[0][0], runs[1][0]) and np.array_equal(runs[0][1], runs[1][1]) and np.array_equal(runs[0][3].e, runs[1][3].e)
+    with pytest.raises(ub.UapicError):
+        ub.Session3D(ub.Mesh3D((0, 0, 0), (1, 1, 1), (16, 16, 1030)), 10)
+    with ub.Session3D(mesh, 10) as s:
+        with pytest.raises(ub.UapicError):
+            s.init_fields()

@@ -12,3 +12,5 @@ from .api import (UA, Mesh, MeshFields, Particles, Poisson, compute_f, compute_r
 from .loaders import landau_sampling, make_particles_dat, plasma, read_particles, write_particles  # noqa: F401
 from .session import Session, run_bupdate  # noqa: F401
 from . import dist  # noqa: F401
+from . import mrc3d  # noqa: F401
+from .mrc3d import Fields3D, Mesh3D, Session3D, run_uapic3d  # noqa: F401

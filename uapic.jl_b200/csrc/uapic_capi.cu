@@ -38,6 +38,20 @@ int fail(int code, const char *fmt, ...) {
                         #expr, cudaGetErrorString(_e), __FILE__, __LINE__);                                   \
     } while (0)
 
+}  // namespace
+
+int uapic_fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+namespace {
+
 struct DeviceInfo { int ok; int sm_count; int major, minor; };
 
 int device_info(int device, DeviceInfo *out) {

@@ -6,6 +6,9 @@
 
 #include "uapic_device.cuh"
 
+// records the message uapic_last_error() returns on this thread and returns `code` (uapic_capi.cu)
+int uapic_fail(int code, const char *fmt, ...);
+
 namespace uapic {
 
 struct LaunchCtx {
