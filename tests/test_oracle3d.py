@@ -60,6 +60,6 @@ def test_both_branches_run_and_quirk_matters():
         assert n == expect and np.all(np.isfinite(x)) and np.all(np.isfinite(v)) and np.all(np.isfinite(e))
     xa, va = x0.copy(order="F"), v0.copy(order="F")
     xb, vb = x0.copy(order="F"), v0.copy(order="F")
-    o.run(m, xa, va, w, 0.5 ** 10, 0.3, 4, 4, np.pi, index_quirk=1)
-    o.run(m, xb, vb, w, 0.5 ** 10, 0.3, 4, 4, np.pi, index_quirk=0)
+    o.run(m, xa, va, w, 0.5 ** 10, 0.03, 4, 4, np.pi, index_quirk=1)
+    o.run(m, xb, vb, w, 0.5 ** 10, 0.03, 4, 4, np.pi, index_quirk=0)
     assert np.abs(va - vb).max() > 1e-8          # p%x(m,1) instead of p%x(1,m) changes the answer (uapic3d.f90:179,182)

@@ -12,6 +12,7 @@
 //    p%x(1,m) was meant (uapic3d.f90:179,182): `index_quirk = 1` (default) reproduces it, 0 uses x(1,m).
 // Everything here is HBM/latency-bound mesh and particle streaming; nothing is shaped like a contraction.
 #include <cmath>
+#include <cstdlib>
 #include <new>
 
 #include "../../include/uapic_b200.h"
@@ -244,7 +245,14 @@ struct uapic3d_session {
     double2 *A = nullptr, *B = nullptr;
     RhoAcc acc{};
     bool have_particles = false, fields_ready = false;
+    bool own_stream = false;
+    // one captured sub-step per kind (uapic3d_substep): the loop body is ~22 launches of microsecond kernels, i.e. launch bound
+    cudaGraphExec_t gexec[3] = {nullptr, nullptr, nullptr};
+    double gdt[3] = {0, 0, 0}, gcoef[3] = {0, 0, 0};
+    int64_t glaunches[3] = {0, 0, 0};
     ~uapic3d_session() {
+        for (cudaGraphExec_t g : gexec) if (g) cudaGraphExecDestroy(g);
+        if (own_stream && stream) cudaStreamDestroy(stream);
         for (void *p : {(void *)x, (void *)v, (void *)ep, (void *)rho, (void *)e, raw, (void *)A, (void *)B}) if (p) cudaFree(p);
     }
 };
@@ -346,6 +354,10 @@ int uapic3d_create(const uapic3d_config_t *cfg, uapic3d_session_t **out) {
     uapic3d_session *s = new (std::nothrow) uapic3d_session();
     if (!s) return uapic_fail(UAPIC_ENOMEM, "host allocation failed");
     s->cfg = *cfg; s->m = m; s->sm_count = sm; s->stream = (cudaStream_t)cfg->stream;
+    if (!s->stream) {          // stream capture needs a real stream, not the legacy default one
+        if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) { delete s; return uapic_fail(UAPIC_ECUDA, "cudaStreamCreate failed"); }
+        s->own_stream = true;
+    }
     const size_t np = (size_t)(cfg->nbpart ? cfg->nbpart : 1);
     cudaError_t e = cudaSuccess;
     auto al = [&](void **p, size_t n) { if (e == cudaSuccess) e = cudaMalloc(p, n); };
@@ -409,16 +421,41 @@ int uapic3d_substep(uapic3d_session_t *s, int kind, double dt, double coef, int 
     CU3(cudaSetDevice(s->cfg.device));
     const int64_t np = s->cfg.nbpart;
     const double half = kind == 0 ? 0.5 * dt : 0.5 * dt * coef;
-    for (int it = 0; it < count; ++it) {
+    auto body = [&]() -> int {
         if (np > 0) k3_push<<<grid3(s->sm_count, 3 * np), k3Block, 0, s->stream>>>(s->m, np, s->x, s->v, half, 1);
         TRY3(field_update3(s));
         if (np > 0) {
             k3_rotate<<<grid3(s->sm_count, np), k3Block, 0, s->stream>>>(kind, np, s->x, s->v, s->ep, dt, s->cfg.ep, coef, s->cfg.delta, s->cfg.index_quirk);
-            k3_push<<<grid3(s->sm_count, 3 * np), k3Block, 0, s->stream>>>(s->m, np, s->x, s->v, half, kind == 0 ? 0 : 1);
+            k3_push<<<grid3(s->sm_count, np ? 3 * np : 1), k3Block, 0, s->stream>>>(s->m, np, s->x, s->v, half, kind == 0 ? 0 : 1);
         }
         s->launches += 3;
+        CU3(cudaGetLastError());
+        return UAPIC_OK;
+    };
+    const char *nog = getenv("UAPIC3D_NO_GRAPH");
+    if (count >= 4 && !(nog && *nog == '1')) {
+        // capture the sub-step once per (kind, dt, coef) and replay it: identical launches every time
+        if (!s->gexec[kind] || s->gdt[kind] != dt || s->gcoef[kind] != coef) {
+            if (s->gexec[kind]) { cudaGraphExecDestroy(s->gexec[kind]); s->gexec[kind] = nullptr; }
+            const int64_t l0 = s->launches;
+            cudaGraph_t g = nullptr;
+            CU3(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+            const int rc = body();
+            cudaError_t e = cudaStreamEndCapture(s->stream, &g);
+            if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+            if (e != cudaSuccess) return uapic_fail(UAPIC_ECUDA, "stream capture of the 3D sub-step failed: %s", cudaGetErrorString(e));
+            e = cudaGraphInstantiate(&s->gexec[kind], g, 0);
+            cudaGraphDestroy(g);
+            if (e != cudaSuccess) return uapic_fail(UAPIC_ECUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+            s->gdt[kind] = dt; s->gcoef[kind] = coef;
+            s->glaunches[kind] = s->launches - l0;
+            s->launches = l0;
+        }
+        for (int it = 0; it < count; ++it) CU3(cudaGraphLaunch(s->gexec[kind], s->stream));
+        s->launches += s->glaunches[kind] * count;
+        return UAPIC_OK;
     }
-    CU3(cudaGetLastError());
+    for (int it = 0; it < count; ++it) TRY3(body());
     return UAPIC_OK;
 }
 

@@ -20,6 +20,7 @@ export integrate, gnuplot, errors
 export Session, upload_particles!, init_fields!, step!, step_host!, generate_particles!, set_sort!, download_particles, download_fields, energy_history
 export STORE_FULL, STORE_HYBRID, STORE_ONEPASS, STORE_ONEPASS_LEAN, SCHEME_M6, SCHEME_CIC
 export nccl_unique_id, init_nccl!, sum_v
+export Mesh3D, Session3D, run_uapic3d!
 export UAPICError
 
 const libuapic = get(ENV, "UAPIC_B200_LIB", joinpath(@__DIR__, "..", "..", "libuapic_b200.so"))
@@ -428,6 +429,59 @@ function energy_history(s::Session)
     out = zeros(n[])
     n[] > 0 && check(ccall((:uapic_session_energy_history, libuapic), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Int64, Ref{Int64}), s.handle, out, n[], n))
     out
+end
+
+# ---------------------------------------------------------------------------------------------------
+# the 3D program fortran/uapic3d.f90 (rotation push + multi-revolution composition, CIC, 3D spectral Poisson)
+# ---------------------------------------------------------------------------------------------------
+struct CMesh3D                # uapic3d_mesh_t
+    xmin :: NTuple{3,Cdouble}
+    xmax :: NTuple{3,Cdouble}
+    n    :: NTuple{3,Int32}
+end
+struct CConfig3D              # uapic3d_config_t
+    mesh :: CMesh3D
+    nbpart :: Int64
+    nbpart_global :: Int64
+    weight :: Cdouble
+    ep :: Cdouble
+    delta :: Cdouble
+    deposit_mode :: Int32
+    index_quirk :: Int32
+    device :: Int32
+    stream :: Ptr{Cvoid}
+end
+struct Mesh3D
+    xmin :: NTuple{3,Float64}
+    xmax :: NTuple{3,Float64}
+    n    :: NTuple{3,Int}
+end
+CMesh3D(m::Mesh3D) = CMesh3D(m.xmin, m.xmax, Int32.(m.n))
+
+mutable struct Session3D
+    handle :: Ptr{Cvoid}
+    mesh   :: Mesh3D
+    nbpart :: Int64
+    function Session3D(mesh::Mesh3D, nbpart; ep = 0.5^10, delta = 3e-3, nbpart_global = nbpart,
+                       weight = prod(mesh.xmax .- mesh.xmin) / nbpart_global, deposit_mode = DEPOSIT_FP64_ATOMIC,
+                       index_quirk = true, device = 0)
+        cfg = CConfig3D(CMesh3D(mesh), nbpart, nbpart_global, weight, ep, delta, deposit_mode, index_quirk ? 1 : 0, device, C_NULL)
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:uapic3d_create, libuapic), Cint, (Ref{CConfig3D}, Ref{Ptr{Cvoid}}), cfg, h))
+        s = new(h[], mesh, nbpart)
+        finalizer(x -> (x.handle != C_NULL && ccall((:uapic3d_destroy, libuapic), Cint, (Ptr{Cvoid},), x.handle); x.handle = C_NULL), s)
+        s
+    end
+end
+
+# x, v :: Array{Float64,2}(3, nbpart); runs uapic3d.f90:74-206 and returns the number of sub-steps; x, v are updated in place
+function run_uapic3d!(s::Session3D, x::Array{Float64,2}, v::Array{Float64,2}; Nmrc = 2^7, Nmrcm = 2^7, tfinal = π)
+    check(ccall((:uapic3d_upload_particles, libuapic), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}), s.handle, x, v))
+    check(ccall((:uapic3d_init_fields, libuapic), Cint, (Ptr{Cvoid},), s.handle))
+    n = Ref{Int64}(0)
+    check(ccall((:uapic3d_run, libuapic), Cint, (Ptr{Cvoid}, Cint, Cint, Cdouble, Cint, Ref{Int64}), s.handle, Nmrc, Nmrcm, tfinal, 0, n))
+    check(ccall((:uapic3d_download_particles, libuapic), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}), s.handle, x, v, C_NULL))
+    n[]
 end
 
 end # module
