@@ -79,7 +79,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     import re
     lib = ub.lib()
     hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "uapic_b200.h")).read()
-    declared = set(re.findall(r"\b(uapic_[a-z0-9_]+)\s*\(", hdr)) - {"uapic_allreduce_fn"}
+    declared = set(re.findall(r"\b(uapic(?:3d)?_[a-z0-9_]+)\s*\(", hdr)) - {"uapic_allreduce_fn"}
     assert declared == set(ub.EXPORTS), declared ^ set(ub.EXPORTS)
     for name in declared:
         assert hasattr(lib, name), name
@@ -92,6 +92,25 @@ def test_library_loads_and_exports_every_declared_symbol():
         assert e.value.code == -2          # UAPIC_ENODEVICE
         with pytest.raises(ub.UapicError):
             ub.Session(m, 16, 0.1, 0.1, 10)
+        with pytest.raises(ub.UapicError) as e3:
+            ub.Session3D(ub.Mesh3D((0, 0, 0), (1, 1, 1), (8, 8, 4)), 10)
+        assert e3.value.code == -2
+
+
+def test_nccl_is_bound_at_run_time_without_a_link_dependency():
+    """uapic_nccl_*: the library dlopens libnccl.so.2 (no DT_NEEDED entry); the unique id is 128 opaque bytes"""
+    import ctypes as C
+    import subprocess
+    so = ub.LIB_PATH
+    needed = subprocess.run(["readelf", "-d", so], capture_output=True, text=True).stdout
+    assert "nccl" not in needed.lower()
+    v = C.c_int(0)
+    rc = ub.lib().uapic_nccl_version(C.byref(v))
+    if rc != 0:
+        pytest.skip("no libnccl.so.2 on this machine: " + ub.lib().uapic_last_error().decode())
+    assert v.value >= 20000
+    a, b = ub.dist.nccl_unique_id(), ub.dist.nccl_unique_id()
+    assert len(a) == 128 and a != b
 
 
 def test_particles_dat_roundtrip(tmp_path):
