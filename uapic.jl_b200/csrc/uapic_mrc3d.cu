@@ -329,6 +329,20 @@ int field_update3(uapic3d_session *s) {        // compute_rho_cic -> solve_poiss
     return UAPIC_OK;
 }
 
+// device scratch of the synchronous stage functions: freed on every return path
+struct Scratch3 {
+    void *p[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int n = 0;
+    ~Scratch3() { for (int i = 0; i < n; ++i) if (p[i]) cudaFree(p[i]); }
+    template <class T> cudaError_t alloc(T **out, size_t bytes) {
+        void *q = nullptr;
+        const cudaError_t e = cudaMalloc(&q, bytes ? bytes : 8);
+        if (e == cudaSuccess) p[n++] = q;
+        *out = reinterpret_cast<T *>(q);
+        return e;
+    }
+};
+
 double fixed_scale3(double total_mass_over_cell) {
     int e = 0;
     std::frexp(total_mass_over_cell > 0 ? total_mass_over_cell : 1.0, &e);
@@ -522,14 +536,15 @@ int uapic3d_compute_rho_cic(const uapic3d_mesh_t *mesh, int64_t nbpart, const do
     int sm = 0;
     TRY3(device_sm_count(0, &sm));
     double *dx = nullptr, *draw = nullptr, *drho = nullptr;
-    CU3(cudaMalloc(&dx, 24 * (size_t)(nbpart ? nbpart : 1))); CU3(cudaMalloc(&draw, 8 * m.nodes())); CU3(cudaMalloc(&drho, 8 * m.nodes()));
+    Scratch3 sc;
+    CU3(sc.alloc(&dx, 24 * (size_t)nbpart)); CU3(sc.alloc(&draw, 8 * m.nodes())); CU3(sc.alloc(&drho, 8 * m.nodes()));
     CU3(cudaMemcpy(dx, x, 24 * (size_t)nbpart, cudaMemcpyHostToDevice));
     CU3(cudaMemset(draw, 0, 8 * m.nodes()));
     RhoAcc acc{draw, nullptr, 1.0};
     if (nbpart > 0) k3_deposit<<<grid3(sm, nbpart), k3Block>>>(m, nbpart, dx, w / (m.d[0] * m.d[1] * m.d[2]), acc);
     k3_rho_finish<<<grid3(sm, (int64_t)m.nodes()), k3Block>>>(m, acc, drho);
+    CU3(cudaGetLastError());
     CU3(cudaMemcpy(rho, drho, 8 * m.nodes(), cudaMemcpyDeviceToHost));
-    cudaFree(dx); cudaFree(draw); cudaFree(drho);
     return UAPIC_OK;
 }
 
@@ -540,11 +555,11 @@ int uapic3d_poisson(const uapic3d_mesh_t *mesh, const double *rho, double *e) {
     int sm = 0;
     TRY3(device_sm_count(0, &sm));
     double *drho = nullptr, *de = nullptr; double2 *A = nullptr, *B = nullptr;
-    CU3(cudaMalloc(&drho, 8 * m.nodes())); CU3(cudaMalloc(&de, 24 * m.nodes())); CU3(cudaMalloc(&A, 16 * m.cells())); CU3(cudaMalloc(&B, 16 * m.cells()));
+    Scratch3 sc;
+    CU3(sc.alloc(&drho, 8 * m.nodes())); CU3(sc.alloc(&de, 24 * m.nodes())); CU3(sc.alloc(&A, 16 * m.cells())); CU3(sc.alloc(&B, 16 * m.cells()));
     CU3(cudaMemcpy(drho, rho, 8 * m.nodes(), cudaMemcpyHostToDevice));
     TRY3(solve3(m, 0, drho, A, B, de, nullptr));
     CU3(cudaMemcpy(e, de, 24 * m.nodes(), cudaMemcpyDeviceToHost));
-    cudaFree(drho); cudaFree(de); cudaFree(A); cudaFree(B);
     return UAPIC_OK;
 }
 
@@ -555,12 +570,12 @@ int uapic3d_interpolate_eb_cic(const uapic3d_mesh_t *mesh, const double *e, int6
     int sm = 0;
     TRY3(device_sm_count(0, &sm));
     double *dx = nullptr, *de = nullptr, *dep = nullptr;
-    const size_t np = (size_t)(nbpart ? nbpart : 1);
-    CU3(cudaMalloc(&dx, 24 * np)); CU3(cudaMalloc(&de, 24 * m.nodes())); CU3(cudaMalloc(&dep, 24 * np));
+    Scratch3 sc;
+    CU3(sc.alloc(&dx, 24 * (size_t)nbpart)); CU3(sc.alloc(&de, 24 * m.nodes())); CU3(sc.alloc(&dep, 24 * (size_t)nbpart));
     CU3(cudaMemcpy(dx, x, 24 * (size_t)nbpart, cudaMemcpyHostToDevice)); CU3(cudaMemcpy(de, e, 24 * m.nodes(), cudaMemcpyHostToDevice));
     if (nbpart > 0) k3_gather<<<grid3(sm, nbpart), k3Block>>>(m, nbpart, dx, de, dep);
+    CU3(cudaGetLastError());
     CU3(cudaMemcpy(ep, dep, 24 * (size_t)nbpart, cudaMemcpyDeviceToHost));
-    cudaFree(dx); cudaFree(de); cudaFree(dep);
     return UAPIC_OK;
 }
 
