@@ -985,12 +985,10 @@ cudaError_t launch_field_solve(const LaunchCtx &c, const MeshDev &m, const Solve
     if (B.nb < 1 || B.nb > 2) return cudaErrorInvalidValue;
     if (!poisson_size_supported(m.nx) || !poisson_size_supported(m.ny) || m.nx < 4 || m.ny < 4) return cudaErrorInvalidValue;
     const size_t smem = sizeof(double2) * (size_t)max(3 * m.nx, 5 * m.ny);
-    static size_t smem_set = 0;
     cudaError_t e;
-    if (smem > 48 * 1024 - 4096 && smem > smem_set) {
+    if (smem > 48 * 1024 - 4096) {      // per device and per context: set it every time it is needed (a host-side table write)
         e = cudaFuncSetAttribute(k_field_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        smem_set = smem;
     }
     int per_sm = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_field_solve, kSolveBlock, smem);

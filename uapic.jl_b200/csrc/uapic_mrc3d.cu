@@ -293,7 +293,7 @@ int device_sm_count(int device, int *sm) {
 }
 
 // rho (ghosted, device) -> e (3, nx+1, ny+1, nz+1)     poisson_3d.f90:47-191 (one forward transform instead of three identical ones)
-int solve3(const Mesh3 &m, cudaStream_t st, const double *rho, double2 *A, double2 *B, double *e, int64_t *launches) {
+int solve3(const Mesh3 &m, int sm_count, cudaStream_t st, const double *rho, double2 *A, double2 *B, double *e, int64_t *launches) {
     const int nx = m.n[0], ny = m.n[1], nz = m.n[2];
     const int lines[3] = {ny * nz, nx * nz, nx * ny};
     auto threads = [](int len) { return len >= 512 ? 256 : (len >= 128 ? 128 : 64); };
@@ -307,7 +307,7 @@ int solve3(const Mesh3 &m, cudaStream_t st, const double *rho, double2 *A, doubl
         k3_fft_pass<<<lines[0], threads(nx), smem(nx), st>>>(m, 0, +1, 2, comp, nullptr, A, B);
         k3_fft_pass<<<lines[1], threads(ny), smem(ny), st>>>(m, 1, +1, 0, 0, nullptr, nullptr, B);
         k3_fft_pass<<<lines[2], threads(nz), smem(nz), st>>>(m, 2, +1, 0, 0, nullptr, nullptr, B);
-        k3_store_e<<<grid3(148, (int64_t)m.nodes()), k3Block, 0, st>>>(m, comp, B, e);
+        k3_store_e<<<grid3(sm_count, (int64_t)m.nodes()), k3Block, 0, st>>>(m, comp, B, e);
     }
     if (launches) *launches += 15;
     CU3(cudaGetLastError());
@@ -322,7 +322,7 @@ int field_update3(uapic3d_session *s) {        // compute_rho_cic -> solve_poiss
     if (np > 0) k3_deposit<<<grid3(s->sm_count, np), k3Block, 0, s->stream>>>(m, np, s->x, vol, s->acc);
     k3_rho_finish<<<grid3(s->sm_count, (int64_t)m.nodes()), k3Block, 0, s->stream>>>(m, s->acc, s->rho);
     s->launches += 2;
-    TRY3(solve3(m, s->stream, s->rho, s->A, s->B, s->e, &s->launches));
+    TRY3(solve3(m, s->sm_count, s->stream, s->rho, s->A, s->B, s->e, &s->launches));
     if (np > 0) k3_gather<<<grid3(s->sm_count, np), k3Block, 0, s->stream>>>(m, np, s->x, s->e, s->ep);
     s->launches += 1;
     CU3(cudaGetLastError());
@@ -558,7 +558,7 @@ int uapic3d_poisson(const uapic3d_mesh_t *mesh, const double *rho, double *e) {
     Scratch3 sc;
     CU3(sc.alloc(&drho, 8 * m.nodes())); CU3(sc.alloc(&de, 24 * m.nodes())); CU3(sc.alloc(&A, 16 * m.cells())); CU3(sc.alloc(&B, 16 * m.cells()));
     CU3(cudaMemcpy(drho, rho, 8 * m.nodes(), cudaMemcpyHostToDevice));
-    TRY3(solve3(m, 0, drho, A, B, de, nullptr));
+    TRY3(solve3(m, sm, 0, drho, A, B, de, nullptr));
     CU3(cudaMemcpy(e, de, 24 * m.nodes(), cudaMemcpyDeviceToHost));
     return UAPIC_OK;
 }
