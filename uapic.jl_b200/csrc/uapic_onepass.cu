@@ -163,8 +163,49 @@ template <int SGN> DEVINL void fft8(cd (&a)[8]) {
     a[1] = cadd(r0, r1); a[5] = csub(r0, r1); a[3] = cadd(s0, s1); a[7] = csub(s0, s1);
 }
 
+// ---- TMEM as lane-private table memory (phase A, UAPIC_OP_TMEM_TABLES) ---------------------------------------------
+// Phase A re-reads three small per-lane tables in every tile (twiddles, 1/l and 1/l^2, cos/sin tau: 23 LDS.128 = 92 wavefronts
+// of the LSU data pipe per lane and tile, broadcast reads cost as much as any other).  Tensor memory has its own path into the
+// register file (LDTM, 12-cycle latency) and every thread can address its own lane of it: the tables live there instead --
+// tcgen05.st once per kernel, tcgen05.ld in the tile loop.  Lanes 32*(warp % 4).., 96 columns per warp at (warp / 4) * 96.
+// MEASURED (profiles/README.md, r2r/r2s): LSU wavefronts of phase A 464 -> 435 per particle, the pipe 80 % -> 74 % busy, time
+// +1 % with one load + wait per entry (1), +-0 with 16-column batches (2): phase A is latency bound, not pipe bound.  Off.
+#ifndef UAPIC_OP_TMEM_TABLES
+#define UAPIC_OP_TMEM_TABLES 0
+#endif
+constexpr int kTmemColsPerWarp = 96;
+DEVINL unsigned smem_addr_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+DEVINL void tmem_st2(unsigned taddr, double2 v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(__double2loint(v.x)), "r"(__double2hiint(v.x)),
+                 "r"(__double2loint(v.y)), "r"(__double2hiint(v.y)));
+}
+DEVINL double2 tmem_ld2(unsigned taddr) {
+    unsigned r0, r1, r2, r3;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(r0), "+r"(r1), "+r"(r2), "+r"(r3));
+    return make_double2(__hiloint2double(r1, r0), __hiloint2double(r3, r2));
+}
+
+// 8 consecutive double2 (32 columns) with ONE wait: two 16-column loads in flight together
+DEVINL void tmem_ld2x8(unsigned taddr, double2 (&out)[8]) {
+    unsigned r[32];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                   "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) : "r"(taddr));
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+                   "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]) : "r"(taddr + 16));
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]),
+                   "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]),
+                   "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]),
+                   "+r"(r[31]));
+#pragma unroll
+    for (int q = 0; q < 8; ++q) out[q] = make_double2(__hiloint2double(r[4 * q + 1], r[4 * q]), __hiloint2double(r[4 * q + 3], r[4 * q + 2]));
+}
+
 // ---- per-lane constants -----------------------------------------------------------------------------------------
-template <int G> struct OpLane {
+template <int G, bool TM = false> struct OpLane {
     static constexpr int N = 8 * G;
     int lane, g, kap;
     double sg1, sg2;            // -1 on the upper lane of an xor-1 / xor-2 pair
@@ -209,6 +250,40 @@ template <int G> struct OpLane {
         __syncthreads();
     }
     DEVINL double lf(int k1) const { return G == 1 ? lmode(k1) : l0 + (double)k1; }
+
+    unsigned taddr = 0;         // TM: this warp's 96 TMEM columns: [0,32) tw, [32,64) il, [64,96) cs of the lane's samples
+    DEVINL double2 twv(int k1) const { return TM ? tmem_ld2(taddr + 4 * k1) : tw[k1]; }
+    DEVINL void tw8(double2 (&w)[8]) const {
+        if (TM && UAPIC_OP_TMEM_TABLES == 2) { tmem_ld2x8(taddr, w); return; }
+#pragma unroll
+        for (int k1 = 0; k1 < 8; ++k1) w[k1] = twv(k1);
+    }
+    DEVINL double2 ilv(int k1) const { return TM ? tmem_ld2(taddr + 32 + 4 * k1) : il[k1]; }
+    DEVINL double2 cs_s(int s) const { return TM ? tmem_ld2(taddr + 64 + 4 * s) : cs[g + G * s]; }     // (cos, sin) tau of sample g + G s
+    // TM only; every thread of the CTA must call, after init(): allocate (warp 0), fill this lane's tables
+    DEVINL void tmem_setup(unsigned *tbase_smem) {
+        if ((threadIdx.x >> 5) == 0) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_addr_u32(tbase_smem)));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;");
+        const int w = threadIdx.x >> 5;
+        taddr = *tbase_smem + ((unsigned)(32 * (w & 3)) << 16) + (unsigned)((w >> 2) * kTmemColsPerWarp);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            tmem_st2(taddr + 4 * q, tw[q]);
+            tmem_st2(taddr + 32 + 4 * q, il[q]);
+            tmem_st2(taddr + 64 + 4 * q, cs[g + G * q]);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;");
+    }
+    DEVINL void tmem_release(const unsigned *tbase_smem) {
+        asm volatile("tcgen05.fence::before_thread_sync;");
+        __syncthreads();
+        if ((threadIdx.x >> 5) == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(*tbase_smem));
+    }
 };
 
 template <int G> DEVINL double shfl_grp(double v, int src) { return G == 1 ? v : __shfl_sync(kFull, v, src, G); }
@@ -229,12 +304,18 @@ DEVINL void xbfly(cd (&a)[8], int mask, double sg) {
 }
 
 // forward length-N transform, unnormalised: time layout in, Fourier layout out
-template <int G> DEVINL void fwdN(cd (&a)[8], const OpLane<G> &L) {
+template <int G, bool TM> DEVINL void fwdN(cd (&a)[8], const OpLane<G, TM> &L) {
     fft8<-1>(a);
     if (G > 1) {
 #if UAPIC_OP_TWIDDLE_TABLE
+        if (TM && UAPIC_OP_TMEM_TABLES == 2) {
+            double2 w[8]; L.tw8(w);
 #pragma unroll
-        for (int k1 = 1; k1 < 8; ++k1) { const double2 w = L.tw[k1]; a[k1] = cmul(a[k1], mk(w.x, w.y)); }
+            for (int k1 = 1; k1 < 8; ++k1) a[k1] = cmul(a[k1], mk(w[k1].x, w[k1].y));
+        } else {
+#pragma unroll
+            for (int k1 = 1; k1 < 8; ++k1) { const double2 w = L.twv(k1); a[k1] = cmul(a[k1], mk(w.x, w.y)); }
+        }
 #else
         // powers of u1 by recurrence: 24 fp64 instructions instead of 7 LDS.128 (the LSU data pipe is the scarce unit)
         cd u = L.u1;
@@ -251,7 +332,7 @@ template <int G> DEVINL void fwdN(cd (&a)[8], const OpLane<G> &L) {
 }
 
 // backward length-N transform, unnormalised: Fourier layout in, time layout out
-template <int G> DEVINL void bwdN(cd (&a)[8], const OpLane<G> &L) {
+template <int G, bool TM> DEVINL void bwdN(cd (&a)[8], const OpLane<G, TM> &L) {
     if (G >= 2) xbfly(a, 1, L.sg1);
     if (G == 4) {
 #pragma unroll
@@ -260,8 +341,14 @@ template <int G> DEVINL void bwdN(cd (&a)[8], const OpLane<G> &L) {
     }
     if (G > 1) {
 #if UAPIC_OP_TWIDDLE_TABLE
+        if (TM && UAPIC_OP_TMEM_TABLES == 2) {
+            double2 w[8]; L.tw8(w);
 #pragma unroll
-        for (int k1 = 1; k1 < 8; ++k1) { const double2 w = L.tw[k1]; a[k1] = cmulc(a[k1], mk(w.x, w.y)); }
+            for (int k1 = 1; k1 < 8; ++k1) a[k1] = cmulc(a[k1], mk(w[k1].x, w[k1].y));
+        } else {
+#pragma unroll
+            for (int k1 = 1; k1 < 8; ++k1) { const double2 w = L.twv(k1); a[k1] = cmulc(a[k1], mk(w.x, w.y)); }
+        }
 #else
         cd u = L.u1;
 #pragma unroll
@@ -274,7 +361,7 @@ template <int G> DEVINL void bwdN(cd (&a)[8], const OpLane<G> &L) {
 // exp(-i l_k t/eps) for the lane's 8 modes: one sincos for the first mode, a recurrence with e1 = exp(-i t/eps) for the
 // others (the reference evaluates every mode directly, ua_steps.F90:64,224,258; the recurrence error, a few ulp, is
 // below the rounding of the phase l*t/eps itself)
-template <int G> DEVINL void elt_modes(const OpLane<G> &L, double t, double eps, cd e1, cd (&elt)[8]) {
+template <int G, bool TM> DEVINL void elt_modes(const OpLane<G, TM> &L, double t, double eps, cd e1, cd (&elt)[8]) {
     if (G == 1) {
         elt[0] = mk(1.0, 0.0);
         elt[1] = e1;
@@ -295,9 +382,9 @@ template <int G> DEVINL void elt_modes(const OpLane<G> &L, double t, double eps,
 }
 
 // pl, ql/t of ua_steps.F90:60-66 for mode (lane, k1); il = (1/l, 1/l^2)
-template <int G>
-DEVINL void pl_qt(const OpLane<G> &L, int k1, double t, double rt, double eps, cd elt, cd &pl, cd &qt) {
-    const double2 il = L.il[k1];
+template <int G, bool TM>
+DEVINL void pl_qt(const OpLane<G, TM> &L, int k1, double t, double rt, double eps, cd elt, cd &pl, cd &qt) {
+    const double2 il = L.ilv(k1);
     const double l = L.lf(k1);
     pl = mk(-eps * elt.im * il.x, eps * (elt.re - 1.0) * il.x);
     qt = mk(eps * eps * (1.0 - elt.re) * il.y * rt, -eps * fma(eps, elt.im, l * t) * il.y * rt);
@@ -402,7 +489,10 @@ __global__ void __launch_bounds__(kOpBlockA, UAPIC_OP_MINB_A) k_onepass_a(OpDev 
     double2 *gx = smem + kTab + wib * kWarpSmA;    // [8][kRow]  positions -> E at the samples
     double *sps = reinterpret_cast<double *>(gx + 8 * kRow);   // [8][kRow] doubles: sin(xt1) sin(xt2) at the samples (row stride 36: conflict-free both ways)
     double2 *yhs = gx + 12 * kRow;                 // [16][32]   yhat1[k1] at slot k1, yhat2[k1] at slot 8+k1
-    OpLane<G> L; L.init(lane, smem);
+    constexpr bool TM = UAPIC_OP_TMEM_TABLES != 0;
+    OpLane<G, TM> L; L.init(lane, smem);
+    __shared__ unsigned tmem_base;
+    if (TM) L.tmem_setup(&tmem_base);
     const int g = L.g, pin = lane / G, gbase = lane - g;
     const double eps = P.eps, inv_eps = D.inv_eps, invN = 1.0 / (double)N;
     const int64_t ntiles = (P.np + PW - 1) / PW;
@@ -443,15 +533,15 @@ __global__ void __launch_bounds__(kOpBlockA, UAPIC_OP_MINB_A) k_onepass_a(OpDev 
                 const double2 rc2 = OP_LDS(rec + 2), rc3 = OP_LDS(rec + 3);
                 const cd e1b = mk(rc2.y, -rc3.x);
                 cd eltb[8], wv[8];
-                elt_modes<G>(L, tb, eps, e1b, eltb);
+                elt_modes(L, tb, eps, e1b, eltb);
 #pragma unroll
                 for (int k1 = 0; k1 < 8; ++k1) {
                     cd pl, qt;
-                    pl_qt<G>(L, k1, tb, rtb, eps, eltb[k1], pl, qt);
+                    pl_qt(L, k1, tb, rtb, eps, eltb[k1], pl, qt);
                     const cd w = cmulc(qt, eltb[k1]);
                     wv[k1] = mk(invN * w.re, -invN * w.im);
                 }
-                bwdN<G>(wv, L);
+                bwdN(wv, L);
                 __syncwarp();
 #pragma unroll
                 for (int s = 0; s < 8; ++s) wx[s * kRow + lane] = make_double2(wv[s].re, -wv[s].im);
@@ -516,7 +606,7 @@ __global__ void __launch_bounds__(kOpBlockA, UAPIC_OP_MINB_A) k_onepass_a(OpDev 
         const double vxb = vx * rb, vyb = vy * rb;                           // :73-74
 #pragma unroll
         for (int s = 0; s < 8; ++s) {
-            const double2 c = L.cs[g + G * s];
+            const double2 c = L.cs_s(s);
             const double xt1 = x1 + eps * (c.y * vxb - c.x * vyb) + eps * vyb;   // :78-81
             const double xt2 = x2 + eps * (c.y * vyb + c.x * vxb) - eps * vxb;   // :79-82
             gx[s * kRow + lane] = make_double2(xt1, xt2);
@@ -540,13 +630,13 @@ __global__ void __launch_bounds__(kOpBlockA, UAPIC_OP_MINB_A) k_onepass_a(OpDev 
         cd z[8];
 #pragma unroll
         for (int s = 0; s < 8; ++s) {
-            const double2 c = L.cs[g + G * s];
+            const double2 c = L.cs_s(s);
             const double iv = (1.0 + 0.5 * sps[s * kRow + lane] - b) * inv_eps;       // :87
             const double exb = ((c.x * vy - c.y * vx) * iv + ee.x) * rb;                    // :89
             const double eyb = ((-c.x * vx - c.y * vy) * iv + ee.y) * rb;                   // :90
             z[s] = mk(c.x * exb - c.y * eyb, c.y * exb + c.x * eyb);                        // r1 + i r2   :92-93
         }
-        fwdN<G>(z, L);                                                       // :97-98, both real signals at once
+        fwdN(z, L);                                                       // :97-98, both real signals at once
         // split the two spectra, filter (:100-103; the k = 0 coefficient cancels in :109-110 and is dropped)
         {
             cd zp[8];
@@ -556,7 +646,7 @@ __global__ void __launch_bounds__(kOpBlockA, UAPIC_OP_MINB_A) k_onepass_a(OpDev 
             cd c1[8], c2[8], cs1 = mk(0.0, 0.0), cs2 = mk(0.0, 0.0);
 #pragma unroll
             for (int k1 = 0; k1 < 8; ++k1) {
-                const double s = 0.5 * invN * L.il[k1].x;
+                const double s = 0.5 * invN * L.ilv(k1).x;
                 c1[k1] = mk(s * (z[k1].im - zp[k1].im), -s * (z[k1].re + zp[k1].re));
                 c2[k1] = mk(-s * (z[k1].re - zp[k1].re), -s * (z[k1].im + zp[k1].im));
                 cs1 = cadd(cs1, c1[k1]); cs2 = cadd(cs2, c2[k1]);
@@ -578,7 +668,7 @@ __global__ void __launch_bounds__(kOpBlockA, UAPIC_OP_MINB_A) k_onepass_a(OpDev 
         cd e1;
         { double s, c; sincos(-t / eps, &s, &c); e1 = mk(c, s); }
         cd elt[8];
-        elt_modes<G>(L, t, eps, e1, elt);
+        elt_modes(L, t, eps, e1, elt);
 
         // ---- x: fhat_x from yhat (a +-1 shift in Fourier space), ua_step1 (:226-227), position sums ----
         double posp1 = 0.0, posp2 = 0.0, swf1 = 0.0, swf2 = 0.0;
@@ -596,7 +686,7 @@ __global__ void __launch_bounds__(kOpBlockA, UAPIC_OP_MINB_A) k_onepass_a(OpDev 
                 cd fx1, fx2;
                 fx_modes(hb, mk(a1.x, a1.y), mk(n1.x, n1.y), mk(a2.x, a2.y), mk(n2.x, n2.y), fx1, fx2);
                 cd pl, qt;
-                pl_qt<G>(L, k1, t, rt, eps, elt[k1], pl, qt);
+                pl_qt(L, k1, t, rt, eps, elt[k1], pl, qt);
                 const cd w = cmulc(qt, elt[k1]);
                 // FFT(xt)/N of the first-order profile: modes 0, +-1 only
                 cd xh1 = mk(0.0, 0.0), xh2 = mk(0.0, 0.0);
@@ -617,8 +707,8 @@ __global__ void __launch_bounds__(kOpBlockA, UAPIC_OP_MINB_A) k_onepass_a(OpDev 
                 a1 = b1; a2 = b2; b1 = n1; b2 = n2;
             }
         }
-        bwdN<G>(X1, L);                                                      // :231
-        bwdN<G>(X2, L);
+        bwdN(X1, L);                                                      // :231
+        bwdN(X2, L);
         char *sbase = P.store + (size_t)ip * SM::stride;
         if (valid) {
 #pragma unroll
@@ -637,7 +727,7 @@ __global__ void __launch_bounds__(kOpBlockA, UAPIC_OP_MINB_A) k_onepass_a(OpDev 
         // H = H1 + i H2 (H: Hermitian parts) gives Re yt1 + i Re yt2, and Im yt_n = Im yhat_0 + (-1)^n Im yhat_{N/2}.
         cd y1[8], y2[8];
         {
-            constexpr int kNyqLane = OpLane<G>::kappa_of(G / 2), kNyqReg = (G == 1) ? 4 : 0;
+            constexpr int kNyqLane = OpLane<G, TM>::kappa_of(G / 2), kNyqReg = (G == 1) ? 4 : 0;
             const double2 m1 = yhs[gbase], m2 = yhs[8 * 32 + gbase];                                   // yhat_0 (lane kappa = 0)
             const double2 q1 = yhs[kNyqReg * 32 + gbase + kNyqLane], q2 = yhs[(8 + kNyqReg) * 32 + gbase + kNyqLane];   // yhat_{N/2}
             cd h[8];
@@ -648,7 +738,7 @@ __global__ void __launch_bounds__(kOpBlockA, UAPIC_OP_MINB_A) k_onepass_a(OpDev 
                 if (k1 == 0 && L.kap == 0) h[k1] = mk(a.x, c.x);
                 if (k1 == kNyqReg && L.kap == G / 2) h[k1] = mk(0.0, 0.0);
             }
-            bwdN<G>(h, L);
+            bwdN(h, L);
 #pragma unroll
             for (int s = 0; s < 8; ++s) {
                 const bool odd = (G == 1) ? (s & 1) : (g & 1);                 // parity of n = g + G s
@@ -658,13 +748,13 @@ __global__ void __launch_bounds__(kOpBlockA, UAPIC_OP_MINB_A) k_onepass_a(OpDev 
         }
 #pragma unroll
         for (int s = 0; s < 8; ++s) {
-            const double2 c = L.cs[g + G * s], et = gx[s * kRow + lane];
+            const double2 c = L.cs_s(s), et = gx[s * kRow + lane];
             const double iv = (1.0 + 0.5 * sps[s * kRow + lane] - b) * inv_eps;       // :177, same as :87
             fy_time(c.x, c.y, rb, iv, y1[s], y2[s], et.x, et.y, y1[s], y2[s]);
         }
         OP_SYNC(4);
-        fwdN<G>(y1, L);                                                      // :189-190
-        fwdN<G>(y2, L);
+        fwdN(y1, L);                                                      // :189-190
+        fwdN(y2, L);
         double qa1 = 0.0, qa2 = 0.0;
         cd wv[8];
 #pragma unroll
@@ -672,7 +762,7 @@ __global__ void __launch_bounds__(kOpBlockA, UAPIC_OP_MINB_A) k_onepass_a(OpDev 
             const cd fy1 = rmul(invN, y1[k1]), fy2 = rmul(invN, y2[k1]);     // :194-195
             const double2 h1 = yhs[k1 * 32 + lane], h2 = yhs[(8 + k1) * 32 + lane];
             cd pl, qt;
-            pl_qt<G>(L, k1, t, rt, eps, elt[k1], pl, qt);
+            pl_qt(L, k1, t, rt, eps, elt[k1], pl, qt);
             wv[k1] = cmulc(qt, elt[k1]);
             const cd yp1 = cfma(pl, fy1, cmul(elt[k1], mk(h1.x, h1.y)));     // :226 for y
             const cd yp2 = cfma(pl, fy2, cmul(elt[k1], mk(h2.x, h2.y)));
@@ -696,8 +786,8 @@ __global__ void __launch_bounds__(kOpBlockA, UAPIC_OP_MINB_A) k_onepass_a(OpDev 
             }
         }
         OP_SYNC(5);
-        bwdN<G>(y1, L);                                                      // :232
-        bwdN<G>(y2, L);
+        bwdN(y1, L);                                                      // :232
+        bwdN(y2, L);
         if (valid) {
 #pragma unroll
             for (int s = 0; s < 8; ++s) {
@@ -709,7 +799,7 @@ __global__ void __launch_bounds__(kOpBlockA, UAPIC_OP_MINB_A) k_onepass_a(OpDev 
             // W_n = (1/N) sum_k w_k exp(-i k tau_n) = conj( B(conj(w)) ) / N
 #pragma unroll
             for (int k1 = 0; k1 < 8; ++k1) wv[k1] = mk(invN * wv[k1].re, -invN * wv[k1].im);
-            bwdN<G>(wv, L);
+            bwdN(wv, L);
             if (valid) {
 #pragma unroll
                 for (int s = 0; s < 8; ++s) SM::wn(sbase)[g + G * s] = make_double2(wv[s].re, -wv[s].im);
@@ -773,6 +863,7 @@ __global__ void __launch_bounds__(kOpBlockA, UAPIC_OP_MINB_A) k_onepass_a(OpDev 
         }
         OP_SYNC(6);
     }
+    if (TM) L.tmem_release(&tmem_base);
 }
 
 // =================================================================================================
@@ -810,15 +901,15 @@ __global__ void __launch_bounds__(kOpBlockB, UAPIC_OP_MINB_B) k_onepass_b(OpDev 
             const double t = rec[1].x, rt = 1.0 / t;
             const cd e1 = mk(rec[2].y, -rec[3].x);
             cd elt[8], wv[8];
-            elt_modes<G>(L, t, eps, e1, elt);
+            elt_modes(L, t, eps, e1, elt);
 #pragma unroll
             for (int k1 = 0; k1 < 8; ++k1) {
                 cd pl, qt;
-                pl_qt<G>(L, k1, t, rt, eps, elt[k1], pl, qt);
+                pl_qt(L, k1, t, rt, eps, elt[k1], pl, qt);
                 const cd w = cmulc(qt, elt[k1]);
                 wv[k1] = mk(invN * w.re, -invN * w.im);
             }
-            bwdN<G>(wv, L);
+            bwdN(wv, L);
             __syncwarp();
 #pragma unroll
             for (int s = 0; s < 8; ++s) wx[s * kRow + lane] = make_double2(wv[s].re, -wv[s].im);
