@@ -278,6 +278,9 @@ typedef struct uapic3d_session uapic3d_session_t;
 int uapic3d_create(const uapic3d_config_t *cfg, uapic3d_session_t **out);
 int uapic3d_destroy(uapic3d_session_t *s);
 int uapic3d_upload_particles(uapic3d_session_t *s, const double *x, const double *v);
+/* particles sharded over ranks (one process per GPU): the library sums the raw rho nodes with ncclAllReduce before the periodic
+   copies, every rank solves the field redundantly (same scheme as uapic_session_init_nccl; id from uapic_nccl_unique_id) */
+int uapic3d_init_nccl(uapic3d_session_t *s, const void *id128, int nranks, int rank);
 /* init_particles_3d densities (particles.F90:152-190) from a counter-based stream keyed by first_global_index + k */
 int uapic3d_generate_particles(uapic3d_session_t *s, uint64_t seed, int64_t first_global_index);
 /* compute_rho_cic -> solve_poisson -> interpolate_eb_cic                         uapic3d.f90:76-83 */

@@ -33,7 +33,7 @@ EXPORTS = [
     "uapic_session_generate_particles", "uapic_session_generate_particles_strided", "uapic_session_init_fields", "uapic_session_step", "uapic_session_step_host", "uapic_session_synchronize",
     "uapic_session_download_particles", "uapic_session_download_particle_e", "uapic_session_download_fields",
     "uapic_session_energy_history", "uapic_session_sum_v", "uapic_session_launch_count", "uapic_session_device_bytes",
-    "uapic3d_create", "uapic3d_destroy", "uapic3d_upload_particles", "uapic3d_generate_particles", "uapic3d_init_fields", "uapic3d_substep",
+    "uapic3d_create", "uapic3d_destroy", "uapic3d_init_nccl", "uapic3d_upload_particles", "uapic3d_generate_particles", "uapic3d_init_fields", "uapic3d_substep",
     "uapic3d_run", "uapic3d_download_particles", "uapic3d_download_fields", "uapic3d_launch_count", "uapic3d_compute_rho_cic",
     "uapic3d_poisson", "uapic3d_interpolate_eb_cic",
 ]

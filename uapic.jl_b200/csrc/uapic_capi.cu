@@ -505,6 +505,27 @@ int nccl_need(NcclApi **out) {
 }
 }  // namespace
 
+// the same run-time NCCL binding for the other translation units (uapic_mrc3d.cu)
+int uapic_internal_nccl_comm_init(void **comm, const void *id128, int nranks, int rank) {
+    NcclApi *a = nullptr;
+    TRY(nccl_need(&a));
+    NcclId id;
+    memcpy(id.internal, id128, sizeof(id.internal));
+    const int rc = a->CommInitRank(comm, nranks, id, rank);
+    if (rc) return fail(UAPIC_ECUDA, "ncclCommInitRank(rank %d of %d) failed: %s", rank, nranks, a->GetErrorString(rc));
+    return UAPIC_OK;
+}
+int uapic_internal_nccl_allreduce(void *comm, void *buf, size_t count, int is_i64, cudaStream_t st) {
+    NcclApi *a = nccl_api();
+    const int rc = a->AllReduce(buf, buf, count, is_i64 ? 4 : 8, 0, comm, st);
+    if (rc) return fail(UAPIC_ECUDA, "ncclAllReduce failed: %s", a->GetErrorString(rc));
+    return UAPIC_OK;
+}
+void uapic_internal_nccl_comm_destroy(void *comm) {
+    NcclApi *a = nccl_api();
+    if (a->h && comm) a->CommDestroy(comm);
+}
+
 struct uapic_session {
     uapic_config_t cfg;
     MeshDev m;

@@ -8,6 +8,10 @@
 
 // records the message uapic_last_error() returns on this thread and returns `code` (uapic_capi.cu)
 int uapic_fail(int code, const char *fmt, ...);
+// NCCL bound at run time (uapic_capi.cu): communicator on the current device, in-place sum on a stream
+int uapic_internal_nccl_comm_init(void **comm, const void *id128, int nranks, int rank);
+int uapic_internal_nccl_allreduce(void *comm, void *buf, size_t count, int is_i64, cudaStream_t st);
+void uapic_internal_nccl_comm_destroy(void *comm);
 
 namespace uapic {
 

@@ -246,12 +246,14 @@ struct uapic3d_session {
     RhoAcc acc{};
     bool have_particles = false, fields_ready = false;
     bool own_stream = false;
+    void *nccl_comm = nullptr;         // particles sharded over ranks: the raw rho nodes are summed before the periodic copies
     // one captured sub-step per kind (uapic3d_substep): the loop body is ~22 launches of microsecond kernels, i.e. launch bound
     cudaGraphExec_t gexec[3] = {nullptr, nullptr, nullptr};
     double gdt[3] = {0, 0, 0}, gcoef[3] = {0, 0, 0};
     int64_t glaunches[3] = {0, 0, 0};
     ~uapic3d_session() {
         for (cudaGraphExec_t g : gexec) if (g) cudaGraphExecDestroy(g);
+        if (nccl_comm) uapic_internal_nccl_comm_destroy(nccl_comm);
         if (own_stream && stream) cudaStreamDestroy(stream);
         for (void *p : {(void *)x, (void *)v, (void *)ep, (void *)rho, (void *)e, raw, (void *)A, (void *)B}) if (p) cudaFree(p);
     }
@@ -320,6 +322,7 @@ int field_update3(uapic3d_session *s) {        // compute_rho_cic -> solve_poiss
     CU3(cudaMemsetAsync(s->raw, 0, 8 * m.nodes(), s->stream));
     const double vol = s->cfg.weight / (m.d[0] * m.d[1] * m.d[2]);                   // compute_rho_cic.f90:30
     if (np > 0) k3_deposit<<<grid3(s->sm_count, np), k3Block, 0, s->stream>>>(m, np, s->x, vol, s->acc);
+    if (s->nccl_comm) TRY3(uapic_internal_nccl_allreduce(s->nccl_comm, s->raw, m.nodes(), s->acc.i64 != nullptr, s->stream));
     k3_rho_finish<<<grid3(s->sm_count, (int64_t)m.nodes()), k3Block, 0, s->stream>>>(m, s->acc, s->rho);
     s->launches += 2;
     TRY3(solve3(m, s->sm_count, s->stream, s->rho, s->A, s->B, s->e, &s->launches));
@@ -395,6 +398,15 @@ int uapic3d_destroy(uapic3d_session_t *s) {
     cudaStreamSynchronize(s->stream);
     delete s;
     return UAPIC_OK;
+}
+
+int uapic3d_init_nccl(uapic3d_session_t *s, const void *id128, int nranks, int rank) {
+    if (!s || !id128) return uapic_fail(UAPIC_EINVAL, "uapic3d_init_nccl: null pointer");
+    if (nranks < 1 || rank < 0 || rank >= nranks) return uapic_fail(UAPIC_EINVAL, "uapic3d_init_nccl: rank %d of %d", rank, nranks);
+    CU3(cudaSetDevice(s->cfg.device));
+    if (s->nccl_comm) { uapic_internal_nccl_comm_destroy(s->nccl_comm); s->nccl_comm = nullptr; }
+    for (cudaGraphExec_t &g : s->gexec) if (g) { cudaGraphExecDestroy(g); g = nullptr; }       // captured sub-steps predate the collective
+    return uapic_internal_nccl_comm_init(&s->nccl_comm, id128, nranks, rank);
 }
 
 int uapic3d_upload_particles(uapic3d_session_t *s, const double *x, const double *v) {

@@ -48,7 +48,7 @@ def attach_nccl(session, group=None):
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     box = [nccl_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
-    session.init_nccl(box[0], world, rank)
+    session.init_nccl(box[0], world, rank)          # Session (2D UA path) and Session3D (fortran/uapic3d.f90) both have it
 
 
 def attach_torch_allreduce(session, group=None):

@@ -106,6 +106,11 @@ class Session3D:
     def __exit__(self, *exc):
         self.close()
 
+    def init_nccl(self, unique_id: bytes, nranks: int, rank: int):
+        """collective: the library sums the raw rho nodes over the ranks itself (uapic3d_init_nccl)"""
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        check(lib().uapic3d_init_nccl(self._h, buf, C.c_int(nranks), C.c_int(rank)))
+
     def upload_particles(self, x, v):
         check(lib().uapic3d_upload_particles(self._h, _f(x, (3, self.nbpart)), _f(v, (3, self.nbpart))))
 
