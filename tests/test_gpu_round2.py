@@ -219,3 +219,20 @@ def test_unsupported_ntau_fails_loudly():
             ub.Session(mesh, bad, 0.1, DT, 100)
     with pytest.raises(ub.UapicError):                    # general kernels exist for the two-barrier storage only
         ub.Session(mesh, 12, 0.1, DT, 100, storage_mode=ub.STORE_ONEPASS_LEAN)
+
+
+@pytest.mark.parametrize("nx,ny,ntau", [(96, 80, 16), (33, 21, 8), (20, 20, 32)])
+def test_session_on_meshes_that_are_not_powers_of_two(corc, nx, ny, ntau):
+    """k_field_solve's direct-DFT lines and the tiled halo for odd sizes (the reference's own particle test uses 20 x 20,
+    test/test_particles.jl:16)"""
+    npart, nstep = 5003, 3
+    om, x0, v0 = seeded_load(npart, nx=nx, ny=ny, seed=nx + ny)
+    mesh = ub.Mesh(0, DIMX, nx, 0, DIMY, ny)
+    w = DIMX * DIMY / npart
+    xo, vo = x0.copy(order="F"), v0.copy(order="F")
+    eno, _, _, emo = corc.run_bupdate(om, ntau, 0.1, DT, nstep, xo, vo, w)
+    x, v, en, em = ub.run_bupdate(mesh, ntau, 0.1, DT, nstep, x0, v0, w)
+    assert np.abs(np.mod(x[0] - xo[0] + DIMX / 2, DIMX) - DIMX / 2).max() < 1e-10 * DIMX
+    assert np.abs(v - vo).max() < 1e-11 * np.abs(vo).max()
+    assert np.abs(en - eno).max() < 1e-10 * np.abs(eno).max()
+    assert np.abs(em - emo).max() < 1e-10 * np.abs(emo).max()
