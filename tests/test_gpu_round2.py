@@ -236,3 +236,32 @@ def test_session_on_meshes_that_are_not_powers_of_two(corc, nx, ny, ntau):
     assert np.abs(v - vo).max() < 1e-11 * np.abs(vo).max()
     assert np.abs(en - eno).max() < 1e-10 * np.abs(eno).max()
     assert np.abs(em - emo).max() < 1e-10 * np.abs(emo).max()
+
+
+def test_empty_single_particle_and_largest_mesh(corc):
+    """edge cases: a session without particles (rho = 0, E = 0, energy 0), one particle, and the largest supported mesh side
+    (1024: 80 KB of dynamic shared memory inside the cooperative field solve)"""
+    mesh = ub.Mesh(0, DIMX, 32, 0, DIMY, 32)
+    with ub.Session(mesh, 16, 0.1, DT, 0, weight=1.0) as s:
+        s.upload_particles(np.zeros((2, 0), order="F"), np.zeros((2, 0), order="F"))
+        s.init_fields()
+        s.step(2)
+        s.synchronize()
+        assert np.array_equal(s.energy_history(), np.zeros(5))
+        e, rho = s.download_fields()
+        assert not e.any() and not rho.any()
+    om, x0, v0 = seeded_load(1, nx=32, ny=32, seed=2)
+    xo, vo = x0.copy(order="F"), v0.copy(order="F")
+    eno, _, _, _ = corc.run_bupdate(om, 16, 0.1, DT, 2, xo, vo, DIMX * DIMY)
+    x, v, en, _ = ub.run_bupdate(mesh, 16, 0.1, DT, 2, x0, v0, DIMX * DIMY)
+    assert np.abs(x - xo).max() < 1e-10 and np.abs(v - vo).max() < 1e-11 and np.abs(en - eno).max() < 1e-10 * np.abs(eno).max()
+    nx, ny, npart = 1024, 512, 4001
+    om, x0, v0 = seeded_load(npart, nx=nx, ny=ny, seed=3)
+    big = ub.Mesh(0, DIMX, nx, 0, DIMY, ny)
+    w = DIMX * DIMY / npart
+    xo, vo = x0.copy(order="F"), v0.copy(order="F")
+    eno, _, _, emo = corc.run_bupdate(om, 8, 0.1, DT, 2, xo, vo, w)
+    x, v, en, em = ub.run_bupdate(big, 8, 0.1, DT, 2, x0, v0, w)
+    assert np.abs(np.mod(x[0] - xo[0] + DIMX / 2, DIMX) - DIMX / 2).max() < 1e-10 * DIMX
+    assert np.abs(v - vo).max() < 1e-10 * np.abs(vo).max()
+    assert np.abs(en - eno).max() < 1e-10 * np.abs(eno).max() and np.abs(em - emo).max() < 1e-9 * np.abs(emo).max()
