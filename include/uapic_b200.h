@@ -182,6 +182,17 @@ int uapic_session_set_allreduce(uapic_session_t *s, uapic_allreduce_fn fn, void 
    a file, torch.distributed); every rank then calls uapic_session_init_nccl (collective: ncclCommInitRank on the session's
    device).  The communicator is destroyed with the session.  uapic_session_set_nccl_comm adopts an existing ncclComm_t
    instead (not destroyed by the session; NULL detaches).  Takes precedence over uapic_session_set_allreduce. */
+/* Peer-memory exchange over NVLink / NVSwitch: NO collective call.  Every rank folds its deposits into an exchange buffer that
+   the other ranks of the node map (CUDA IPC); a step then publishes a counter with st.release.sys and the field-solve kernel of
+   every rank waits for all counters (ld.acquire.sys over NVLink) and adds the ranks' buffers in rank order in its first phase --
+   the all-reduce is fused into the solve, the sum has the same bits on every rank (fp64 included), and a step is 6 launches.
+   Protocol: every rank calls uapic_session_peer_handle, the 64-byte handles are gathered by any means, every rank calls
+   uapic_session_init_peers with all of them (rank order); uapic_session_close_peers before destroying (all ranks, after a
+   barrier of the caller's).  Same node only; at most 16 ranks.  Takes precedence over NCCL and the callback. */
+#define UAPIC_PEER_HANDLE_BYTES 64
+int uapic_session_peer_handle(uapic_session_t *s, void *handle64);
+int uapic_session_init_peers(uapic_session_t *s, const void *handles, int nranks, int rank);
+int uapic_session_close_peers(uapic_session_t *s);
 #define UAPIC_NCCL_ID_BYTES 128
 int uapic_nccl_unique_id(void *id128);
 int uapic_nccl_version(int *version);

@@ -23,7 +23,9 @@ def run(mode, npart, ntau, nstep, x0, v0, mesh, w, rank, world, local, reducer="
     s = ub.Session(mesh, ntau, 0.1, np.pi / 16, hi - lo, weight=w, nbpart_global=npart, deposit_mode=mode, device=local,
                    stream=torch.cuda.current_stream().cuda_stream)
     if world > 1:
-        if reducer == "nccl":
+        if reducer == "peer":
+            ub.dist.attach_peer_exchange(s)     # no collective: the solve kernel sums the ranks' buffers over NVLink
+        elif reducer == "nccl":
             ub.dist.attach_nccl(s)              # in-library ncclAllReduce (uapic_session_init_nccl)
         else:
             ub.dist.attach_torch_allreduce(s)   # host callback hook (uapic_session_set_allreduce)
@@ -49,7 +51,8 @@ def main():
     w = 8 * np.pi ** 2 / npart
     res = {}
     for name, mode, reducer in (("fixed", ub.DEPOSIT_FIXED_POINT, "nccl"), ("fp64", ub.DEPOSIT_FP64_ATOMIC, "nccl"),
-                                ("fixed_callback", ub.DEPOSIT_FIXED_POINT, "torch")):
+                                ("fixed_callback", ub.DEPOSIT_FIXED_POINT, "torch"), ("fixed_peer", ub.DEPOSIT_FIXED_POINT, "peer"),
+                                ("fp64_peer", ub.DEPOSIT_FP64_ATOMIC, "peer")):
         x, v, en, e = run(mode, npart, ntau, nstep, x0, v0, mesh, w, rank, world, local, reducer)
         # gather the shards on rank 0
         xs = [None] * world

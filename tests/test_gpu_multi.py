@@ -31,6 +31,11 @@ def test_sharded_run_matches_single_gpu(tmp_path, world):
     assert fx["ranks_agree_on_energy"]
     fc = res["fixed_callback"]      # the host-callback hook gives the same bits as the in-library collective
     assert fc["bit_identical_x"] and fc["bit_identical_v"] and fc["bit_identical_energy"] and fc["bit_identical_emesh"], fc
+    fpeer = res["fixed_peer"]       # peer-memory exchange (sum inside the solve kernel over NVLink): same bits again
+    assert fpeer["bit_identical_x"] and fpeer["bit_identical_v"] and fpeer["bit_identical_energy"] and fpeer["bit_identical_emesh"], fpeer
+    assert fpeer["ranks_agree_on_energy"]
+    pp = res["fp64_peer"]           # fp64 deposits: every rank adds the ranks' buffers in the same order -> the ranks agree bit for bit
+    assert pp["ranks_agree_on_energy"] and pp["max_abs_dx"] < 1e-10 * 4 * 3.15 and pp["max_abs_dv"] < 1e-9 and pp["max_rel_denergy"] < 1e-10, pp
     m3 = res["mrc3d_fixed"]         # the 3D program sharded the same way
     assert m3["bit_identical_x"] and m3["bit_identical_v"] and m3["bit_identical_e"], m3
     fp = res["fp64"]

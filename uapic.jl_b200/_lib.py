@@ -28,7 +28,8 @@ EXPORTS = [
     "uapic_compute_f", "uapic_fft_tau", "uapic_ua_step_predict", "uapic_ua_step_correct", "uapic_ua_step1",
     "uapic_ua_step2", "uapic_compute_rho_m6_tau", "uapic_compute_v",
     "uapic_session_create", "uapic_session_destroy", "uapic_session_set_allreduce", "uapic_nccl_unique_id", "uapic_nccl_version",
-    "uapic_session_init_nccl", "uapic_session_set_nccl_comm", "uapic_session_upload_particles", "uapic_session_upload_particle_e",
+    "uapic_session_init_nccl", "uapic_session_set_nccl_comm", "uapic_session_peer_handle", "uapic_session_init_peers",
+    "uapic_session_close_peers", "uapic_session_upload_particles", "uapic_session_upload_particle_e",
     "uapic_session_set_fusion", "uapic_session_enable_timing", "uapic_session_phase_times", "uapic_session_field_barrier_time", "uapic_session_set_sort",
     "uapic_session_generate_particles", "uapic_session_generate_particles_strided", "uapic_session_init_fields", "uapic_session_step", "uapic_session_step_host", "uapic_session_synchronize",
     "uapic_session_download_particles", "uapic_session_download_particle_e", "uapic_session_download_fields",

@@ -555,6 +555,12 @@ struct uapic_session {
     int64_t n_energy = 0, cap_energy = 0;
     uapic_allreduce_fn reduce = nullptr;
     void *reduce_ctx = nullptr;
+    // peer-memory exchange (uapic_session_init_peers): every rank's folded deposits sit in an IPC-exported buffer that the other
+    // ranks map over NVLink; the sum over the ranks happens inside k_field_solve -- no collective call at all
+    DevBuf xchg, peer_err;             // [256 B of flags | parity 0: 2 meshes | parity 1: 2 meshes]
+    void *peer_base[kMaxPeers] = {};   // rank r's xchg as mapped here (own entry = xchg.p)
+    int npeers = 0, peer_rank = 0;
+    unsigned long long xchg_seq = 0;
     void *nccl_comm = nullptr;         // ncclComm_t: the library sums the raw rho meshes itself (uapic_session_init_nccl)
     bool nccl_owned = false;
     int nccl_rank = 0, nccl_nranks = 1;
@@ -572,6 +578,7 @@ struct uapic_session {
         if (up_stream) cudaStreamDestroy(up_stream);
         if (down_stream) cudaStreamDestroy(down_stream);
         if (nccl_comm && nccl_owned) { NcclApi *a = nccl_api(); if (a->h) a->CommDestroy(nccl_comm); }
+        for (int r = 0; r < npeers; ++r) if (r != peer_rank && peer_base[r]) cudaIpcCloseMemHandle(peer_base[r]);
     }
 };
 
@@ -620,6 +627,40 @@ int session_field_barrier(uapic_session *s, int nmesh) {
     const bool copies = s->onepass && nmesh == 2;
     const bool exchange = s->nccl_comm || s->reduce;
     int fold_in_kernel = 1;
+    if (s->npeers > 0 && !s->split_solve) {
+        // fold my copies into my exchange buffer, publish, and let the solve kernel add the ranks' buffers over NVLink
+        const unsigned long long seq = ++s->xchg_seq;
+        const size_t half = 2 * nrho * 8;                              // bytes of one parity (room for two meshes)
+        const size_t off = 256 + (size_t)(seq & 1) * half;
+        CU(launch_fold_publish(s->lc, s->acc, (int64_t)nrho * nmesh, copies ? UAPIC_RAW_COPIES : 1, s->xchg.as<char>() + off,
+                               s->xchg.as<unsigned long long>(), seq));
+        SolveBatch B{};
+        B.nb = nmesh;
+        B.partial = s->solve_scratch.as<double>();
+        B.halo_tiled = s->onepass ? 1 : 0;
+        B.fold_copies = 1;
+        B.fold_stride = 2 * nrho;
+        B.npeers = s->npeers;
+        for (int r = 0; r < s->npeers; ++r) {
+            B.peer_data[r] = reinterpret_cast<const unsigned long long *>(static_cast<const char *>(s->peer_base[r]) + off);
+            B.peer_flag[r] = reinterpret_cast<const unsigned long long *>(s->peer_base[r]);
+        }
+        B.peer_seq = seq;
+        B.peer_mesh_stride = nrho;
+        B.peer_error = s->peer_err.as<int>();
+        if (nmesh == 2) {
+            B.acc[0] = s->acc;   B.rho[0] = s->rho_p.as<double>(); B.emesh[0] = s->emesh_p.as<double2>(); B.ehalo[0] = s->ehalo_p.as<double2>();
+            B.rk[0] = s->rk2.as<double2>(); B.ek[0] = s->ek2.as<double2>(); B.energy[0] = s->energy.as<double>() + s->n_energy;
+            B.acc[1] = s->acc_c; B.rho[1] = s->rho.as<double>();   B.emesh[1] = s->emesh.as<double2>();   B.ehalo[1] = s->ehalo.as<double2>();
+            B.rk[1] = s->rk.as<double2>();  B.ek[1] = s->ek.as<double2>();  B.energy[1] = s->energy.as<double>() + s->n_energy + 1;
+        } else {
+            B.acc[0] = s->acc;   B.rho[0] = s->rho.as<double>();   B.emesh[0] = s->emesh.as<double2>();   B.ehalo[0] = s->ehalo.as<double2>();
+            B.rk[0] = s->rk.as<double2>();  B.ek[0] = s->ek.as<double2>();  B.energy[0] = s->energy.as<double>() + s->n_energy;
+        }
+        CU(launch_field_solve(s->lc, s->m, B));
+        s->n_energy += nmesh;
+        return UAPIC_OK;
+    }
     if (copies) {
         if (exchange || s->split_solve) CU(launch_fold_raw(s->lc, s->acc, 2 * (int64_t)nrho, UAPIC_RAW_COPIES));
         else fold_in_kernel = UAPIC_RAW_COPIES;        // single GPU: the solve kernel folds the copies while it scales them
@@ -934,6 +975,58 @@ int uapic_session_set_nccl_comm(uapic_session_t *s, void *comm) {
     if (comm) { NcclApi *a = nullptr; TRY(nccl_need(&a)); }
     session_drop_nccl(s);
     s->nccl_comm = comm; s->nccl_owned = false;
+    return UAPIC_OK;
+}
+
+int uapic_session_peer_handle(uapic_session_t *s, void *handle64) {
+    if (!s || !handle64) return fail(UAPIC_EINVAL, "uapic_session_peer_handle: null pointer");
+    static_assert(sizeof(cudaIpcMemHandle_t) == UAPIC_PEER_HANDLE_BYTES, "cudaIpcMemHandle_t is 64 bytes");
+    TRY(session_bind(s));
+    if (!s->xchg.p) {
+        const size_t nrho = (size_t)s->m.ld * (s->m.ny + 1);
+        TRY(session_alloc(s, s->xchg, 256 + 2 * (2 * nrho * 8)));
+        TRY(session_alloc(s, s->peer_err, 256));
+        CU(cudaMemset(s->xchg.p, 0, s->xchg.bytes));
+        CU(cudaMemset(s->peer_err.p, 0, 256));
+    }
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, s->xchg.p));
+    memcpy(handle64, &h, sizeof(h));
+    return UAPIC_OK;
+}
+
+int uapic_session_init_peers(uapic_session_t *s, const void *handles, int nranks, int rank) {
+    if (!s || !handles) return fail(UAPIC_EINVAL, "uapic_session_init_peers: null pointer");
+    if (nranks < 1 || nranks > kMaxPeers || rank < 0 || rank >= nranks) return fail(UAPIC_EINVAL, "uapic_session_init_peers: rank %d of %d (at most %d ranks)", rank, nranks, kMaxPeers);
+    if (!s->xchg.p) return fail(UAPIC_ESTATE, "call uapic_session_peer_handle first (every rank), then exchange the handles");
+    if (s->npeers) return fail(UAPIC_ESTATE, "peers are already attached");
+    TRY(session_bind(s));
+    for (int r = 0; r < nranks; ++r) {
+        if (r == rank) { s->peer_base[r] = s->xchg.p; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, static_cast<const char *>(handles) + (size_t)r * sizeof(h), sizeof(h));
+        void *p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            for (int q = 0; q < r; ++q) if (q != rank && s->peer_base[q]) { cudaIpcCloseMemHandle(s->peer_base[q]); s->peer_base[q] = nullptr; }
+            return fail(UAPIC_ECUDA, "cudaIpcOpenMemHandle for rank %d failed: %s (peer access over NVLink is needed)", r, cudaGetErrorString(e));
+        }
+        s->peer_base[r] = p;
+    }
+    s->npeers = nranks; s->peer_rank = rank;
+    return UAPIC_OK;
+}
+
+int uapic_session_close_peers(uapic_session_t *s) {
+    if (!s) return fail(UAPIC_EINVAL, "session is null");
+    TRY(session_bind(s));
+    CU(cudaStreamSynchronize(s->lc.stream));
+    int err = 0;
+    if (s->peer_err.p) CU(cudaMemcpy(&err, s->peer_err.p, sizeof(int), cudaMemcpyDeviceToHost));
+    for (int r = 0; r < s->npeers; ++r) if (r != s->peer_rank && s->peer_base[r]) { cudaIpcCloseMemHandle(s->peer_base[r]); s->peer_base[r] = nullptr; }
+    s->npeers = 0;
+    if (err) return fail(UAPIC_ECUDA, "a peer rank did not publish its deposits within 4 s during this session: results after that point are invalid");
     return UAPIC_OK;
 }
 

@@ -73,6 +73,7 @@ cudaError_t launch_poisson(const LaunchCtx &c, const MeshDev &m, const PoissonWo
 bool poisson_size_supported(int n);
 // the session's field solve in one cooperative launch for nb <= 2 meshes at once (k_field_solve, uapic_kernels.cu):
 // fold of `fold_copies` raw copies (copy k of mesh b at acc[b] + k*fold_stride) -> rho epilogue -> Poisson -> energy -> halo copy
+constexpr int kMaxPeers = 16;
 struct SolveBatch {
     int nb;
     RhoAcc acc[2];         // summed raw deposits (fp64 or fixed point)
@@ -85,7 +86,16 @@ struct SolveBatch {
     int halo_tiled;        // 1: 2 x 4-node tiled halo (one-pass kernels); 0: linear halo (two-barrier kernels)
     int fold_copies;       // >= 1
     size_t fold_stride;    // elements between copies
+    // peer mode (uapic_session_init_peers): the sum over the ranks happens in phase 0, straight out of the ranks' exchange buffers
+    int npeers;                                   // 0 = off
+    const unsigned long long *peer_data[kMaxPeers];   // rank r's folded deposits of this exchange: mesh b at + b * peer_mesh_stride (8-byte elements)
+    const unsigned long long *peer_flag[kMaxPeers];   // rank r's "published" counter
+    unsigned long long peer_seq;                  // wait until every flag >= this
+    size_t peer_mesh_stride;
+    int *peer_error;                              // set to 1 if a rank did not publish within ~4 s
 };
+cudaError_t launch_fold_publish(const LaunchCtx &c, const RhoAcc &acc, int64_t n, int copies, void *dst, unsigned long long *flag,
+                                unsigned long long seq);
 size_t field_solve_scratch_bytes();
 cudaError_t launch_field_solve(const LaunchCtx &c, const MeshDev &m, const SolveBatch &B);
 // periodic halo copy of the E mesh for the fused gathers: node (i,j), i in [-2,nx+3], j in [-2,ny+3], holds E(i mod nx, j mod ny)

@@ -521,6 +521,22 @@ __global__ void __launch_bounds__(kSolveBlock) k_field_solve(MeshDev m, SolveBat
     const double dxdy = m.dx * m.dy;
     const int ncell = nx * ny, per = (ncell + kSolveParts - 1) / kSolveParts;
 
+    // ---- peer mode: wait until every rank has published exchange number B.peer_seq (its folded deposits sit in ITS exchange
+    //      buffer, mapped here over NVLink), then phase 0 sums the ranks' buffers in rank order -- the all-reduce lives inside the
+    //      solve, every rank adds in the same order, so the sum is the same bits everywhere (fp64 included)
+    if (B.npeers > 0) {
+        if (threadIdx.x == 0) {
+            const long long t0 = clock64();
+            for (int r = 0; r < B.npeers; ++r) {
+                unsigned long long seen;
+                do {
+                    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(B.peer_flag[r]) : "memory");
+                    if (seen < B.peer_seq && clock64() - t0 > (1ll << 33)) { atomicExch(B.peer_error, 1); break; }   // ~4 s: a rank is gone
+                } while (seen < B.peer_seq);
+            }
+        }
+        __syncthreads();
+    }
     // ---- phase 0: fold the copies, scale, partial sums over fixed chunks ----
     for (int task = blockIdx.x; task < nb * kSolveParts; task += gridDim.x) {
         const int b = task / kSolveParts, c = task - b * kSolveParts;
@@ -532,7 +548,27 @@ __global__ void __launch_bounds__(kSolveBlock) k_field_solve(MeshDev m, SolveBat
         for (int idx = lo + threadIdx.x; idx < hi; idx += kSolveBlock) {
             const int j = idx / nx, i = idx - j * nx, q = i + ld * j;
             double raw;
-            if (acc.i64) {
+            if (B.npeers > 0) {
+                const size_t off = (size_t)b * B.peer_mesh_stride + q;
+                if (acc.i64) {
+                    unsigned long long t = 0;
+                    for (int r = 0; r < B.npeers; ++r) {
+                        unsigned long long u;
+                        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(u) : "l"(B.peer_data[r] + off));
+                        t += u;
+                    }
+                    ipart += (long long)t;
+                    raw = (double)(long long)t * inv_scale;
+                } else {
+                    double t = 0.0;
+                    for (int r = 0; r < B.npeers; ++r) {
+                        double u;
+                        asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(u) : "l"(B.peer_data[r] + off));
+                        t += u;
+                    }
+                    raw = t;
+                }
+            } else if (acc.i64) {
                 unsigned long long t = acc.i64[q];
                 for (int k = 1; k < B.fold_copies; ++k) t += acc.i64[(size_t)k * B.fold_stride + q];
                 ipart += (long long)t;
@@ -931,6 +967,37 @@ __global__ void __launch_bounds__(kBlock) k_fold_raw(RhoAcc acc, int64_t n, int 
     }
 }
 }  // namespace
+
+namespace {
+// fold the CTA-private copies of `acc` (n elements each, `copies` of them) into `dst` (the exchange buffer peers read)
+__global__ void __launch_bounds__(kBlock) k_fold_to(RhoAcc acc, int64_t n, int copies, unsigned long long *dst) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        if (acc.i64) {
+            unsigned long long t = acc.i64[i];
+            for (int c = 1; c < copies; ++c) t += acc.i64[(size_t)c * n + i];
+            dst[i] = t;
+        } else {
+            double t = acc.f64[i];
+            for (int c = 1; c < copies; ++c) t += acc.f64[(size_t)c * n + i];
+            reinterpret_cast<double *>(dst)[i] = t;
+        }
+    }
+}
+// "my deposits of exchange number `seq` are in place": release at system scope, peers acquire it over NVLink
+__global__ void k_publish(unsigned long long *flag, unsigned long long seq) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(seq) : "memory");
+}
+}  // namespace
+
+cudaError_t launch_fold_publish(const LaunchCtx &c, const RhoAcc &acc, int64_t n, int copies, void *dst, unsigned long long *flag,
+                                unsigned long long seq) {
+    if (n <= 0) return cudaErrorInvalidValue;
+    k_fold_to<<<grid_for(c, n, kBlock), kBlock, 0, c.stream>>>(acc, n, copies < 1 ? 1 : copies, reinterpret_cast<unsigned long long *>(dst));
+    k_publish<<<1, 1, 0, c.stream>>>(flag, seq);
+    count(c, 2);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_fold_raw(const LaunchCtx &c, const RhoAcc &acc, int64_t n, int copies) {
     if (copies <= 1 || n <= 0) return cudaSuccess;

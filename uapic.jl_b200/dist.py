@@ -51,6 +51,19 @@ def attach_nccl(session, group=None):
     session.init_nccl(box[0], world, rank)          # Session (2D UA path) and Session3D (fortran/uapic3d.f90) both have it
 
 
+def attach_peer_exchange(session, group=None):
+    """the fused path: no collective in the step.  The ranks' deposit meshes are summed inside the field-solve kernel straight
+    out of each other's memory over NVLink (uapic_session_init_peers).  torch.distributed is used once, to gather the 64-byte
+    IPC handles; Session.close() then synchronises the ranks before anything is unmapped."""
+    import torch.distributed as dist
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    handles = [None] * world
+    dist.all_gather_object(handles, session.peer_handle(), group=group)
+    session.init_peers(b"".join(handles), world, rank)
+    session._peer_group = group
+
+
 def attach_torch_allreduce(session, group=None):
     """make `session` sum its raw rho mesh over the ranks of `group` with torch.distributed (NCCL), through the C ABI's
     callback hook.  The collective is issued on the stream handle the library passes (the session's stream), whatever

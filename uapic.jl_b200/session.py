@@ -57,6 +57,13 @@ class Session:
     # ---- lifetime --------------------------------------------------------------------------------------
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
+            if getattr(self, "_peer_group", False) is not False:
+                # nobody may unmap or free an exchange buffer a peer still reads: barrier, unmap, barrier, then free
+                import torch.distributed as dist
+                group, self._peer_group = self._peer_group, False
+                dist.barrier(group=group)
+                lib().uapic_session_close_peers(self._h)
+                dist.barrier(group=group)
             lib().uapic_session_destroy(self._h)
             self._h = C.c_void_p()
 
@@ -192,6 +199,20 @@ class Session:
         return n.value
 
     # ---- multi-GPU ---------------------------------------------------------------------------------------
+    def peer_handle(self) -> bytes:
+        """64-byte CUDA IPC handle of this session's exchange buffer (uapic_session_peer_handle)"""
+        buf = C.create_string_buffer(64)
+        check(lib().uapic_session_peer_handle(self._h, buf))
+        return buf.raw
+
+    def init_peers(self, handles: bytes, nranks: int, rank: int):
+        """map the exchange buffers of all ranks (handles concatenated in rank order): the sum of the raw rho meshes over the
+        ranks then happens inside the field-solve kernel, over NVLink, without a collective call"""
+        if len(handles) != 64 * nranks:
+            raise ValueError("need one 64-byte handle per rank")
+        buf = C.create_string_buffer(bytes(handles), len(handles))
+        check(lib().uapic_session_init_peers(self._h, buf, C.c_int(nranks), C.c_int(rank)))
+
     def init_nccl(self, unique_id: bytes, nranks: int, rank: int):
         """collective: create this session's NCCL communicator inside the library (uapic_session_init_nccl); from then on
         the library itself sums the raw rho meshes with ncclAllReduce on the session's stream"""
