@@ -232,8 +232,9 @@ def main():
                          "legacy two-barrier kernels 128 B (full) / 16 B + recompute (hybrid)")
     ap.add_argument("--scheme", default="m6", choices=["m6", "cic"],
                     help="shape function: m6 = what the reference ships (the metric is quoted on it); cic = build-defined bilinear variant")
-    ap.add_argument("--reduce", default="nccl", choices=["nccl", "torch"],
-                    help="N > 1: who sums the raw rho meshes -- nccl: ncclAllReduce enqueued by the library (default); torch: host callback")
+    ap.add_argument("--reduce", default="nccl", choices=["nccl", "torch", "peer"],
+                    help="N > 1: who sums the raw rho meshes -- nccl: ncclAllReduce enqueued by the library (default); torch: host callback; "
+                         "peer: inside the field-solve kernel, out of the ranks' IPC-mapped buffers over NVLink (no collective)")
     ap.add_argument("--eps", type=float, default=EPS, help="the small parameter (bupdate.F90:18: 0.1); BASELINE config 4 sweeps 1e-1 .. 1e-5")
     ap.add_argument("--particles", type=int, default=0, help="override the workload's TOTAL particle count (strong scaling)")
     ap.add_argument("--peaks", action="store_true", help="measure the fp64 DFMA peak of the device, write profiles/fp64_peak.json, exit")
@@ -302,7 +303,9 @@ def main():
     if not sort_on:
         s.set_sort(0)
     if world > 1:
-        if args.reduce == "nccl":
+        if args.reduce == "peer":
+            ub.dist.attach_peer_exchange(s)        # no collective: the field-solve kernel sums the ranks' deposit meshes over NVLink
+        elif args.reduce == "nccl":
             ub.dist.attach_nccl(s)                 # the library owns the communicator and enqueues ncclAllReduce itself
         else:
             ub.dist.attach_torch_allreduce(s)      # host-callback hook (torch.distributed)
@@ -434,7 +437,7 @@ def main():
                                    "onepass-lean": "one-pass lean (one field barrier per step, 48 B per particle-tau across it)"}[storage],
                        "hbm_free_gb_before_alloc": round(free_b / 1e9, 1), "particle_reordering": "every step, 8x8-cell bins" if (sort_on and onepass) else "off",
                        "l2": f"inputs larger than L2: {s.device_bytes / 1e9:.1f} GB of particle state per GPU streamed every step",
-                       "parallelism": f"particle shards x{world}, allreduce(rho) over NCCL ({'in-library ncclAllReduce' if args.reduce == 'nccl' else 'torch.distributed callback'})" if world > 1 else "single GPU"},
+                       "parallelism": f"particle shards x{world}, allreduce(rho) over NCCL ({ {'nccl': 'in-library ncclAllReduce', 'torch': 'torch.distributed callback', 'peer': 'summed inside the field-solve kernel over NVLink peer memory, no collective'}[args.reduce] })" if world > 1 else "single GPU"},
             "e2e": e2e,
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": hbm, "unit": "GB/s",
