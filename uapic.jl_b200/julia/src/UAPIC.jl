@@ -19,7 +19,7 @@ export fft_tau!, ifft_tau!
 export integrate, gnuplot, errors
 export Session, upload_particles!, init_fields!, step!, step_host!, generate_particles!, set_sort!, download_particles, download_fields, energy_history
 export STORE_FULL, STORE_HYBRID, STORE_ONEPASS, STORE_ONEPASS_LEAN, SCHEME_M6, SCHEME_CIC
-export nccl_unique_id, init_nccl!, sum_v
+export nccl_unique_id, init_nccl!, sum_v, peer_handle, init_peers!, close_peers!
 export Mesh3D, Session3D, run_uapic3d!
 export UAPICError
 
@@ -389,6 +389,16 @@ end
 init_nccl!(s::Session, id::Vector{UInt8}, nranks, rank) =
     (length(id) == 128 || error("the NCCL unique id is 128 bytes");
      check(ccall((:uapic_session_init_nccl, libuapic), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Cint, Cint), s.handle, id, nranks, rank)))
+# the same exchange without any collective (one node): the field-solve kernel adds the ranks' deposit meshes out of each other's
+# memory over NVLink.  handles = the 64-byte handles of all ranks, concatenated in rank order (e.g. MPI.Allgather(peer_handle(s), comm))
+function peer_handle(s::Session)
+    h = zeros(UInt8, 64)
+    check(ccall((:uapic_session_peer_handle, libuapic), Cint, (Ptr{Cvoid}, Ptr{UInt8}), s.handle, h))
+    h
+end
+init_peers!(s::Session, handles::Vector{UInt8}, nranks, rank) =
+    check(ccall((:uapic_session_init_peers, libuapic), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Cint, Cint), s.handle, handles, nranks, rank))
+close_peers!(s::Session) = check(ccall((:uapic_session_close_peers, libuapic), Cint, (Ptr{Cvoid},), s.handle))   # all ranks, after a barrier
 # sum(v[1,:]), sum(v[2,:]) of this shard -- what test/bupdate.jl:112 prints every step
 function sum_v(s::Session)
     out = zeros(2)
