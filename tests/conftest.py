@@ -33,3 +33,10 @@ def seeded_load(npart, nx=128, ny=64, seed=1234):
 
 def periodic_diff(a, b, period):
     return np.abs(np.mod(a - b + period / 2, period) - period / 2)
+
+
+def golden_files():
+    """tests/golden/bupdate_*.npz (frozen agreement of the two oracles, make_golden.py) and, when somebody has run
+    tools/pin_against_reference.sh on a machine with gfortran + FFTW, pinned_*.npz: outputs of the reference's own Fortran"""
+    import glob
+    return sorted(glob.glob(os.path.join(GOLDEN, "bupdate_*.npz")) + glob.glob(os.path.join(GOLDEN, "pinned_*.npz")))

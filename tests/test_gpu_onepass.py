@@ -12,7 +12,7 @@ import pytest
 
 import uapic_b200 as ub
 
-from conftest import GOLDEN, periodic_diff, seeded_load
+from conftest import golden_files, GOLDEN, periodic_diff, seeded_load
 
 pytestmark = pytest.mark.gpu
 
@@ -69,7 +69,7 @@ def test_onepass_session_vs_oracle(corc, mode, ntau, nx, ny, npart, nstep, eps):
     assert np.abs(emesh_g - emesh_o).max() < 1e-10 * np.abs(emesh_o).max()
 
 
-@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "bupdate_*.npz"))))
+@pytest.mark.parametrize("path", golden_files(), ids=lambda p: os.path.basename(p)[:-4])
 def test_onepass_against_golden(path):
     g = np.load(path)
     nx, ny, ntau, nstep = int(g["nx"]), int(g["ny"]), int(g["ntau"]), int(g["nstep"])

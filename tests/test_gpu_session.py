@@ -15,7 +15,7 @@ import pytest
 import oracle
 import uapic_b200 as ub
 
-from conftest import GOLDEN, periodic_diff, seeded_load
+from conftest import golden_files, GOLDEN, periodic_diff, seeded_load
 
 pytestmark = pytest.mark.gpu
 
@@ -76,7 +76,7 @@ def test_session_julia_wrap_vs_oracle(corc):
     assert xg[0].min() >= 0 and xg[0].max() < DIMX and xg[1].min() >= 0 and xg[1].max() < DIMY   # stored wrapped
 
 
-@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "bupdate_*.npz"))))
+@pytest.mark.parametrize("path", golden_files(), ids=lambda p: os.path.basename(p)[:-4])
 def test_session_against_golden(path):
     g = np.load(path)
     nx, ny, ntau, nstep = int(g["nx"]), int(g["ny"]), int(g["ntau"]), int(g["nstep"])

@@ -9,7 +9,7 @@ import pytest
 import oracle
 from oracle import nporc
 
-from conftest import GOLDEN, periodic_diff, seeded_load
+from conftest import golden_files, GOLDEN, periodic_diff, seeded_load
 
 
 # ---- test/test_poisson.jl:1-49 -----------------------------------------------------------------
@@ -148,7 +148,7 @@ def test_threads_do_not_change_results_beyond_roundoff(corc):
     assert np.abs(outs[0][2] - outs[1][2]).max() / outs[0][2].max() < 1e-13
 
 
-@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "bupdate_*.npz"))))
+@pytest.mark.parametrize("path", golden_files(), ids=lambda p: os.path.basename(p)[:-4])
 def test_c_oracle_against_golden(corc, path):
     g = np.load(path)
     nx, ny, ntau, nstep = int(g["nx"]), int(g["ny"]), int(g["ntau"]), int(g["nstep"])
