@@ -627,7 +627,9 @@ int session_field_barrier(uapic_session *s, int nmesh) {
     const bool copies = s->onepass && nmesh == 2;
     const bool exchange = s->nccl_comm || s->reduce;
     int fold_in_kernel = 1;
-    if (s->npeers > 0 && !s->split_solve) {
+    if (s->npeers > 0 && s->split_solve)
+        return fail(UAPIC_EUNSUPPORTED, "UAPIC_SPLIT_SOLVE=1 (the six-kernel field solve) cannot sum over peer memory: use NCCL or the callback with it");
+    if (s->npeers > 0) {
         // fold my copies into my exchange buffer, publish, and let the solve kernel add the ranks' buffers over NVLink
         const unsigned long long seq = ++s->xchg_seq;
         const size_t half = 2 * nrho * 8;                              // bytes of one parity (room for two meshes)
