@@ -17,76 +17,76 @@ program pin_driver
 
     implicit none
 
-    integer(8) :: nbpart
-    integer    :: nx, ny, ntau, nstep, istep, ie
-    real(8)    :: eps, dt, xmax, ymax, w
-    type(mesh_t)      :: mesh
-    type(fields_2d_t) :: fields
-    type(particles_t) :: particles
-    type(poisson_t)   :: poisson
-    type(ua_t)        :: ua
-    complex(8), allocatable :: xt(:,:,:), xf(:,:,:), yt(:,:,:), yf(:,:,:), fx(:,:,:), fy(:,:,:), gx(:,:,:), gy(:,:,:)
-    real(8), allocatable :: et(:,:,:), energy(:)
+    integer(8) :: npt
+    integer    :: nx, ny, nta, nst, it, ie
+    real(8)    :: epsv, dtm, xmax, ymax, w
+    type(mesh_t)      :: msh
+    type(fields_2d_t) :: fld
+    type(particles_t) :: pt
+    type(poisson_t)   :: psn
+    type(ua_t)        :: uat
+    complex(8), allocatable :: xtau(:,:,:), xhat(:,:,:), ytau(:,:,:), yhat(:,:,:), fxh(:,:,:), fyh(:,:,:), gxh(:,:,:), gyh(:,:,:)
+    real(8), allocatable :: etau(:,:,:), energy(:)
     character(len=512) :: fin, fout
 
     call get_command_argument(1, fin)
     call get_command_argument(2, fout)
     open(10, file=trim(fin), access='stream', form='unformatted', status='old')
-    read(10) nbpart, nx, ny, ntau, nstep
-    read(10) eps, dt, xmax, ymax, w
-    particles%nbpart = nbpart
-    allocate(particles%x(2,nbpart), particles%v(2,nbpart), particles%e(2,nbpart), particles%b(nbpart), particles%t(nbpart))
-    read(10) particles%x
-    read(10) particles%v
+    read(10) npt, nx, ny, nta, nst
+    read(10) epsv, dtm, xmax, ymax, w
+    pt%nbpart = npt
+    allocate(pt%x(2,npt), pt%v(2,npt), pt%e(2,npt), pt%b(npt), pt%t(npt))
+    read(10) pt%x
+    read(10) pt%v
     close(10)
-    particles%w = w
+    pt%w = w
 
     pi = 4d0 * atan(1d0)
-    call init_mesh( mesh, 0d0, xmax, nx, 0d0, ymax, ny )
-    call init_fields( fields, mesh )
-    call init_poisson( poisson, mesh )
-    call init_ua( ua, ntau, eps, nbpart )
+    call init_mesh( msh, 0d0, xmax, nx, 0d0, ymax, ny )
+    call init_fields( fld, msh )
+    call init_poisson( psn, msh )
+    call init_ua( uat, nta, epsv, npt )
 
-    allocate(et(ntau,2,nbpart), xt(ntau,2,nbpart), xf(ntau,2,nbpart), yt(ntau,2,nbpart), yf(ntau,2,nbpart))
-    allocate(fx(ntau,2,nbpart), fy(ntau,2,nbpart), gx(ntau,2,nbpart), gy(ntau,2,nbpart))
-    allocate(energy(1 + 2*nstep))
+    allocate(etau(nta,2,npt), xtau(nta,2,npt), xhat(nta,2,npt), ytau(nta,2,npt), yhat(nta,2,npt))
+    allocate(fxh(nta,2,npt), fyh(nta,2,npt), gxh(nta,2,npt), gyh(nta,2,npt))
+    allocate(energy(1 + 2*nst))
     ie = 0
 
-    call compute_rho_m6_real( fields, particles )
-    call solve_poisson( poisson, fields );  call record()
-    call interpolate_eb_m6_real( particles, fields )
+    call compute_rho_m6_real( fld, pt )
+    call solve_poisson( psn, fld );  call record()
+    call interpolate_eb_m6_real( pt, fld )
 
-    do istep = 1, nstep
-        call preparation( ua, dt, particles, xt, yt)
-        call interpolation( particles, et, fields, ua, xt)
-        call compute_f( fx, fy, ua, particles, xt, yt, et )
-        call ua_step1( xt, xf, ua, particles, fx )
-        call ua_step1( yt, yf, ua, particles, fy )
-        call deposition( particles, fields, ua, xt)
-        call solve_poisson( poisson, fields );  call record()
-        call interpolation( particles, et, fields, ua, xt)
-        call compute_f( gx, gy, ua, particles, xt, yt, et )
-        call ua_step2( xt, xf, ua, particles, fx, gx )
-        call ua_step2( yt, yf, ua, particles, fy, gy )
-        call deposition( particles, fields, ua, xt)
-        call solve_poisson( poisson, fields );  call record()
-        call interpolation( particles, et, fields, ua, xt)
-        call compute_v( ua, particles, yt, yf )
+    do it = 1, nst
+        call preparation( uat, dtm, pt, xtau, ytau)
+        call interpolation( pt, etau, fld, uat, xtau)
+        call compute_f( fxh, fyh, uat, pt, xtau, ytau, etau )
+        call ua_step1( xtau, xhat, uat, pt, fxh )
+        call ua_step1( ytau, yhat, uat, pt, fyh )
+        call deposition( pt, fld, uat, xtau)
+        call solve_poisson( psn, fld );  call record()
+        call interpolation( pt, etau, fld, uat, xtau)
+        call compute_f( gxh, gyh, uat, pt, xtau, ytau, etau )
+        call ua_step2( xtau, xhat, uat, pt, fxh, gxh )
+        call ua_step2( ytau, yhat, uat, pt, fyh, gyh )
+        call deposition( pt, fld, uat, xtau)
+        call solve_poisson( psn, fld );  call record()
+        call interpolation( pt, etau, fld, uat, xtau)
+        call compute_v( uat, pt, ytau, yhat )
     end do
 
     open(11, file=trim(fout), access='stream', form='unformatted', status='replace')
-    write(11) nbpart, nx, ny, ntau, nstep
-    write(11) particles%x
-    write(11) particles%v
+    write(11) npt, nx, ny, nta, nst
+    write(11) pt%x
+    write(11) pt%v
     write(11) energy
-    write(11) fields%e
+    write(11) fld%e
     close(11)
 
 contains
 
     subroutine record()
         ie = ie + 1
-        energy(ie) = sum(fields%e(1,:,:)**2 + fields%e(2,:,:)**2) * mesh%dx * mesh%dy
+        energy(ie) = sum(fld%e(1,:,:)**2 + fld%e(2,:,:)**2) * msh%dx * msh%dy
     end subroutine record
 
 end program pin_driver

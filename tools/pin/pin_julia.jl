@@ -5,45 +5,45 @@ ref, fin, fout = ARGS
 using UAPIC, FFTW, LinearAlgebra          # UAPIC = the reference package itself (--project=$REF)
 
 io = open(fin)
-nbpart = read(io, Int64); nx, ny, ntau, nstep = read(io, Int32), read(io, Int32), read(io, Int32), read(io, Int32)
+npt = read(io, Int64); nx, ny, nta, nst = read(io, Int32), read(io, Int32), read(io, Int32), read(io, Int32)
 eps, dt, xmax, ymax, w = [read(io, Float64) for _ = 1:5]
-x = Array{Float64}(undef, 2, nbpart); read!(io, x)
-v = Array{Float64}(undef, 2, nbpart); read!(io, v)
+x = Array{Float64}(undef, 2, npt); read!(io, x)
+v = Array{Float64}(undef, 2, npt); read!(io, v)
 close(io)
 
 mesh = Mesh(0.0, xmax, Int(nx), 0.0, ymax, Int(ny))
-fields = MeshFields(mesh)
-particles = Particles(Int(nbpart), w)
-particles.x .= x; particles.v .= v
-poisson! = Poisson(mesh)
-ua = UA(Int(ntau), eps, Int(nbpart))
+fld = MeshFields(mesh)
+pt = Particles(Int(npt), w)
+pt.x .= x; pt.v .= v
+solve! = Poisson(mesh)
+uat = UA(Int(nta), eps, Int(npt))
 energy = Float64[]
-et = zeros(Float64, (ntau, 2, nbpart))
-xt, x̃t, yt, ỹt, fx, fy, gx, gy = [zeros(ComplexF64, (ntau, 2, nbpart)) for _ = 1:8]
-ftau = plan_fft(xt, 1)
+etau = zeros(Float64, (nta, 2, npt))
+xtau, xhat, ytau, yhat, fxh, fyh, gxh, gyh = [zeros(ComplexF64, (nta, 2, npt)) for _ = 1:8]
+planτ = plan_fft(xtau, 1)
 
-compute_rho_m6!(fields, particles)
-push!(energy, poisson!(fields))
-interpol_eb_m6!(particles, fields)
-for istep = 1:nstep
-    preparation!(ua, dt, particles, xt, yt)
-    update_particles_e!(particles, et, fields, ua, xt)
-    compute_f!(fx, fy, ua, particles, xt, yt, et)
-    mul!(x̃t, ftau, xt); ua_step!(xt, x̃t, ua, particles, fx)
-    mul!(ỹt, ftau, yt); ua_step!(yt, ỹt, ua, particles, fy)
-    ifft!(xt, 1); ifft!(yt, 1)
-    update_particles_x!(particles, fields, ua, xt)
-    push!(energy, poisson!(fields))
-    update_particles_e!(particles, et, fields, ua, xt)
-    compute_f!(gx, gy, ua, particles, xt, yt, et)
-    ua_step!(xt, x̃t, ua, particles, fx, gx)
-    ua_step!(yt, ỹt, ua, particles, fy, gy)
-    ifft!(xt, 1)
-    update_particles_x!(particles, fields, ua, xt)
-    push!(energy, poisson!(fields))
-    compute_v!(yt, particles, ua)
+compute_rho_m6!(fld, pt)
+push!(energy, solve!(fld))
+interpol_eb_m6!(pt, fld)
+for it = 1:nst
+    preparation!(uat, dt, pt, xtau, ytau)
+    update_particles_e!(pt, etau, fld, uat, xtau)
+    compute_f!(fxh, fyh, uat, pt, xtau, ytau, etau)
+    mul!(xhat, planτ, xtau); ua_step!(xtau, xhat, uat, pt, fxh)
+    mul!(yhat, planτ, ytau); ua_step!(ytau, yhat, uat, pt, fyh)
+    ifft!(xtau, 1); ifft!(ytau, 1)
+    update_particles_x!(pt, fld, uat, xtau)
+    push!(energy, solve!(fld))
+    update_particles_e!(pt, etau, fld, uat, xtau)
+    compute_f!(gxh, gyh, uat, pt, xtau, ytau, etau)
+    ua_step!(xtau, xhat, uat, pt, fxh, gxh)
+    ua_step!(ytau, yhat, uat, pt, fyh, gyh)
+    ifft!(xtau, 1)
+    update_particles_x!(pt, fld, uat, xtau)
+    push!(energy, solve!(fld))
+    compute_v!(ytau, pt, uat)
 end
 open(fout, "w") do o
-    write(o, Int64(nbpart), Int32(nx), Int32(ny), Int32(ntau), Int32(nstep))
-    write(o, particles.x); write(o, particles.v); write(o, energy); write(o, fields.e)
+    write(o, Int64(npt), Int32(nx), Int32(ny), Int32(nta), Int32(nst))
+    write(o, pt.x); write(o, pt.v); write(o, energy); write(o, fld.e)
 end
