@@ -1,9 +1,13 @@
-# The reference's test files (test/runtests.jl:6-9) against the ccall-backed module.  test_efd.jl is out of scope
-# (external-E variant, no assertions).  Needs a B200 and libuapic_b200.so; Julia is absent from the development image,
-# so these are exercised through their Python twins in tests/test_gpu_stages.py and tests/test_gpu_session.py.
-using Test
-using UAPIC
+# Runs the ccall-backed module through the reference's own test cases (reference test/runtests.jl:6-9 lists them;
+# its external-E case has no assertions and is out of scope).  Needs a B200 and libuapic_b200.so; Julia is absent
+# from the development image, so the same cases are exercised by their Python twins in tests/test_gpu_stages.py
+# and tests/test_gpu_session.py.
+using Test, UAPIC
 
-include("test_poisson.jl")
-include("test_particles.jl")
-include("bupdate.jl")
+const CASES = ("test_poisson", "test_particles", "bupdate")
+
+@testset "UAPIC on libuapic_b200" begin
+    for case in CASES
+        include(joinpath(@__DIR__, case * ".jl"))
+    end
+end
