@@ -15,6 +15,7 @@ import subprocess
 import numpy as np
 
 from . import uapic_oracle_np as nporc  # noqa: F401
+from . import efd_np  # noqa: F401
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "liboracle.so")
@@ -202,6 +203,15 @@ class _COracle:
         self.lib.orc_generate(C.byref(m), C.c_int(kind), C.c_uint64(seed), C.c_int64(first), C.c_int64(stride), C.c_int64(npart),
                               C.c_int64(np_global if np_global is not None else npart), C.c_double(alpha), C.c_double(kx), _p(x), _p(v))
         return x, v
+
+    def efd_run(self, x, v, ntau=16, eps=1e-3, dt=np.pi / 16, tfinal=np.pi / 2, box=(0.0, 4 * np.pi, 0.0, 2 * np.pi)):
+        """fortran/efd.f90 over all particles (the text behind its `stop`); returns (x, v) at tfinal, inputs untouched"""
+        xo, vo = np.array(x, order="F", dtype=np.float64), np.array(v, order="F", dtype=np.float64)
+        b = np.array(box, dtype=np.float64)
+        n = self.lib.orc_efd_run(C.c_int(ntau), C.c_int64(xo.shape[1]), C.c_double(eps), C.c_double(dt), C.c_double(tfinal), _p(b), _p(xo), _p(vo))
+        if n < 0:
+            raise ValueError("ntau must be even, 2..256")
+        return xo, vo
 
     def plasma_from_uniforms(self, m, npart, alpha, kx, u):
         x = np.zeros((2, npart), order="F")

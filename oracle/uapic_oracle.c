@@ -1247,3 +1247,284 @@ void orc3_generate(const orc3_mesh *m, uint64_t seed, int64_t first, int64_t np,
         }
     }
 }
+
+/* ==================================================================================== */
+/* External-field two-scale program      fortran/efd.f90 (test/test_efd.jl is its twin)  */
+/* ==================================================================================== */
+/*
+ * Every particle is integrated on its own in the prescribed field
+ *   E(x,t) = (cos(x1/2) sin(x2) / 2, sin(x1/2) cos(x2)) (1 + sin(t)/2),   b(x) = 1 + sin(x1) sin(x2) / 2
+ * with a third-order prepared initial datum (efd.f90:133-383) and `nstep` second-order IMEX steps in tau-Fourier
+ * space (efd.f90:388-454); the physical state is read off at tau = tfinal b / eps (efd.f90:456-478).  As shipped the
+ * program handles ONE particle and stops after printing intermediate sums (efd.f90:131,257); this is the text behind
+ * that `stop`, run over all particles, which is what produced the constants on efd.f90:481:
+ * with init_particles_2d's load (libgfortran stream, seed of particles.F90:57-64), ntau = 16, eps = 1e-3,
+ * dt = pi/16, tfinal = pi/2 it gives sum(v) = (-857.95049281063, -593.40700170710), the printed reference
+ * values, to 13 digits -- PINNED by tests/test_efd_oracle.py.
+ * Forward transforms carry 1/ntau (fft.f90:44-72).  Quantities the program computes and never uses (pl, ql, gx, ave2:
+ * efd.f90:143-149,275,283) are left out.
+ */
+#include <complex.h>
+typedef double complex zc;
+
+typedef struct {
+    int ntau;
+    orc_fft_plan *plan;
+    double tau[ORC_MAX_NTAU], ltau[ORC_MAX_NTAU], ct[ORC_MAX_NTAU], st[ORC_MAX_NTAU];
+} efd_ctx;
+
+static void efd_fft(const efd_ctx *c, const zc *in, zc *out)        /* fft.f90:61-72 */
+{
+    orc_fft_exec(c->plan, (const cplx *)in, 1, (cplx *)out, 1, -1);
+    for (int n = 0; n < c->ntau; n++) out[n] /= (double)c->ntau;
+}
+static void efd_ifft(const efd_ctx *c, const zc *in, zc *out)       /* fft.f90:74-81 */
+{
+    orc_fft_exec(c->plan, (const cplx *)in, 1, (cplx *)out, 1, +1);
+}
+/* tilde(n) = -i tilde(n) / ltau(n), n >= 2 ; tilde(1) = 0 ; back-transform      (efd.f90:183-188 and its repeats) */
+static void efd_primitive(const efd_ctx *c, const zc *in, zc *out)
+{
+    zc t[ORC_MAX_NTAU];
+    efd_fft(c, in, t);
+    for (int n = 1; n < c->ntau; n++) t[n] = -I * t[n] / c->ltau[n];
+    t[0] = 0.0;
+    efd_ifft(c, t, out);
+}
+static inline double efd_b(double a, double b) { return 1.0 + 0.5 * sin(a) * sin(b); }
+
+/* efd.f90:509-524 */
+static void efd_compute_fy(const efd_ctx *c, double eps, double bx, double time, const zc (*xt)[ORC_MAX_NTAU],
+                           const zc (*yt)[ORC_MAX_NTAU], zc (*fy)[ORC_MAX_NTAU])
+{
+    for (int n = 0; n < c->ntau; n++) {
+        double a = creal(xt[0][n]), b = creal(xt[1][n]);
+        double e1 = (0.5 * cos(a / 2.0) * sin(b)) * (1.0 + 0.5 * sin(time));
+        double e2 = (cos(b) * sin(a / 2.0)) * (1.0 + 0.5 * sin(time));
+        double interv = (efd_b(a, b) - bx) / bx / eps;
+        double t1 = (c->ct[n] * e1 - c->st[n] * e2) / bx;
+        double t2 = (c->ct[n] * e2 + c->st[n] * e1) / bx;
+        fy[0][n] = t1 + interv * yt[1][n];
+        fy[1][n] = t2 - interv * yt[0][n];
+    }
+}
+
+static void efd_one(const efd_ctx *c, double eps, double dt, double tfinal, int nstep, const double *box, double *xp, double *vp)
+{
+    const int nt = c->ntau;
+    const double *ct = c->ct, *st = c->st;
+    zc xt[2][ORC_MAX_NTAU], yt[2][ORC_MAX_NTAU], h[2][ORC_MAX_NTAU], r[2][ORC_MAX_NTAU], fx[2][ORC_MAX_NTAU], fy[2][ORC_MAX_NTAU];
+    zc temp[2][ORC_MAX_NTAU], tilde[2][ORC_MAX_NTAU], xf[2][ORC_MAX_NTAU], yf[2][ORC_MAX_NTAU], gx[2][ORC_MAX_NTAU], gy[2][ORC_MAX_NTAU];
+    const double x1 = xp[0], x2 = xp[1], v1 = vp[0], v2 = vp[1];
+    double time = 0.0;
+    const double bx = efd_b(x1, x2);                                    /* efd.f90:138-140 */
+    const double ds = dt * bx;
+    double ave[2], e1, e2, interv;
+
+    /* first-order datum (efd.f90:157-195) */
+    for (int n = 0; n < nt; n++) {
+        h[0][n] = eps * (st[n] * (v1 / bx) - ct[n] * (v2 / bx));
+        h[1][n] = eps * (st[n] * (v2 / bx) + ct[n] * (v1 / bx));
+    }
+    for (int n = 0; n < nt; n++) { xt[0][n] = x1 + h[0][n] - h[0][0]; xt[1][n] = x2 + h[1][n] - h[1][0]; }
+    e1 = (0.5 * cos(x1 / 2.0) * sin(x2)) * (1.0 + 0.5 * sin(time));
+    e2 = (sin(x1 / 2.0) * cos(x2)) * (1.0 + 0.5 * sin(time));
+    for (int n = 0; n < nt; n++) {
+        interv = (efd_b(creal(xt[0][n]), creal(xt[1][n])) - bx) / bx;
+        r[0][n] = interv * v2;
+        r[1][n] = -interv * v1;
+    }
+    efd_fft(c, r[0], tilde[0]); efd_fft(c, r[1], tilde[1]);
+    ave[0] = creal(tilde[0][0]) / eps; ave[1] = creal(tilde[1][0]) / eps;
+    for (int d = 0; d < 2; d++) {
+        for (int n = 1; n < nt; n++) tilde[d][n] = -I * tilde[d][n] / c->ltau[n];
+        tilde[d][0] = 0.0;
+        efd_ifft(c, tilde[d], r[d]);
+    }
+    for (int n = 0; n < nt; n++) {
+        r[0][n] = eps * (st[n] * e1 + ct[n] * e2) / bx + r[0][n];
+        r[1][n] = eps * (st[n] * e2 - ct[n] * e1) / bx + r[1][n];
+    }
+    for (int n = 0; n < nt; n++) { yt[0][n] = v1 + (r[0][n] - r[0][0]); yt[1][n] = v2 + (r[1][n] - r[1][0]); }
+
+    /* second-order position (efd.f90:200-222) */
+    for (int n = 0; n < nt; n++) {
+        temp[0][n] = eps * (ct[n] * yt[0][n] + st[n] * yt[1][n]) / bx;
+        temp[1][n] = eps * (ct[n] * yt[1][n] - st[n] * yt[0][n]) / bx;
+    }
+    efd_primitive(c, temp[0], h[0]); efd_primitive(c, temp[1], h[1]);
+    for (int n = 0; n < nt; n++) {
+        h[0][n] = h[0][n] - eps * eps / bx * (-ct[n] * ave[0] - st[n] * ave[1]);
+        h[1][n] = h[1][n] - eps * eps / bx * (-ct[n] * ave[1] + st[n] * ave[0]);
+    }
+    for (int n = 0; n < nt; n++) { xt[0][n] = x1 + h[0][n] - h[0][0]; xt[1][n] = x2 + h[1][n] - h[1][0]; }
+
+    /* second-order velocity (efd.f90:226-310): the time derivative of E enters here */
+    e1 = (0.5 * cos(x1 / 2.0) * sin(x2)) * 0.5 * cos(time);
+    e2 = (sin(x1 / 2.0) * cos(x2)) * 0.5 * cos(time);
+    for (int n = 0; n < nt; n++) {
+        interv = (efd_b(creal(xt[0][n]), creal(xt[1][n])) - bx) / bx;
+        fx[0][n] = interv * ave[1];
+        fx[1][n] = -interv * ave[0];
+        fy[0][n] = eps / bx * (st[n] * ave[0] - ct[n] * ave[1]);
+        fy[1][n] = eps / bx * (ct[n] * ave[0] + st[n] * ave[1]);
+        double w = creal(cos(x1) * sin(x2) * fy[0][n] + sin(x1) * cos(x2) * fy[1][n]);  /* `interv` is real(8) */
+        fy[0][n] = w / bx / 2.0 * v2 + fx[0][n];
+        fy[1][n] = -w / bx / 2.0 * v1 + fx[1][n];
+        fx[0][n] = eps / (bx * bx) * (-st[n] * e2 + ct[n] * e1);
+        fx[1][n] = eps / (bx * bx) * (st[n] * e1 + ct[n] * e2);
+    }
+    for (int d = 0; d < 2; d++) {
+        for (int n = 0; n < nt; n++) temp[d][n] = fy[d][n] + fx[d][n];
+        efd_fft(c, temp[d], tilde[d]);
+        for (int n = 1; n < nt; n++) {
+            fx[d][n] = -I * tilde[d][n] / c->ltau[n];
+            tilde[d][n] = -tilde[d][n] / (c->ltau[n] * c->ltau[n]);
+        }
+        fx[d][0] = 0.0; tilde[d][0] = 0.0;
+        efd_ifft(c, tilde[d], temp[d]);
+        for (int n = 0; n < nt; n++) r[d][n] = -eps * temp[d][n];
+        efd_ifft(c, fx[d], fy[d]);
+    }
+    for (int n = 0; n < nt; n++) {
+        double a = creal(xt[0][n]), b = creal(xt[1][n]);
+        e1 = (0.5 * cos(a / 2.0) * sin(b)) * (1.0 + 0.5 * sin(time));
+        e2 = (sin(a / 2.0) * cos(b)) * (1.0 + 0.5 * sin(time));
+        interv = (efd_b(a, b) - bx) / bx;
+        temp[0][n] = interv * yt[1][n] + eps / bx * (-st[n] * e2 + ct[n] * e1);
+        temp[1][n] = -interv * yt[0][n] + eps / bx * (st[n] * e1 + ct[n] * e2);
+    }
+    zc ydot[2];
+    for (int d = 0; d < 2; d++) {
+        efd_fft(c, temp[d], tilde[d]);
+        ydot[d] = tilde[d][0] / eps;                                     /* xf(1,:), efd.f90:299 */
+        for (int n = 1; n < nt; n++) tilde[d][n] = -I * tilde[d][n] / c->ltau[n];
+        tilde[d][0] = 0.0;
+        efd_ifft(c, tilde[d], temp[d]);
+        for (int n = 0; n < nt; n++) r[d][n] = r[d][n] + temp[d][n];
+    }
+    for (int n = 0; n < nt; n++) { yt[0][n] = v1 + r[0][n] - r[0][0]; yt[1][n] = v2 + r[1][n] - r[1][0]; }
+
+    /* third-order position (efd.f90:315-383) */
+    for (int n = 0; n < nt; n++) {
+        temp[0][n] = (ct[n] * r[0][n] + st[n] * r[1][n]) / bx;
+        temp[1][n] = (ct[n] * r[1][n] - st[n] * r[0][n]) / bx;
+    }
+    efd_fft(c, temp[0], tilde[0]); efd_fft(c, temp[1], tilde[1]);
+    double w0 = creal(cos(x1) * sin(x2) * tilde[0][0] + sin(x1) * cos(x2) * tilde[1][0]);   /* real(8) `interv` again */
+    zc acc[2];
+    acc[0] = w0 / eps / bx * v2 / 2.0;
+    acc[1] = -w0 / eps / bx * v1 / 2.0;
+    for (int n = 0; n < nt; n++) temp[0][n] = (efd_b(creal(xt[0][n]), creal(xt[1][n])) - bx) / bx;
+    efd_fft(c, temp[0], tilde[0]);
+    acc[0] = acc[0] + tilde[0][0] / eps * ave[1];
+    acc[1] = acc[1] - tilde[0][0] / eps * ave[0];
+    for (int n = 0; n < nt; n++) {
+        yf[0][n] = ydot[0] + fy[0][n];
+        yf[1][n] = ydot[1] + fy[1][n];
+        temp[0][n] = ct[n] * yf[0][n] + st[n] * yf[1][n];
+        temp[1][n] = ct[n] * yf[1][n] - st[n] * yf[0][n];
+    }
+    efd_primitive(c, temp[0], temp[0]); efd_primitive(c, temp[1], temp[1]);
+    for (int n = 0; n < nt; n++) {
+        fy[0][n] = temp[0][n] * eps / bx - eps * eps / bx * (-ct[n] * acc[0] - st[n] * acc[1]);
+        fy[1][n] = temp[1][n] * eps / bx - eps * eps / bx * (-ct[n] * acc[1] + st[n] * acc[0]);
+    }
+    efd_primitive(c, fy[0], temp[0]); efd_primitive(c, fy[1], temp[1]);
+    for (int d = 0; d < 2; d++) for (int n = 0; n < nt; n++) h[d][n] = -eps * temp[d][n];
+    for (int n = 0; n < nt; n++) {
+        temp[0][n] = eps * (ct[n] * yt[0][n] + st[n] * yt[1][n]) / bx;
+        temp[1][n] = eps * (ct[n] * yt[1][n] - st[n] * yt[0][n]) / bx;
+    }
+    efd_primitive(c, temp[0], temp[0]); efd_primitive(c, temp[1], temp[1]);
+    for (int d = 0; d < 2; d++) for (int n = 0; n < nt; n++) h[d][n] = h[d][n] + temp[d][n];
+    for (int n = 0; n < nt; n++) { xt[0][n] = x1 + h[0][n] - h[0][0]; xt[1][n] = x2 + h[1][n] - h[1][0]; }
+
+    /* IMEX2 steps (efd.f90:388-454) */
+    for (int istep = 0; istep < nstep; istep++) {
+        efd_compute_fy(c, eps, bx, time, xt, yt, fy);
+        for (int d = 0; d < 2; d++) {
+            for (int n = 0; n < nt; n++) gy[d][n] = yt[d][n] + ds / 2.0 * fy[d][n];
+            efd_fft(c, gy[d], fy[d]);
+            for (int n = 0; n < nt; n++) fy[d][n] = fy[d][n] / (1.0 + I * ds / 2.0 * c->ltau[n] / eps);
+            efd_ifft(c, fy[d], yf[d]);
+        }
+        for (int n = 0; n < nt; n++) {
+            fx[0][n] = (ct[n] * yf[0][n] + st[n] * yf[1][n]) / bx;
+            fx[1][n] = (ct[n] * yf[1][n] - st[n] * yf[0][n]) / bx;
+        }
+        for (int d = 0; d < 2; d++) {
+            for (int n = 0; n < nt; n++) gx[d][n] = xt[d][n] + ds / 2.0 * fx[d][n];
+            efd_fft(c, gx[d], fx[d]);
+            for (int n = 0; n < nt; n++) fx[d][n] = fx[d][n] / (1.0 + I * ds / 2.0 * c->ltau[n] / eps);
+            efd_ifft(c, fx[d], xf[d]);
+        }
+        time = time + dt / 2.0;
+        efd_compute_fy(c, eps, bx, time, xf, yf, fy);
+        for (int d = 0; d < 2; d++) {
+            efd_fft(c, fy[d], gy[d]);
+            efd_fft(c, yt[d], yf[d]);
+            for (int n = 0; n < nt; n++)
+                fy[d][n] = (yf[d][n] * (1.0 - I * ds / eps / 2.0 * c->ltau[n]) + ds * gy[d][n]) / (1.0 + I * ds / 2.0 * c->ltau[n] / eps);
+            for (int n = 0; n < nt; n++) yf[d][n] = yt[d][n];
+            efd_ifft(c, fy[d], yt[d]);
+            for (int n = 0; n < nt; n++) yf[d][n] = (yt[d][n] + yf[d][n]) / 2.0;
+        }
+        for (int n = 0; n < nt; n++) {
+            fx[0][n] = (ct[n] * yf[0][n] + st[n] * yf[1][n]) / bx;
+            fx[1][n] = (ct[n] * yf[1][n] - st[n] * yf[0][n]) / bx;
+        }
+        for (int d = 0; d < 2; d++) {
+            efd_fft(c, fx[d], gx[d]);
+            efd_fft(c, xt[d], xf[d]);
+            for (int n = 0; n < nt; n++)
+                fx[d][n] = (xf[d][n] * (1.0 - I * ds / eps / 2.0 * c->ltau[n]) + ds * gx[d][n]) / (1.0 + I * ds / 2.0 * c->ltau[n] / eps);
+            efd_ifft(c, fx[d], xt[d]);
+        }
+        time = time + dt / 2.0;
+    }
+
+    /* physical state at tau = tfinal b / eps (efd.f90:456-478), positions wrapped as apply_bc (efd.f90:526-544) */
+    zc s[2];
+    for (int d = 0; d < 2; d++) {
+        efd_fft(c, xt[d], tilde[d]);
+        s[d] = 0.0;
+        for (int n = 0; n < nt; n++) s[d] = s[d] + tilde[d][n] * cexp(I * c->ltau[n] * tfinal * bx / eps);
+    }
+    double xx = creal(s[0]), yy = creal(s[1]);
+    const double dimx = box[1] - box[0], dimy = box[3] - box[2];
+    while (xx > box[1]) xx -= dimx;
+    while (xx < box[0]) xx += dimx;
+    while (yy > box[3]) yy -= dimy;
+    while (yy < box[2]) yy += dimy;
+    xp[0] = xx; xp[1] = yy;
+    for (int d = 0; d < 2; d++) {
+        efd_fft(c, yt[d], tilde[d]);
+        s[d] = 0.0;
+        for (int n = 0; n < nt; n++) s[d] = s[d] + tilde[d][n] * cexp(I * c->ltau[n] * tfinal * bx / eps);
+    }
+    vp[0] = creal(cos(tfinal * bx / eps) * s[0] + sin(tfinal * bx / eps) * s[1]);
+    vp[1] = creal(cos(tfinal * bx / eps) * s[1] - sin(tfinal * bx / eps) * s[0]);
+}
+
+/* x, v: (2, np), overwritten with the state at tfinal.  box = xmin, xmax, ymin, ymax.  nstep = nint(tfinal/dt) (efd.f90:102) */
+int orc_efd_run(int ntau, int64_t np, double eps, double dt, double tfinal, const double *box, double *x, double *v)
+{
+    if (ntau < 2 || ntau > ORC_MAX_NTAU || (ntau & 1)) return -1;
+    efd_ctx c;
+    c.ntau = ntau;
+    c.plan = orc_fft_new(ntau);
+    const double pi = 4.0 * atan(1.0);
+    const double dtau = 2.0 * pi / ntau;                                /* efd.f90:107,111-116 */
+    for (int n = 0; n < ntau; n++) {
+        c.tau[n] = n * dtau;
+        c.ltau[n] = (n < ntau / 2) ? (double)n : (double)(n - ntau);
+        c.ct[n] = cos(c.tau[n]);
+        c.st[n] = sin(c.tau[n]);
+    }
+    const int nstep = (int)lround(tfinal / dt);
+#pragma omp parallel for schedule(static) num_threads(g_threads)
+    for (int64_t m = 0; m < np; m++) efd_one(&c, eps, dt, tfinal, nstep, box, x + 2 * m, v + 2 * m);
+    orc_fft_free(c.plan);
+    return nstep;
+}

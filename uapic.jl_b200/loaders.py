@@ -48,11 +48,21 @@ def write_particles(filename: str, mesh: Mesh, x: np.ndarray, v: np.ndarray) -> 
             f.write(f"{ix[k]:d} {iy[k]:d} {px[k] - ix[k]:.17g} {py[k] - iy[k]:.17g} {v[0, k]:.17g} {v[1, k]:.17g}\n")
 
 
+class _GfDesc(C.Structure):
+    """gfortran array descriptor of a rank-1 array (GCC >= 8 layout)"""
+    _fields_ = [("base", C.c_void_p), ("offset", C.c_size_t), ("elem_len", C.c_size_t), ("version", C.c_int),
+                ("rank", C.c_int8), ("type", C.c_int8), ("attr", C.c_int16), ("span", C.c_ssize_t),
+                ("stride", C.c_ssize_t), ("lbound", C.c_ssize_t), ("ubound", C.c_ssize_t)]
+
+
 class _Uniforms:
-    """stream of U[0,1) deviates: gfortran's random_number with the reference seed, or a numpy generator"""
+    """stream of U[0,1) deviates: gfortran's random_number with the reference seed, or a numpy generator.
+    `take(n)` hands out the next n deviates, `give_back(k)` returns the last k unused ones to the stream, so a
+    vectorised rejection loop consumes exactly the deviates the one-trial-at-a-time Fortran loop does."""
 
     def __init__(self, seed=None, use_gfortran=False):
         self.gf = None
+        self._buf, self._pos = np.empty(0), 0
         if use_gfortran:
             import scipy
             cands = glob.glob(os.path.join(os.path.dirname(scipy.__file__), "..", "scipy.libs", "libgfortran*.so*"))
@@ -60,17 +70,12 @@ class _Uniforms:
                 try:
                     lib = C.CDLL(c)
                     arr = (C.c_int32 * 33)(*FORTRAN_SEED)
-                    # _gfortran_random_seed_i4(size, put, get) with gfortran array descriptors is awkward from C;
-                    # the descriptor for a rank-1 int32 array (GCC >= 8 layout):
-                    class Desc(C.Structure):
-                        _fields_ = [("base", C.c_void_p), ("offset", C.c_size_t), ("elem_len", C.c_size_t), ("version", C.c_int),
-                                    ("rank", C.c_int8), ("type", C.c_int8), ("attr", C.c_int16), ("span", C.c_ssize_t),
-                                    ("stride", C.c_ssize_t), ("lbound", C.c_ssize_t), ("ubound", C.c_ssize_t)]
-                    d = Desc(C.addressof(arr), C.c_size_t(-1 & (2 ** 64 - 1)), 4, 0, 1, 1, 0, 4, 1, 1, 33)
+                    # random_seed(put = seed): _gfortran_random_seed_i4(size, put, get), put a rank-1 int32 array (type 1)
+                    d = _GfDesc(C.addressof(arr), C.c_size_t(-1 & (2 ** 64 - 1)), 4, 0, 1, 1, 0, 4, 1, 1, 33)
                     lib._gfortran_random_seed_i4(None, C.byref(d), None)
-                    lib._gfortran_random_r8.argtypes = [C.POINTER(C.c_double)]
+                    lib._gfortran_arandom_r8.argtypes = [C.POINTER(_GfDesc)]
+                    lib._gfortran_arandom_r8.restype = None
                     self.gf = lib
-                    self._keep = (arr, d)
                     break
                 except (OSError, AttributeError):
                     continue
@@ -80,69 +85,66 @@ class _Uniforms:
     def source(self):
         return "libgfortran random_number, seed of particles.F90:57-64" if self.gf else "numpy PCG64"
 
-    def draw(self, n):
+    def _fresh(self, n):
         if self.gf is None:
             return self.rng.random(n)
         out = np.empty(n)
-        tmp = C.c_double()
-        f = self.gf._gfortran_random_r8
-        for i in range(n):
-            f(C.byref(tmp))
-            out[i] = tmp.value
+        # random_number on a real(8) rank-1 array (type 3) draws the same sequence as n scalar calls
+        d = _GfDesc(out.ctypes.data, C.c_size_t(-1 & (2 ** 64 - 1)), 8, 0, 1, 3, 0, 8, 1, 1, n)
+        self.gf._gfortran_arandom_r8(C.byref(d))
         return out
+
+    def take(self, n):
+        left = self._buf.size - self._pos
+        if left < n:
+            self._buf = np.concatenate([self._buf[self._pos:], self._fresh(max(n - left, 1 << 20))])
+            self._pos = 0
+        out = self._buf[self._pos:self._pos + n]
+        self._pos += n
+        return out
+
+    def give_back(self, k):
+        self._pos -= k
+
+    def draw(self, n):
+        return self.take(n).copy()
 
 
 def plasma(mesh: Mesh, nbpart: int, seed=None, alpha=0.05, kx=0.5, use_gfortran=False, return_source=False):
     """src/plasma.jl:3-52 / fortran/particles.F90:68-103: x from 1+sin(y)+alpha*cos(kx*x) (bound 2+alpha),
-    v from the two-bump Maxwellian on [-5,5]^2.  Draw order identical to the reference (xi, yi, zi per trial)."""
+    v from the two-bump Maxwellian on [-5,5]^2.  Three deviates per trial (xi, yi, zi), consumed strictly in the
+    reference's order: the position loop stops at its nbpart-th accepted trial and the velocity loop starts at the
+    very next deviate.  With `use_gfortran` the stream is libgfortran's under the seed of particles.F90:57-64, and
+    the load is the one the reference's Fortran programs run on: the Fortran external-field program's printed
+    sum(v) after its run (efd.f90:481) is reproduced from it to 13 digits (tests/test_efd_oracle.py)."""
     dimx, dimy = mesh.xmax - mesh.xmin, mesh.ymax - mesh.ymin
     p = Particles(nbpart, (dimx * dimy) / nbpart)
     u = _Uniforms(seed, use_gfortran)
 
-    def fill(accept_fn, target):
+    def fill(trial, rate, target):
         k = 0
         while k < nbpart:
-            n = max(1024, int((nbpart - k) * 1.2 / accept_fn.rate))
-            d = u.draw(3 * n).reshape(n, 3)
-            a, b, ok = accept_fn(d)
-            take = min(int(ok.sum()), nbpart - k)
-            idx = np.flatnonzero(ok)[:take]
-            target[0, k:k + take], target[1, k:k + take] = a[idx], b[idx]
-            k += take
-            # the reference consumes deviates strictly in order; discarding the tail of the last batch only matters
-            # for bit-reproduction of the gfortran stream, which draws one trial at a time below
-        return
+            n = max(1024, int((nbpart - k) * 1.1 / rate))
+            d = u.take(3 * n).reshape(n, 3)
+            a, b, ok = trial(d)
+            idx = np.flatnonzero(ok)
+            if idx.size > nbpart - k:           # the loop ends at this trial: the later ones were never drawn
+                idx = idx[:nbpart - k]
+                u.give_back(3 * (n - 1 - int(idx[-1])))
+            target[0, k:k + idx.size], target[1, k:k + idx.size] = a[idx], b[idx]
+            k += idx.size
 
-    if u.gf is not None:
-        # strict one-trial-at-a-time order, as init_particles_2d
-        k = 0
-        while k < nbpart:
-            d = u.draw(3)
-            xi, yi, zi = d[0] * dimx, d[1] * dimy, (2.0 + alpha) * d[2]
-            if 1.0 + np.sin(yi) + alpha * np.cos(kx * xi) >= zi:
-                p.x[0, k], p.x[1, k] = xi, yi
-                k += 1
-        k = 0
-        while k < nbpart:
-            d = u.draw(3)
-            xi, yi, zi = (d[0] - 0.5) * 10.0, (d[1] - 0.5) * 10.0, d[2]
-            temm = (np.exp(-((xi - 2.0) ** 2 + yi ** 2) / 2.0) + np.exp(-((xi + 2.0) ** 2 + yi ** 2) / 2.0)) / 2.0
-            if temm >= zi:
-                p.v[0, k], p.v[1, k] = xi, yi
-                k += 1
-    else:
-        def acc_x(d):
-            xi, yi, zi = d[:, 0] * dimx, d[:, 1] * dimy, (2.0 + alpha) * d[:, 2]
-            return xi, yi, (1.0 + np.sin(yi) + alpha * np.cos(kx * xi)) >= zi
-        acc_x.rate = 1.0 / (2.0 + alpha)
+    def trial_x(d):                              # particles.F90:68-83
+        xi, yi, zi = d[:, 0] * dimx, d[:, 1] * dimy, (2.0 + alpha) * d[:, 2]
+        return xi, yi, (1.0 + np.sin(yi) + alpha * np.cos(kx * xi)) >= zi
 
-        def acc_v(d):
-            xi, yi, zi = (d[:, 0] - 0.5) * 10.0, (d[:, 1] - 0.5) * 10.0, d[:, 2]
-            temm = (np.exp(-((xi - 2.0) ** 2 + yi ** 2) / 2.0) + np.exp(-((xi + 2.0) ** 2 + yi ** 2) / 2.0)) / 2.0
-            return xi, yi, temm >= zi
-        acc_v.rate = 2 * np.pi / 100.0
-        fill(acc_x, p.x)
-        fill(acc_v, p.v)
+    def trial_v(d):                              # particles.F90:85-103
+        xi, yi, zi = (d[:, 0] - 0.5) * 10.0, (d[:, 1] - 0.5) * 10.0, d[:, 2]
+        temm = (np.exp(-((xi - 2.0) ** 2 + yi ** 2) / 2.0) + np.exp(-((xi + 2.0) ** 2 + yi ** 2) / 2.0)) / 2.0
+        return xi, yi, temm >= zi
+
+    fill(trial_x, 1.0 / (2.0 + alpha), p.x)
+    fill(trial_v, 2 * np.pi / 100.0, p.v)
     if return_source:
         return p, u.source
     return p
