@@ -310,6 +310,29 @@ int uapic3d_compute_rho_cic(const uapic3d_mesh_t *mesh, int64_t nbpart, const do
 int uapic3d_poisson(const uapic3d_mesh_t *mesh, const double *rho, double *e);
 int uapic3d_interpolate_eb_cic(const uapic3d_mesh_t *mesh, const double *e, int64_t nbpart, const double *x, double *e_particles);
 
+/* ------------------------------------------------------------------------------------------
+ * Sibling scheme: the external-field two-scale program of fortran/efd.f90 (test/test_efd.jl is its Julia twin).  Every
+ * particle is integrated on its own in the prescribed field of efd.f90:166-167 with b(x) of efd.f90:139: third-order prepared
+ * datum (efd.f90:157-383), nstep IMEX2 steps in tau-Fourier space (:388-454), state read off at tau = tfinal b/eps and
+ * wrapped into the box (:456-478, :526-544).  This is the text behind the program's `stop` (efd.f90:257) over ALL particles --
+ * the run whose sum(v) the program prints against on efd.f90:481.  One kernel launch; x, v, x_out, v_out are (2,nbpart),
+ * column-major; the outputs may alias the inputs.  ntau: any even value 2..256.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct uapic_efd_config {
+    int32_t ntau;                    /* efd.f90:18 (16) */
+    int32_t nstep;                   /* 0 = nint(tfinal/dt), efd.f90:102 */
+    double  eps;                     /* efd.f90:106 (1e-3) */
+    double  dt;                      /* efd.f90:100 (pi/16) */
+    double  tfinal;                  /* efd.f90:101 (pi/2) */
+    double  xmin, xmax, ymin, ymax;  /* efd.f90:117-118 */
+} uapic_efd_config_t;
+
+/* host buffers, synchronous */
+int uapic_efd_run(const uapic_efd_config_t *cfg, int64_t nbpart, const double *x, const double *v, double *x_out, double *v_out);
+/* device buffers on the current device, asynchronous on `stream` (cudaStream_t, may be null) */
+int uapic_efd_run_device(const uapic_efd_config_t *cfg, int64_t nbpart, const double *x, const double *v, double *x_out,
+                         double *v_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

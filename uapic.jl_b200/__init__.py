@@ -14,3 +14,5 @@ from .session import Session, run_bupdate  # noqa: F401
 from . import dist  # noqa: F401
 from . import mrc3d  # noqa: F401
 from .mrc3d import Fields3D, Mesh3D, Session3D, run_uapic3d  # noqa: F401
+from . import external_field  # noqa: F401
+from .external_field import efd, efd_run, efd_run_device  # noqa: F401

@@ -438,6 +438,41 @@ int uapic_compute_v(int ntau, double eps, int64_t nbpart, const double *t, const
     return UAPIC_OK;
 }
 
+static int efd_check(const uapic_efd_config_t *cfg, int64_t nbpart, const double *x, const double *v, double *xo, double *vo, int *nstep) {
+    if (!cfg || nbpart < 0 || (nbpart > 0 && (!x || !v || !xo || !vo))) return fail(UAPIC_EINVAL, "uapic_efd_run: bad argument");
+    if (!efd_ntau_supported(cfg->ntau)) return fail(UAPIC_EINVAL, "ntau must be even, 2..%d (got %d)", kGenericMaxNtau, cfg->ntau);
+    if (!(cfg->eps > 0) || !(cfg->dt > 0) || !(cfg->tfinal >= 0) || !(cfg->xmax > cfg->xmin) || !(cfg->ymax > cfg->ymin) || cfg->nstep < 0)
+        return fail(UAPIC_EINVAL, "uapic_efd_run: eps, dt must be positive, tfinal and nstep non-negative, the box non-empty");
+    *nstep = cfg->nstep > 0 ? cfg->nstep : (int)std::lround(cfg->tfinal / cfg->dt);          // efd.f90:102
+    return UAPIC_OK;
+}
+
+int uapic_efd_run_device(const uapic_efd_config_t *cfg, int64_t nbpart, const double *x, const double *v, double *x_out,
+                         double *v_out, void *stream) {
+    int nstep = 0;
+    TRY(efd_check(cfg, nbpart, x, v, x_out, v_out, &nstep));
+    STAGE_BEGIN();
+    sc.lc.stream = reinterpret_cast<cudaStream_t>(stream);
+    const double box[4] = {cfg->xmin, cfg->xmax, cfg->ymin, cfg->ymax};
+    CU(launch_efd(sc.lc, cfg->ntau, cfg->eps, cfg->dt, cfg->tfinal, nstep, box, nbpart, x, v, x_out, v_out));
+    return UAPIC_OK;
+}
+
+int uapic_efd_run(const uapic_efd_config_t *cfg, int64_t nbpart, const double *x, const double *v, double *x_out, double *v_out) {
+    int nstep = 0;
+    TRY(efd_check(cfg, nbpart, x, v, x_out, v_out, &nstep));
+    STAGE_BEGIN();
+    const size_t bytes = 16 * (size_t)nbpart;
+    DevBuf dx, dv;
+    TRY(up(dx, x, bytes)); TRY(up(dv, v, bytes));
+    const double box[4] = {cfg->xmin, cfg->xmax, cfg->ymin, cfg->ymax};
+    CU(launch_efd(sc.lc, cfg->ntau, cfg->eps, cfg->dt, cfg->tfinal, nstep, box, nbpart, dx.as<double>(), dv.as<double>(),
+                  dx.as<double>(), dv.as<double>()));
+    CU(cudaDeviceSynchronize());
+    TRY(down(x_out, dx, bytes)); TRY(down(v_out, dv, bytes));
+    return UAPIC_OK;
+}
+
 }  // extern "C"
 
 // ================================================================================================

@@ -160,6 +160,12 @@ cudaError_t launch_sort_particles(const LaunchCtx &c, const MeshDev &m, int bin_
                                   double2 *ep2, uint32_t *perm2, uint16_t *binid, unsigned *hist, uint32_t index_base = 0);
 cudaError_t launch_unpermute(const LaunchCtx &c, int64_t np, const uint32_t *perm, const double2 *a, double2 *out);
 
+// ---- the external-field program of fortran/efd.f90 as one kernel (uapic_efd.cu) -------------------------------------
+// box = xmin, xmax, ymin, ymax; x, v, x_out, v_out: (2, np) device arrays (x_out / v_out may alias x / v)
+bool efd_ntau_supported(int ntau);
+cudaError_t launch_efd(const LaunchCtx &c, int ntau, double eps, double dt, double tfinal, int nstep, const double *box, int64_t np,
+                       const double *x, const double *v, double *x_out, double *v_out);
+
 // ---- loaders / diagnostics --------------------------------------------------------------------------------------
 cudaError_t launch_generate(const LaunchCtx &c, const MeshDev &m, int kind, uint64_t seed, int64_t first, int64_t stride, int64_t np,
                             int64_t np_global, double alpha, double kx, double *x, double *v);
