@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -63,11 +64,26 @@ int device_info(int device, DeviceInfo *out) {
                     e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
     }
     if (device < 0 || device >= n) return fail(UAPIC_EINVAL, "device %d out of range (0..%d)", device, n - 1);
-    cudaDeviceProp prop;
-    CU(cudaGetDeviceProperties(&prop, device));
-    if (prop.major != 10)
-        return fail(UAPIC_ENODEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
-    out->ok = 1; out->sm_count = prop.multiProcessorCount; out->major = prop.major; out->minor = prop.minor;
+    // three attribute queries, remembered per device: cudaGetDeviceProperties fills ~100 fields on every call and every
+    // stage-API entry point comes through here
+    constexpr int kCached = 64;
+    static std::mutex mu;
+    static DeviceInfo cache[kCached] = {};
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (device < kCached && cache[device].ok) { *out = cache[device]; return UAPIC_OK; }
+    }
+    int major = 0, minor = 0, sms = 0;
+    CU(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    CU(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device));
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    if (major != 10)
+        return fail(UAPIC_ENODEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device, major, minor);
+    out->ok = 1; out->sm_count = sms; out->major = major; out->minor = minor;
+    if (device < kCached) {
+        std::lock_guard<std::mutex> lock(mu);
+        cache[device] = *out;
+    }
     return UAPIC_OK;
 }
 

@@ -39,6 +39,7 @@ struct EfdArgs {
 template <int N> struct LaneTau {
     static constexpr int SPL = 1;
     static constexpr int kLanesPerParticle = N;
+    static constexpr int kMinBlocks = 4;          // 128 registers: 16 warps per SM hide the shuffle and DFMA latencies of the butterflies
     TauLane<N> L;
     DEVINL void init(int, cd *) { L.init(threadIdx.x & 31); }
     DEVINL bool leader() const { return L.j == 0; }
@@ -56,6 +57,7 @@ template <int N> struct LaneTau {
 template <int R> struct WarpTau {
     static constexpr int SPL = R;
     static constexpr int kLanesPerParticle = 32;
+    static constexpr int kMinBlocks = 1;
     int N, lane;
     cd *buf;
     const cd *tw;
@@ -112,7 +114,7 @@ template <int R> struct WarpTau {
 };
 
 
-template <class P> __global__ void __launch_bounds__(kEfdBlock) k_efd(const EfdArgs q) {
+template <class P> __global__ void __launch_bounds__(kEfdBlock, P::kMinBlocks) k_efd(const EfdArgs q) {
     extern __shared__ double2 efd_smem[];
     P T;
     T.init(q.ntau, reinterpret_cast<cd *>(efd_smem));

@@ -34,9 +34,8 @@ DEVINL cd operator/(cd b, double a) { return mk(b.re / a, b.im / a); }
 DEVINL cd operator-(cd b) { return mk(-b.re, -b.im); }
 DEVINL cd operator*(cd a, cd b) { return cmul(a, b); }
 DEVINL cd mul_mi(cd a) { return mk(a.im, -a.re); }                       // -i a
-DEVINL cd over_1pia(cd z, double a) {                                    // z / (1 + i a)
-    const double d = 1.0 + a * a;
-    return mk((z.re + z.im * a) / d, (z.im - z.re * a) / d);
+DEVINL cd over_1pia(cd z, double a, double rd) {                         // z / (1 + i a), rd = 1 / (1 + a^2)
+    return mk((z.re + z.im * a) * rd, (z.im - z.re * a) * rd);
 }
 DEVINL double bfun(double a, double b) { return 1.0 + 0.5 * sin(a) * sin(b); }    // efd.f90:139
 
@@ -59,8 +58,10 @@ template <class P, int S> DEVINL void rebase(const P &T, cd (&out)[S], double ba
     EACH out[j] = base + a[j] - a0;
 }
 // compute_fy                                                                      efd.f90:509-524
+// (ibx = 1/b, ibe = 1/b/eps: the loop-invariant divisions of the reference are hoisted into reciprocals, and sin(a) comes from the
+//  half-angle pair the field needs anyway -- each a <= 1 ulp change, far inside the conditioning of the map, see tests/test_gpu_efd.py)
 template <class P, int S>
-DEVINL void force(const P &T, double eps, double bx, double time, const cd (&X1)[S], const cd (&X2)[S], const cd (&Y1)[S],
+DEVINL void force(const P &T, double ibx, double ibe, double bx, double time, const cd (&X1)[S], const cd (&X2)[S], const cd (&Y1)[S],
                   const cd (&Y2)[S], cd (&f1)[S], cd (&f2)[S]) {
     const double amp = 1.0 + 0.5 * sin(time);
     EACH {
@@ -70,9 +71,9 @@ DEVINL void force(const P &T, double eps, double bx, double time, const cd (&X1)
         sincos(b, &sb, &cb);
         const double e1 = (0.5 * ch * sb) * amp;
         const double e2 = (cb * sh) * amp;
-        const double interv = (1.0 + 0.5 * sin(a) * sb - bx) / bx / eps;
-        const double t1 = (T.ct(j) * e1 - T.st(j) * e2) / bx;
-        const double t2 = (T.ct(j) * e2 + T.st(j) * e1) / bx;
+        const double interv = (1.0 + 0.5 * (2.0 * sh * ch) * sb - bx) * ibe;
+        const double t1 = (T.ct(j) * e1 - T.st(j) * e2) * ibx;
+        const double t2 = (T.ct(j) * e2 + T.st(j) * e1) * ibx;
         f1[j] = t1 + interv * Y2[j];
         f2[j] = t2 - interv * Y1[j];
     }
@@ -198,46 +199,50 @@ DEVINL void efd_particle(const P &T, const EfdScalars &q, double x1, double x2, 
     rebase<P, S>(T, xt1, x1, t1); rebase<P, S>(T, xt2, x2, t2);
 
     // ---- IMEX2 steps (efd.f90:388-454) --------------------------------------------------------------------------
+    // per-slot constants of the two spectral operators: z / (1 + i a) = z (1 - i a) / (1 + a^2) and (1 - i an)
+    const double ibx = 1.0 / bx, ibe = 1.0 / bx / eps;
+    double a_[S], rd_[S], an_[S];
+    EACH {
+        a_[j] = ds / 2.0 * T.lmode(j) / eps;
+        an_[j] = ds / eps / 2.0 * T.lmode(j);
+        rd_[j] = 1.0 / (1.0 + a_[j] * a_[j]);
+    }
     for (int istep = 0; istep < q.nstep; ++istep) {
-        force<P, S>(T, eps, bx, time, xt1, xt2, yt1, yt2, f1, f2);
+        force<P, S>(T, ibx, ibe, bx, time, xt1, xt2, yt1, yt2, f1, f2);
         EACH { r1[j] = yt1[j] + ds / 2.0 * f1[j]; r2[j] = yt2[j] + ds / 2.0 * f2[j]; }
         T.fwd(r1); T.fwd(r2);
-        EACH { const double a = ds / 2.0 * T.lmode(j) / eps; r1[j] = over_1pia(r1[j], a); r2[j] = over_1pia(r2[j], a); }
+        EACH { r1[j] = over_1pia(r1[j], a_[j], rd_[j]); r2[j] = over_1pia(r2[j], a_[j], rd_[j]); }
         T.inv(r1); T.inv(r2);                                                                // yt(tn+1/2)
         EACH {
-            t1[j] = xt1[j] + ds / 2.0 * ((T.ct(j) * r1[j] + T.st(j) * r2[j]) / bx);
-            t2[j] = xt2[j] + ds / 2.0 * ((T.ct(j) * r2[j] - T.st(j) * r1[j]) / bx);
+            t1[j] = xt1[j] + ds / 2.0 * ((T.ct(j) * r1[j] + T.st(j) * r2[j]) * ibx);
+            t2[j] = xt2[j] + ds / 2.0 * ((T.ct(j) * r2[j] - T.st(j) * r1[j]) * ibx);
         }
         T.fwd(t1); T.fwd(t2);
-        EACH { const double a = ds / 2.0 * T.lmode(j) / eps; t1[j] = over_1pia(t1[j], a); t2[j] = over_1pia(t2[j], a); }
+        EACH { t1[j] = over_1pia(t1[j], a_[j], rd_[j]); t2[j] = over_1pia(t2[j], a_[j], rd_[j]); }
         T.inv(t1); T.inv(t2);                                                                // xt(tn+1/2)
         time = time + q.dt / 2.0;
-        force<P, S>(T, eps, bx, time, t1, t2, r1, r2, f1, f2);
+        force<P, S>(T, ibx, ibe, bx, time, t1, t2, r1, r2, f1, f2);
         T.fwd(f1); T.fwd(f2);
         EACH { r1[j] = yt1[j]; r2[j] = yt2[j]; }
         T.fwd(r1); T.fwd(r2);
         EACH {
-            const double l = T.lmode(j);
-            const cd nm = mk(1.0, -(ds / eps / 2.0 * l));
-            const double a = ds / 2.0 * l / eps;
-            r1[j] = over_1pia(r1[j] * nm + ds * f1[j], a);
-            r2[j] = over_1pia(r2[j] * nm + ds * f2[j], a);
+            const cd nm = mk(1.0, -an_[j]);
+            r1[j] = over_1pia(r1[j] * nm + ds * f1[j], a_[j], rd_[j]);
+            r2[j] = over_1pia(r2[j] * nm + ds * f2[j], a_[j], rd_[j]);
         }
         T.inv(r1); T.inv(r2);                                                                // yt(tn+1)
         EACH {
-            const cd m1 = (r1[j] + yt1[j]) / 2.0, m2 = (r2[j] + yt2[j]) / 2.0;
+            const cd m1 = (r1[j] + yt1[j]) * 0.5, m2 = (r2[j] + yt2[j]) * 0.5;
             yt1[j] = r1[j]; yt2[j] = r2[j];
-            f1[j] = (T.ct(j) * m1 + T.st(j) * m2) / bx;
-            f2[j] = (T.ct(j) * m2 - T.st(j) * m1) / bx;
+            f1[j] = (T.ct(j) * m1 + T.st(j) * m2) * ibx;
+            f2[j] = (T.ct(j) * m2 - T.st(j) * m1) * ibx;
         }
         T.fwd(f1); T.fwd(f2);
         T.fwd(xt1); T.fwd(xt2);
         EACH {
-            const double l = T.lmode(j);
-            const cd nm = mk(1.0, -(ds / eps / 2.0 * l));
-            const double a = ds / 2.0 * l / eps;
-            xt1[j] = over_1pia(xt1[j] * nm + ds * f1[j], a);
-            xt2[j] = over_1pia(xt2[j] * nm + ds * f2[j], a);
+            const cd nm = mk(1.0, -an_[j]);
+            xt1[j] = over_1pia(xt1[j] * nm + ds * f1[j], a_[j], rd_[j]);
+            xt2[j] = over_1pia(xt2[j] * nm + ds * f2[j], a_[j], rd_[j]);
         }
         T.inv(xt1); T.inv(xt2);                                                              // xt(tn+1)
         time = time + q.dt / 2.0;
