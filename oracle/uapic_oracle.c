@@ -12,6 +12,8 @@
  *   - test/test_poisson.jl:28,47       (Poisson vs analytic, atol 1e-14)
  *   - test/test_particles.jl:45        (integral of rho ~ 0)
  *   - test/test_particles.jl:73-74     (M6 interpolation reproduces a linear field)
+ *   - efd.f90:481                      (the external-field program's printed sum(v), 13 digits: orc_efd_run below, run on
+ *                                       init_particles_2d's load regenerated from the libgfortran stream)
  * and an independently written numpy twin (oracle/uapic_oracle_np.py, following the Julia
  * sources) must agree with this file to <= 1e-12 (tests/test_oracle.py).
  *

@@ -21,6 +21,7 @@ export Session, upload_particles!, init_fields!, step!, step_host!, generate_par
 export STORE_FULL, STORE_HYBRID, STORE_ONEPASS, STORE_ONEPASS_LEAN, SCHEME_M6, SCHEME_CIC
 export nccl_unique_id, init_nccl!, sum_v, peer_handle, init_peers!, close_peers!
 export Mesh3D, Session3D, run_uapic3d!
+export efd, efd_run!
 export UAPICError
 
 const libuapic = get(ENV, "UAPIC_B200_LIB", joinpath(@__DIR__, "..", "..", "libuapic_b200.so"))
@@ -492,6 +493,44 @@ function run_uapic3d!(s::Session3D, x::Array{Float64,2}, v::Array{Float64,2}; Nm
     check(ccall((:uapic3d_run, libuapic), Cint, (Ptr{Cvoid}, Cint, Cint, Cdouble, Cint, Ref{Int64}), s.handle, Nmrc, Nmrcm, tfinal, 0, n))
     check(ccall((:uapic3d_download_particles, libuapic), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}), s.handle, x, v, C_NULL))
     n[]
+end
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the external-field program (fortran/efd.f90, test/test_efd.jl) -- uapic_efd_run, one kernel for all particles
+# ---------------------------------------------------------------------------------------------------------------------
+struct EfdConfig            # uapic_efd_config_t
+    ntau   :: Int32
+    nstep  :: Int32
+    eps    :: Float64
+    dt     :: Float64
+    tfinal :: Float64
+    xmin   :: Float64
+    xmax   :: Float64
+    ymin   :: Float64
+    ymax   :: Float64
+end
+
+# x, v :: Array{Float64,2}(2, nbpart), advanced in place to tfinal (efd.f90:133-478 over all particles)
+function efd_run!(x::Array{Float64,2}, v::Array{Float64,2}, mesh::Mesh; ntau = 16, eps = 1e-3, dt = π/2/2^3, tfinal = π/2, nstep = 0)
+    cfg = Ref(EfdConfig(ntau, nstep, eps, dt, tfinal, mesh.xmin, mesh.xmax, mesh.ymin, mesh.ymax))
+    check(ccall((:uapic_efd_run, libuapic), Cint, (Ref{EfdConfig}, Int64, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
+                cfg, size(x, 2), x, v, x, v))
+    x, v
+end
+
+# `efd(ntau, nbpart)` of test/test_efd.jl:8: the program with its own constants on the first nbpart particles of
+# particles.dat, then the M6 deposit; returns (particles, fields, the pair the program prints against efd.f90:481)
+function efd(ntau, nbpart; filename = "particles.dat", eps = 1e-3)
+    kx, ky = 0.5, 1.0
+    mesh = Mesh(0.0, 2π/kx, 128, 0.0, 2π/ky, 64)
+    f = MeshFields(mesh)
+    p = read_particles(filename, mesh)
+    x, v = p.x[:, 1:nbpart], p.v[:, 1:nbpart]
+    efd_run!(x, v, mesh; ntau = ntau, eps = eps)
+    p.x[:, 1:nbpart] .= x
+    p.v[:, 1:nbpart] .= v
+    compute_rho_m6!(f, p)
+    p, f, (sum(p.v[1, :]) + 857.95049281063064, sum(p.v[2, :]) + 593.40700170710875)
 end
 
 end # module
