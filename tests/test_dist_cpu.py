@@ -136,3 +136,29 @@ def test_gfortran_stream_reproduces_the_reference_seed():
     b = ub.plasma(mesh, 300, use_gfortran=True)
     assert np.array_equal(a.x, b.x) and np.array_equal(a.v, b.v)
     assert 0 <= a.x[0].min() and a.x[0].max() < 4 * np.pi
+
+
+def test_write_data_xdmf_dump(tmp_path):
+    """output.f90:10-110: fields-NNNN.xmf describing ex, ey, ez, rho on the (nx+1, ny+1, nz+1) nodes; heavy data beside it"""
+    import xml.etree.ElementTree as ET
+    mesh = ub.Mesh3D((0, 0, 0), (18, 18, 1), (6, 4, 2))
+    f = ub.Fields3D(mesh)
+    rng = np.random.default_rng(0)
+    f.e[...] = rng.normal(size=f.e.shape)
+    f.rho[...] = rng.normal(size=f.rho.shape)
+    path = ub.write_data(1, f, str(tmp_path))
+    assert path.endswith("fields-0001.xmf")
+    root = ET.parse(path).getroot()
+    grid = root.find("Domain/Grid")
+    assert grid.find("Topology").get("NumberOfElements").split() == ["3", "5", "7"]          # nz+1, ny+1, nx+1
+    geo = [list(map(float, d.text.split())) for d in grid.findall("Geometry/DataItem")]
+    assert geo == [[0.0, 0.0, 0.0], [3.0, 4.5, 0.5]]
+    raw = np.fromfile(tmp_path / "fields-0001.bin", dtype="<f8")
+    want = {"ex": f.e[0], "ey": f.e[1], "ez": f.e[2], "rho": f.rho}
+    for a in grid.findall("Attribute"):
+        item = a.find("DataItem")
+        off = int(item.get("Seek")) // 8
+        got = raw[off:off + f.rho.size].reshape(f.rho.shape, order="F")
+        assert item.text.strip() == "fields-0001.bin" and np.array_equal(got, want[a.get("Name")])
+    with pytest.raises(ValueError):
+        ub.write_data(10000, f, str(tmp_path))

@@ -13,6 +13,6 @@ from .loaders import landau_sampling, make_particles_dat, plasma, read_particles
 from .session import Session, run_bupdate  # noqa: F401
 from . import dist  # noqa: F401
 from . import mrc3d  # noqa: F401
-from .mrc3d import Fields3D, Mesh3D, Session3D, run_uapic3d  # noqa: F401
+from .mrc3d import Fields3D, Mesh3D, Session3D, run_uapic3d, write_data  # noqa: F401
 from . import external_field  # noqa: F401
 from .external_field import efd, efd_run, efd_run_device  # noqa: F401

@@ -76,6 +76,42 @@ def interpolate_eb_cic(x: np.ndarray, fields: Fields3D) -> np.ndarray:
     return ep
 
 
+def write_data(istep: int, fields: Fields3D, directory: str = ".") -> str:
+    """write_data(istep, fields)          output.f90:10-110 -- the field dump the three 3D programs make (uapic3d.f90:82,
+    test_pic_3d.f90:56, test_poisson_3d.f90:48): `fields-NNNN.xmf`, an XDMF 2.2 description of a 3DCoRectMesh with node
+    attributes ex, ey, ez, rho.  The reference keeps the heavy data in `fields-NNNN.h5`; no HDF5 library exists in this image,
+    so the arrays go to `fields-NNNN.bin` and the DataItems say Format='Binary' with a byte offset (little-endian doubles,
+    x fastest, exactly the bytes the HDF5 datasets would hold) -- ParaView / VisIt read both forms.  Host-side diagnostic;
+    returns the path of the .xmf file."""
+    import os
+    if not 0 <= istep < 10 ** 4:                          # int2string, output.f90:113-133
+        raise ValueError("istep must be in 0..9999")
+    name = f"fields-{istep:04d}"
+    m = fields.mesh
+    nx1, ny1, nz1 = m.node_shape
+    arrays = [("ex", fields.e[0]), ("ey", fields.e[1]), ("ez", fields.e[2]), ("rho", fields.rho)]
+    nbytes = 8 * nx1 * ny1 * nz1
+    with open(os.path.join(directory, name + ".bin"), "wb") as f:
+        for _, a in arrays:
+            f.write(np.asfortranarray(a, dtype="<f8").tobytes(order="F"))
+    dims = f"{nz1:5d}{ny1:5d}{nx1:5d}"
+    lines = ["<?xml version='1.0' ?>", "<!DOCTYPE Xdmf SYSTEM 'Xdmf.dtd' []>",
+             "<Xdmf xmlns:xi='http://www.w3.org/2003/XInclude' Version='2.2'>", "<Domain>", "<Grid Name='mesh' GridType='Uniform'>",
+             f"<Topology TopologyType='3DCoRectMesh' NumberOfElements='{dims}'/>", "<Geometry GeometryType='ORIGIN_DXDYDZ'>",
+             "<DataItem Dimensions='3' NumberType='Float' Format='XML'>", "".join(f"{c:12.5f}" for c in m.xmin), "</DataItem>",
+             "<DataItem Dimensions='3' NumberType='Float' Format='XML'>", "".join(f"{c:12.5f}" for c in m.d), "</DataItem>",
+             "</Geometry>"]
+    for k, (attr, _) in enumerate(arrays):
+        lines += [f"<Attribute Name='{attr}' AttributeType='Scalar' Center='Node'>",
+                  f"<DataItem Dimensions='{dims}' NumberType='Float' Precision='8' Format='Binary' Endian='Little' Seek='{k * nbytes}'>",
+                  name + ".bin", "</DataItem>", "</Attribute>"]
+    lines += ["</Grid>", "</Domain>", "</Xdmf>"]
+    path = os.path.join(directory, name + ".xmf")
+    with open(path, "w") as f:
+        f.write("\n".join(lines) + "\n")
+    return path
+
+
 class Session3D:
     """device-resident state of fortran/uapic3d.f90"""
 
