@@ -12,9 +12,9 @@ namespace uapic {
 struct cd { double re, im; };
 DEVINL cd mk(double r, double i) { cd z; z.re = r; z.im = i; return z; }
 DEVINL cd cmul(cd a, cd b) { return mk(a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re); }
+inline double efd_sin(double x) { return std::sin(x); }
+inline void efd_sincos(double x, double *s, double *c) { *s = std::sin(x); *c = std::cos(x); }
 }  // namespace uapic
-using std::cos;
-using std::sin;
 #include "../uapic.jl_b200/csrc/uapic_efd_body.cuh"
 
 namespace {
@@ -51,6 +51,8 @@ template <int N> struct HostTau {
     }
     void fwd(uapic::cd (&a)[N]) const { dft(a, true); }
     void inv(uapic::cd (&a)[N]) const { dft(a, false); }
+    void fwd2(uapic::cd (&a)[N], uapic::cd (&b)[N]) const { dft(a, true); dft(b, true); }
+    void inv2(uapic::cd (&a)[N], uapic::cd (&b)[N]) const { dft(a, false); dft(b, false); }
     uapic::cd first(const uapic::cd (&a)[N]) const { return a[0]; }
     uapic::cd sum(uapic::cd v) const { return v; }
 };

@@ -19,6 +19,18 @@
 //
 // Quantities the program computes and never uses (pl, ql, gx, ave2: efd.f90:143-149,275,283) are left out.
 #include "uapic_internal.h"
+
+namespace uapic {
+namespace {
+// Out-of-line transcendentals.  Every inlined fp64 sin / cos / sincos is ~60 instructions plus the slow-path call; the body has
+// about a hundred of them and, inlined, was larger than the SM's instruction cache several times over.
+struct sc2 { double s, c; };
+__device__ __noinline__ double efd_sin(double x) { return sin(x); }
+__device__ __noinline__ sc2 efd_sincos_ool(double x) { sc2 r; sincos(x, &r.s, &r.c); return r; }
+DEVINL void efd_sincos(double x, double *s, double *c) { const sc2 r = efd_sincos_ool(x); *s = r.s; *c = r.c; }
+}  // namespace
+}  // namespace uapic
+
 #include "uapic_efd_body.cuh"
 
 namespace uapic {
@@ -36,24 +48,108 @@ struct EfdArgs {
 };
 
 // ---- one tau sample per lane ------------------------------------------------------------------------------------
+// The butterflies are NOT inlined.  Inlined, the ~55 transforms of a particle made the kernel ~110 KB of SASS and the IMEX
+// loop alone larger than the 32 KB instruction cache of an SM: ncu showed 4.4 "no instruction" stall cycles per issued
+// instruction and the fp64 pipe at 37 % (profiles/r2g_efd_ncu_full.csv).  As two out-of-line functions that take both
+// components at once (fft_2d / ifft_2d of fft.f90:37-59; the two butterflies interleave), the loop body fits.
+struct cd2 { cd a, b; };
+
+template <int N> struct LaneFft {
+    static constexpr int LOG = Log2<N>::v;
+    // stage twiddles of lane j, written once per CTA by LaneTau::init: tw[s * N + j], s < LOG - 1
+    static __device__ __noinline__ cd2 fwd(cd a, cd b) {
+        extern __shared__ double2 efd_smem[];
+        const cd *tw = reinterpret_cast<const cd *>(efd_smem);
+        const int j = threadIdx.x & (N - 1);
+#pragma unroll
+        for (int s = 0; s < LOG; ++s) {
+            const int h = N >> (s + 1);
+            const cd oa = shfl_xor(a, h), ob = shfl_xor(b, h);
+            const double sg = (j & h) ? -1.0 : 1.0;
+            cd da = mk(fma(sg, a.re, oa.re), fma(sg, a.im, oa.im));      // upper: v+o ; lower: o-v
+            cd db = mk(fma(sg, b.re, ob.re), fma(sg, b.im, ob.im));
+            if (h > 1) { const cd w = tw[s * N + j]; da = cmul(da, w); db = cmul(db, w); }
+            a = da; b = db;
+        }
+        cd2 r;
+        r.a = rmul(1.0 / (double)N, a); r.b = rmul(1.0 / (double)N, b);       // fft.f90:44-59 carries 1/n
+        return r;
+    }
+    static __device__ __noinline__ cd2 inv(cd a, cd b) {
+        extern __shared__ double2 efd_smem[];
+        const cd *tw = reinterpret_cast<const cd *>(efd_smem);
+        const int j = threadIdx.x & (N - 1);
+#pragma unroll
+        for (int s = LOG - 1; s >= 0; --s) {
+            const int h = N >> (s + 1);
+            if (h > 1) { const cd w = tw[s * N + j]; a = cmulc(a, w); b = cmulc(b, w); }
+            const cd oa = shfl_xor(a, h), ob = shfl_xor(b, h);
+            const double sg = (j & h) ? -1.0 : 1.0;
+            a = mk(fma(sg, a.re, oa.re), fma(sg, a.im, oa.im));
+            b = mk(fma(sg, b.re, ob.re), fma(sg, b.im, ob.im));
+        }
+        cd2 r;
+        r.a = a; r.b = b;
+        return r;
+    }
+};
+
 template <int N> struct LaneTau {
     static constexpr int SPL = 1;
     static constexpr int kLanesPerParticle = N;
     static constexpr int kMinBlocks = 4;          // 128 registers: 16 warps per SM hide the shuffle and DFMA latencies of the butterflies
-    TauLane<N> L;
-    DEVINL void init(int, cd *) { L.init(threadIdx.x & 31); }
-    DEVINL bool leader() const { return L.j == 0; }
-    DEVINL double ct(int) const { return L.ct; }
-    DEVINL double st(int) const { return L.st; }
+    static constexpr int LOG = Log2<N>::v;
+    int j;
+    double c_, s_, lf_;
+    static size_t smem_bytes(int) { return sizeof(cd) * (size_t)N * (LOG > 1 ? LOG - 1 : 1); }
+    DEVINL void init(int, cd *smem) {
+        TauLane<N> L;
+        L.init(threadIdx.x & 31);
+        j = L.j; c_ = L.ct; s_ = L.st; lf_ = L.lf;
+        if (threadIdx.x < N) {
+#pragma unroll
+            for (int s = 0; s < LOG - 1; ++s) smem[s * N + j] = mk(L.twr[s], L.twi[s]);
+        }
+        __syncthreads();
+    }
+    DEVINL bool leader() const { return j == 0; }
+    DEVINL double ct(int) const { return c_; }
+    DEVINL double st(int) const { return s_; }
     DEVINL bool mode_live(int) const { return true; }
-    DEVINL double lmode(int) const { return L.lf; }
-    DEVINL void fwd(cd (&a)[1]) const { a[0] = rmul(1.0 / (double)N, fft_fwd<N>(a[0], L)); }      // fft.f90:61-72 (carries 1/n)
-    DEVINL void inv(cd (&a)[1]) const { a[0] = fft_bwd<N>(a[0], L); }                             // fft.f90:74-81
+    DEVINL double lmode(int) const { return lf_; }                        // Fourier slot of lane j is bitrev(j)
+    DEVINL void fwd2(cd (&a)[1], cd (&b)[1]) const { const cd2 r = LaneFft<N>::fwd(a[0], b[0]); a[0] = r.a; b[0] = r.b; }
+    DEVINL void inv2(cd (&a)[1], cd (&b)[1]) const { const cd2 r = LaneFft<N>::inv(a[0], b[0]); a[0] = r.a; b[0] = r.b; }
+    DEVINL void fwd(cd (&a)[1]) const { a[0] = LaneFft<N>::fwd(a[0], mk(0.0, 0.0)).a; }
     DEVINL cd first(const cd (&a)[1]) const { return group_bcast0<N>(a[0]); }                     // tau index 0 == Fourier slot 0
     DEVINL cd sum(cd v) const { return mk(group_sum<N>(v.re), group_sum<N>(v.im)); }
 };
 
 // ---- one warp per particle, R samples per lane ------------------------------------------------------------------
+// out of line for the same reason as LaneFft (inlined at ~110 call sites with R unrolled, WarpTau<8> was 2 MB of SASS)
+template <int R> __device__ __noinline__ void warp_dft(cd (&a)[R], cd *buf, const cd *tw, int N, int lane, bool forward) {
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < R; ++j) { const int n = lane + 32 * j; if (n < N) buf[n] = a[j]; }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+        const int k = lane + 32 * j;
+        cd acc = mk(0.0, 0.0);
+        if (k < N) {
+            int idx = 0;
+            for (int n = 0; n < N; ++n) {
+                cd w = tw[idx];
+                if (!forward) w.im = -w.im;
+                acc = cfma(buf[n], w, acc);
+                idx += k; if (idx >= N) idx -= N;
+            }
+            if (forward) acc = acc / (double)N;
+        }
+        a[j] = acc;
+    }
+    __syncwarp();
+}
+
 template <int R> struct WarpTau {
     static constexpr int SPL = R;
     static constexpr int kLanesPerParticle = 32;
@@ -80,31 +176,12 @@ template <int R> struct WarpTau {
     DEVINL double st(int j) const { return s_[j]; }
     DEVINL bool mode_live(int j) const { return lane + 32 * j < N; }
     DEVINL double lmode(int j) const { const int k = lane + 32 * j; return (double)(k < N / 2 ? k : k - N); }
-    DEVINL void dft(cd (&a)[R], bool forward) const {
-        __syncwarp();
-#pragma unroll
-        for (int j = 0; j < R; ++j) { const int n = lane + 32 * j; if (n < N) buf[n] = a[j]; }
-        __syncwarp();
-#pragma unroll
-        for (int j = 0; j < R; ++j) {
-            const int k = lane + 32 * j;
-            cd acc = mk(0.0, 0.0);
-            if (k < N) {
-                int idx = 0;
-                for (int n = 0; n < N; ++n) {
-                    cd w = tw[idx];
-                    if (!forward) w.im = -w.im;
-                    acc = cfma(buf[n], w, acc);
-                    idx += k; if (idx >= N) idx -= N;
-                }
-                if (forward) acc = acc / (double)N;
-            }
-            a[j] = acc;
-        }
-        __syncwarp();
-    }
+    DEVINL void dft(cd (&a)[R], bool forward) const { warp_dft<R>(a, buf, tw, N, lane, forward); }
+    static size_t smem_bytes(int ntau) { return sizeof(cd) * (size_t)ntau * (1 + kEfdBlock / 32); }
     DEVINL void fwd(cd (&a)[R]) const { dft(a, true); }
     DEVINL void inv(cd (&a)[R]) const { dft(a, false); }
+    DEVINL void fwd2(cd (&a)[R], cd (&b)[R]) const { dft(a, true); dft(b, true); }
+    DEVINL void inv2(cd (&a)[R], cd (&b)[R]) const { dft(a, false); dft(b, false); }
     DEVINL cd first(const cd (&a)[R]) const { return mk(__shfl_sync(kFull, a[0].re, 0), __shfl_sync(kFull, a[0].im, 0)); }
     DEVINL cd sum(cd v) const {
 #pragma unroll
@@ -130,7 +207,8 @@ template <class P> __global__ void __launch_bounds__(kEfdBlock, P::kMinBlocks) k
     }
 }
 
-template <class P> cudaError_t launch_one(const LaunchCtx &c, const EfdArgs &q, size_t smem) {
+template <class P> cudaError_t launch_one(const LaunchCtx &c, const EfdArgs &q) {
+    const size_t smem = P::smem_bytes(q.ntau);
     constexpr int per_block = kEfdBlock / P::kLanesPerParticle;
     const int64_t rounds = (q.np + per_block - 1) / per_block;
     int64_t grid = (int64_t)c.sm_count * 8;
@@ -154,18 +232,17 @@ cudaError_t launch_efd(const LaunchCtx &c, int ntau, double eps, double dt, doub
     q.x = reinterpret_cast<const double2 *>(x); q.v = reinterpret_cast<const double2 *>(v);
     q.xo = reinterpret_cast<double2 *>(x_out); q.vo = reinterpret_cast<double2 *>(v_out);
     switch (ntau) {
-        case 2: return launch_one<LaneTau<2>>(c, q, 0);
-        case 4: return launch_one<LaneTau<4>>(c, q, 0);
-        case 8: return launch_one<LaneTau<8>>(c, q, 0);
-        case 16: return launch_one<LaneTau<16>>(c, q, 0);
-        case 32: return launch_one<LaneTau<32>>(c, q, 0);
+        case 2: return launch_one<LaneTau<2>>(c, q);
+        case 4: return launch_one<LaneTau<4>>(c, q);
+        case 8: return launch_one<LaneTau<8>>(c, q);
+        case 16: return launch_one<LaneTau<16>>(c, q);
+        case 32: return launch_one<LaneTau<32>>(c, q);
         default: break;
     }
-    const size_t smem = sizeof(cd) * (size_t)ntau * (1 + kEfdBlock / 32);
-    if (ntau <= 32) return launch_one<WarpTau<1>>(c, q, smem);
-    if (ntau <= 64) return launch_one<WarpTau<2>>(c, q, smem);
-    if (ntau <= 128) return launch_one<WarpTau<4>>(c, q, smem);
-    return launch_one<WarpTau<8>>(c, q, smem);
+    if (ntau <= 32) return launch_one<WarpTau<1>>(c, q);
+    if (ntau <= 64) return launch_one<WarpTau<2>>(c, q);
+    if (ntau <= 128) return launch_one<WarpTau<4>>(c, q);
+    return launch_one<WarpTau<8>>(c, q);
 }
 
 }  // namespace uapic
