@@ -54,6 +54,90 @@ struct EfdArgs {
 // components at once (fft_2d / ifft_2d of fft.f90:37-59; the two butterflies interleave), the loop body fits.
 struct cd2 { cd a, b; };
 
+#ifndef UAPIC_EFD_TW_REGS
+#define UAPIC_EFD_TW_REGS 0     // 0: stage twiddles read from a per-CTA shared-memory table; 1: passed in registers (measured 4.8 % slower: 128 registers + spills, profiles/r2k2_efd_twiddle_ab.log)
+#endif
+#if UAPIC_EFD_TW_REGS
+struct Tw4 { double r[4], i[4]; };     // stage twiddles of this lane (stage s <-> half-size N >> (s+1)); unused stages 1, 0
+
+template <int N> struct LaneFft {
+    static constexpr int LOG = Log2<N>::v;
+    // twiddles travel in registers (by value): as LDS.128 from a per-CTA table they were a quarter of the kernel's L1 data-pipe
+    // wavefronts, the unit this kernel is bound by once the instruction fetch is out of the way (profiles/r2h_efd_ncu_full.csv)
+    static __device__ __noinline__ cd2 fwd(cd a, cd b, double w0r, double w0i, double w1r, double w1i, double w2r, double w2i,
+                                           double w3r, double w3i) {
+        const double wr[4] = {w0r, w1r, w2r, w3r}, wi[4] = {w0i, w1i, w2i, w3i};
+        const int j = threadIdx.x & (N - 1);
+#pragma unroll
+        for (int s = 0; s < LOG; ++s) {
+            const int h = N >> (s + 1);
+            const cd oa = shfl_xor(a, h), ob = shfl_xor(b, h);
+            const double sg = (j & h) ? -1.0 : 1.0;
+            cd da = mk(fma(sg, a.re, oa.re), fma(sg, a.im, oa.im));      // upper: v+o ; lower: o-v
+            cd db = mk(fma(sg, b.re, ob.re), fma(sg, b.im, ob.im));
+            if (h > 1) { const cd w = mk(wr[s], wi[s]); da = cmul(da, w); db = cmul(db, w); }
+            a = da; b = db;
+        }
+        cd2 r;
+        r.a = rmul(1.0 / (double)N, a); r.b = rmul(1.0 / (double)N, b);       // fft.f90:44-59 carries 1/n
+        return r;
+    }
+    static __device__ __noinline__ cd2 inv(cd a, cd b, double w0r, double w0i, double w1r, double w1i, double w2r, double w2i,
+                                           double w3r, double w3i) {
+        const double wr[4] = {w0r, w1r, w2r, w3r}, wi[4] = {w0i, w1i, w2i, w3i};
+        const int j = threadIdx.x & (N - 1);
+#pragma unroll
+        for (int s = LOG - 1; s >= 0; --s) {
+            const int h = N >> (s + 1);
+            if (h > 1) { const cd w = mk(wr[s], wi[s]); a = cmulc(a, w); b = cmulc(b, w); }
+            const cd oa = shfl_xor(a, h), ob = shfl_xor(b, h);
+            const double sg = (j & h) ? -1.0 : 1.0;
+            a = mk(fma(sg, a.re, oa.re), fma(sg, a.im, oa.im));
+            b = mk(fma(sg, b.re, ob.re), fma(sg, b.im, ob.im));
+        }
+        cd2 r;
+        r.a = a; r.b = b;
+        return r;
+    }
+};
+
+template <int N> struct LaneTau {
+    static constexpr int SPL = 1;
+    static constexpr int kLanesPerParticle = N;
+    static constexpr int kMinBlocks = 4;          // 128 registers: 16 warps per SM hide the shuffle and DFMA latencies of the butterflies
+    static constexpr int LOG = Log2<N>::v;
+    int j;
+    double c_, s_, lf_;
+    Tw4 w;
+    static size_t smem_bytes(int) { return 0; }
+    DEVINL void init(int, cd *) {
+        TauLane<N> L;
+        L.init(threadIdx.x & 31);
+        j = L.j; c_ = L.ct; s_ = L.st; lf_ = L.lf;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) { w.r[s] = (s < LOG - 1) ? L.twr[s] : 1.0; w.i[s] = (s < LOG - 1) ? L.twi[s] : 0.0; }
+    }
+    DEVINL bool leader() const { return j == 0; }
+    DEVINL double ct(int) const { return c_; }
+    DEVINL double st(int) const { return s_; }
+    DEVINL bool mode_live(int) const { return true; }
+    DEVINL double lmode(int) const { return lf_; }                        // Fourier slot of lane j is bitrev(j)
+    DEVINL void fwd2(cd (&a)[1], cd (&b)[1]) const {
+        const cd2 r = LaneFft<N>::fwd(a[0], b[0], w.r[0], w.i[0], w.r[1], w.i[1], w.r[2], w.i[2], w.r[3], w.i[3]);
+        a[0] = r.a; b[0] = r.b;
+    }
+    DEVINL void inv2(cd (&a)[1], cd (&b)[1]) const {
+        const cd2 r = LaneFft<N>::inv(a[0], b[0], w.r[0], w.i[0], w.r[1], w.i[1], w.r[2], w.i[2], w.r[3], w.i[3]);
+        a[0] = r.a; b[0] = r.b;
+    }
+    DEVINL void fwd(cd (&a)[1]) const {
+        a[0] = LaneFft<N>::fwd(a[0], mk(0.0, 0.0), w.r[0], w.i[0], w.r[1], w.i[1], w.r[2], w.i[2], w.r[3], w.i[3]).a;
+    }
+    DEVINL cd first(const cd (&a)[1]) const { return group_bcast0<N>(a[0]); }                     // tau index 0 == Fourier slot 0
+    DEVINL cd sum(cd v) const { return mk(group_sum<N>(v.re), group_sum<N>(v.im)); }
+};
+
+#else
 template <int N> struct LaneFft {
     static constexpr int LOG = Log2<N>::v;
     // stage twiddles of lane j, written once per CTA by LaneTau::init: tw[s * N + j], s < LOG - 1
@@ -125,6 +209,8 @@ template <int N> struct LaneTau {
 };
 
 // ---- one warp per particle, R samples per lane ------------------------------------------------------------------
+#endif
+
 // out of line for the same reason as LaneFft (inlined at ~110 call sites with R unrolled, WarpTau<8> was 2 MB of SASS)
 template <int R> __device__ __noinline__ void warp_dft(cd (&a)[R], cd *buf, const cd *tw, int N, int lane, bool forward) {
     __syncwarp();
