@@ -93,6 +93,13 @@ int uapic_compute_rho_m6(const uapic_mesh_t *mesh, int64_t nbpart, double *x, do
    e (2,nx+1,ny+1) in, ep (2,nbpart) out; x rewritten only for UAPIC_WRAP_JULIA. */
 int uapic_interpol_eb_m6(const uapic_mesh_t *mesh, const double *e, int64_t nbpart, double *x, double *ep, int wrap);
 
+/* The same two stages with the bilinear (CIC) shape of UAPIC_SCHEME_CIC -- build-defined: the reference has no 2D CIC deposit
+   (SURVEY.md 2.4); weights of performance/test_cic.F90:73-76 = the 2D restriction of compute_rho_cic.f90:46-53, with the wrap,
+   ghost copy, 1/(dx dy) and neutralisation of the M6 routines.  Same arguments as the M6 entry points. */
+int uapic_compute_rho_cic(const uapic_mesh_t *mesh, int64_t nbpart, double *x, double w, double *rho,
+                          int wrap, int deposit_mode, double *rho_total);
+int uapic_interpol_eb_cic(const uapic_mesh_t *mesh, const double *e, int64_t nbpart, double *x, double *ep, int wrap);
+
 /* (p::Poisson)(fields)                          src/poisson.jl:62-83, poisson_2d.f90:85-111
    rho (nx+1,ny+1) in, e (2,nx+1,ny+1) out, *energy = sum(e1^2+e2^2)*dx*dy over the ghosted array. */
 int uapic_poisson(const uapic_mesh_t *mesh, const double *rho, double *e, double *energy);

@@ -281,3 +281,40 @@ def test_bad_arguments_fail_loudly():
     f = ub.MeshFields(ub.Mesh(0, 1, 1030, 0, 1, 8))
     with pytest.raises(ub.UapicError):
         ub.Poisson(f.mesh)(f)
+
+
+@pytest.mark.parametrize("nx,ny,wrap", [(128, 64, ub.WRAP_FORTRAN), (20, 12, ub.WRAP_JULIA)])
+def test_cic_stage_entry_points_vs_oracle(corc, nx, ny, wrap):
+    """uapic_compute_rho_cic / uapic_interpol_eb_cic (build-defined bilinear shape, include/uapic_b200.h) against the oracle in
+    its CIC mode; a linear field is reproduced exactly by bilinear interpolation (the check test/test_particles.jl:52-74 makes for M6)"""
+    mesh, om = _mesh_pair(nx, ny)
+    rng = np.random.default_rng(nx + ny)
+    n = 20000
+    p = ub.Particles(n, (mesh.xmax - mesh.xmin) * (mesh.ymax - mesh.ymin) / n)
+    p.x[0], p.x[1] = rng.uniform(-1, 1, n) * 3 * (mesh.xmax - mesh.xmin), rng.uniform(-1, 1, n) * 3 * (mesh.ymax - mesh.ymin)
+    f = ub.MeshFields(mesh)
+    f.e[:] = rng.standard_normal(f.e.shape)
+    f.e[:, nx, :], f.e[:, :, ny] = f.e[:, 0, :], f.e[:, :, 0]             # periodic ghosts, as every solve leaves them
+    f.e[:, nx, ny] = f.e[:, 0, 0]
+    corc.set_scheme("cic")
+    try:
+        xo, rho_o, ep_o = p.x.copy(order="F"), np.zeros_like(f.rho, order="F"), np.zeros_like(p.e, order="F")
+        tot_o = corc.compute_rho_m6(om, xo, p.w, rho_o, wrap=wrap)
+        xo2 = p.x.copy(order="F")
+        corc.interpol_eb_m6(om, f.e, xo2, ep_o, wrap=wrap)
+    finally:
+        corc.set_scheme("m6")
+    x0 = p.x.copy(order="F")
+    tot = ub.compute_rho_cic(f, p, wrap=wrap)
+    assert np.abs(f.rho - rho_o).max() < 1e-12 * max(1.0, np.abs(rho_o).max()) and abs(tot - tot_o) < 1e-9 * abs(tot_o)
+    assert np.abs(p.x - xo).max() < 1e-12 * (mesh.xmax - mesh.xmin)        # the wrap convention's effect on x, as the oracle
+    p.x[:] = x0
+    ub.interpol_eb_cic(p, f, wrap=wrap)
+    assert np.abs(p.e - ep_o).max() < 1e-13 * np.abs(ep_o).max()
+    # bilinear interpolation reproduces a field that is linear inside every cell
+    q = ub.Particles(500, 1.0)
+    q.x[0], q.x[1] = rng.uniform(0.05, 0.9, 500) * (mesh.xmax - mesh.xmin), rng.uniform(0.05, 0.9, 500) * (mesh.ymax - mesh.ymin)
+    for i in range(nx + 1):
+        f.e[0, i, :], f.e[1, i, :] = i * mesh.dx, np.arange(ny + 1) * mesh.dy
+    ub.interpol_eb_cic(q, f, wrap=ub.WRAP_FORTRAN)
+    assert np.abs(q.e - q.x).max() < 1e-12

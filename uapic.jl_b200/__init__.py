@@ -6,8 +6,8 @@ All compute happens in `libuapic_b200.so` (hand-written sm_100a CUDA).  There is
 """
 from ._lib import (DEPOSIT_FIXED_POINT, DEPOSIT_FP64_ATOMIC, LIB_PATH, SCHEME_CIC, SCHEME_M6, STORE_FULL, STORE_HYBRID,  # noqa: F401
                    STORE_ONEPASS, STORE_ONEPASS_LEAN, WRAP_FORTRAN, WRAP_JULIA, EXPORTS, UapicError, device_count, lib, probe_fp64_peak)
-from .api import (UA, Mesh, MeshFields, Particles, Poisson, compute_f, compute_rho_m6, compute_v, errors, fft_tau,  # noqa: F401
-                  gnuplot, ifft_tau, integrate, interpol_eb_m6, preparation, ua_step, ua_step1, ua_step2, update_particles_e,
+from .api import (UA, Mesh, MeshFields, Particles, Poisson, compute_f, compute_rho_cic, compute_rho_m6, compute_v, errors, fft_tau,  # noqa: F401
+                  gnuplot, ifft_tau, integrate, interpol_eb_cic, interpol_eb_m6, preparation, ua_step, ua_step1, ua_step2, update_particles_e,
                   update_particles_x)
 from .loaders import landau_sampling, make_particles_dat, plasma, read_particles, write_particles  # noqa: F401
 from .session import Session, run_bupdate  # noqa: F401

@@ -37,7 +37,7 @@ EXPORTS = [
     "uapic3d_create", "uapic3d_destroy", "uapic3d_init_nccl", "uapic3d_upload_particles", "uapic3d_generate_particles", "uapic3d_init_fields", "uapic3d_substep",
     "uapic3d_run", "uapic3d_download_particles", "uapic3d_download_fields", "uapic3d_launch_count", "uapic3d_compute_rho_cic",
     "uapic3d_poisson", "uapic3d_interpolate_eb_cic",
-    "uapic_efd_run", "uapic_efd_run_device",
+    "uapic_efd_run", "uapic_efd_run_device", "uapic_compute_rho_cic", "uapic_interpol_eb_cic",
 ]
 
 

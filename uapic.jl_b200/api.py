@@ -155,6 +155,22 @@ def interpol_eb_m6(*args, wrap=_lib.WRAP_JULIA):
         raise TypeError("interpol_eb_m6(particles, fields) or interpol_eb_m6(e, fields, x, nbpart, ntau)")
 
 
+def compute_rho_cic(fields: MeshFields, particles: Particles, wrap=_lib.WRAP_JULIA, deposit_mode=_lib.DEPOSIT_FP64_ATOMIC):
+    """the plain deposit with the bilinear shape of SCHEME_CIC (build-defined, include/uapic_b200.h); returns rho_total"""
+    ms = fields.mesh._struct()
+    tot = C.c_double(0.0)
+    check(lib().uapic_compute_rho_cic(C.byref(ms), C.c_int64(particles.nbpart), _ptr(_f64(particles.x)), C.c_double(particles.w),
+                                      _ptr(_f64(fields.rho)), C.c_int(wrap), C.c_int(deposit_mode), C.byref(tot)))
+    return tot.value
+
+
+def interpol_eb_cic(particles: Particles, fields: MeshFields, wrap=_lib.WRAP_JULIA):
+    """the plain gather with the bilinear shape of SCHEME_CIC (build-defined)"""
+    ms = fields.mesh._struct()
+    check(lib().uapic_interpol_eb_cic(C.byref(ms), _ptr(_f64(fields.e)), C.c_int64(particles.nbpart), _ptr(_f64(particles.x)),
+                                      _ptr(_f64(particles.e)), C.c_int(wrap)))
+
+
 def preparation(ua: UA, dt: float, particles: Particles, xt, yt):
     """preparation!(ua, dt, particles, xt, yt)     src/ua_steps.jl:3-78"""
     n = particles.nbpart

@@ -224,10 +224,10 @@ int uapic_probe_fp64_peak(int device, int launches, double *dfma_per_s, double *
 
 // ---- stage API ---------------------------------------------------------------------------------------------
 
-int uapic_compute_rho_m6(const uapic_mesh_t *mesh, int64_t nbpart, double *x, double w, double *rho, int wrap,
-                         int deposit_mode, double *rho_total) {
+static int compute_rho_stage(const uapic_mesh_t *mesh, int64_t nbpart, double *x, double w, double *rho, int wrap,
+                             int deposit_mode, double *rho_total, int scheme) {
     TRY(check_mesh(mesh));
-    if (!x || !rho || nbpart < 0) return fail(UAPIC_EINVAL, "uapic_compute_rho_m6: null pointer or negative nbpart");
+    if (!x || !rho || nbpart < 0) return fail(UAPIC_EINVAL, "uapic_compute_rho: null pointer or negative nbpart");
     STAGE_BEGIN();
     const MeshDev m = make_mesh(mesh);
     const size_t nrho = (size_t)m.ld * (m.ny + 1);
@@ -237,7 +237,7 @@ int uapic_compute_rho_m6(const uapic_mesh_t *mesh, int64_t nbpart, double *x, do
     TRY(raw.init(m, deposit_mode, m.dimx * m.dimy > w * (double)nbpart ? m.dimx * m.dimy : w * (double)nbpart, 0));
     CU(drho.alloc(nrho * 8));
     CU(dtot.alloc(8));
-    CU(launch_deposit(sc.lc, m, nbpart, dx.as<double>(), w, raw.acc, wrap));
+    CU(launch_deposit(sc.lc, m, nbpart, dx.as<double>(), w, raw.acc, wrap, scheme));
     CU(launch_rho_epilogue(sc.lc, m, raw.acc, drho.as<double>(), dtot.as<double>()));
     CU(cudaDeviceSynchronize());
     TRY(down(rho, drho, nrho * 8));
@@ -246,9 +246,19 @@ int uapic_compute_rho_m6(const uapic_mesh_t *mesh, int64_t nbpart, double *x, do
     return UAPIC_OK;
 }
 
-int uapic_interpol_eb_m6(const uapic_mesh_t *mesh, const double *e, int64_t nbpart, double *x, double *ep, int wrap) {
+int uapic_compute_rho_m6(const uapic_mesh_t *mesh, int64_t nbpart, double *x, double w, double *rho, int wrap,
+                         int deposit_mode, double *rho_total) {
+    return compute_rho_stage(mesh, nbpart, x, w, rho, wrap, deposit_mode, rho_total, UAPIC_SCHEME_M6);
+}
+
+int uapic_compute_rho_cic(const uapic_mesh_t *mesh, int64_t nbpart, double *x, double w, double *rho, int wrap,
+                          int deposit_mode, double *rho_total) {
+    return compute_rho_stage(mesh, nbpart, x, w, rho, wrap, deposit_mode, rho_total, UAPIC_SCHEME_CIC);
+}
+
+static int interpol_eb_stage(const uapic_mesh_t *mesh, const double *e, int64_t nbpart, double *x, double *ep, int wrap, int scheme) {
     TRY(check_mesh(mesh));
-    if (!e || !x || !ep || nbpart < 0) return fail(UAPIC_EINVAL, "uapic_interpol_eb_m6: null pointer or negative nbpart");
+    if (!e || !x || !ep || nbpart < 0) return fail(UAPIC_EINVAL, "uapic_interpol_eb: null pointer or negative nbpart");
     STAGE_BEGIN();
     const MeshDev m = make_mesh(mesh);
     const size_t nrho = (size_t)m.ld * (m.ny + 1);
@@ -256,11 +266,19 @@ int uapic_interpol_eb_m6(const uapic_mesh_t *mesh, const double *e, int64_t nbpa
     TRY(up(de, e, nrho * 16));
     TRY(up(dx, x, sizeof(double) * 2 * (size_t)nbpart));
     CU(dep.alloc(sizeof(double) * 2 * (size_t)nbpart));
-    CU(launch_gather(sc.lc, m, de.as<double>(), nbpart, dx.as<double>(), dep.as<double>(), wrap));
+    CU(launch_gather(sc.lc, m, de.as<double>(), nbpart, dx.as<double>(), dep.as<double>(), wrap, scheme));
     CU(cudaDeviceSynchronize());
     TRY(down(ep, dep, sizeof(double) * 2 * (size_t)nbpart));
     if (wrap == UAPIC_WRAP_JULIA) TRY(down(x, dx, sizeof(double) * 2 * (size_t)nbpart));
     return UAPIC_OK;
+}
+
+int uapic_interpol_eb_m6(const uapic_mesh_t *mesh, const double *e, int64_t nbpart, double *x, double *ep, int wrap) {
+    return interpol_eb_stage(mesh, e, nbpart, x, ep, wrap, UAPIC_SCHEME_M6);
+}
+
+int uapic_interpol_eb_cic(const uapic_mesh_t *mesh, const double *e, int64_t nbpart, double *x, double *ep, int wrap) {
+    return interpol_eb_stage(mesh, e, nbpart, x, ep, wrap, UAPIC_SCHEME_CIC);
 }
 
 int uapic_poisson(const uapic_mesh_t *mesh, const double *rho, double *e, double *energy) {
