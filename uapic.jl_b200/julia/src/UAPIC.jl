@@ -13,7 +13,7 @@ module UAPIC
 
 export Mesh, MeshFields, Particle, Particles, UA, Poisson
 export read_particles, plasma, landau_sampling
-export compute_rho_m6!, interpol_eb_m6!
+export compute_rho_m6!, interpol_eb_m6!, compute_rho_cic!, interpol_eb_cic!
 export preparation!, update_particles_e!, update_particles_x!, compute_f!, ua_step!, compute_v!
 export fft_tau!, ifft_tau!
 export integrate, gnuplot, errors
@@ -167,6 +167,22 @@ end
 
 function interpol_eb_m6!(particles::Particles, fields::MeshFields)
     check(ccall((:uapic_interpol_eb_m6, libuapic), Cint,
+                (Ref{CMesh}, Ptr{Cdouble}, Int64, Ptr{Cdouble}, Ptr{Cdouble}, Cint),
+                CMesh(fields.mesh), fields.e, particles.nbpart, particles.x, particles.e, WRAP_JULIA))
+    nothing
+end
+
+# the same two stages with the bilinear shape of SCHEME_CIC (build-defined: the reference has no 2D CIC deposit)
+function compute_rho_cic!(fields::MeshFields, particles::Particles; deposit_mode = DEPOSIT_FP64_ATOMIC)
+    tot = Ref{Cdouble}(0.0)
+    check(ccall((:uapic_compute_rho_cic, libuapic), Cint,
+                (Ref{CMesh}, Int64, Ptr{Cdouble}, Cdouble, Ptr{Cdouble}, Cint, Cint, Ref{Cdouble}),
+                CMesh(fields.mesh), particles.nbpart, particles.x, particles.w, fields.ρ, WRAP_JULIA, deposit_mode, tot))
+    tot[]
+end
+
+function interpol_eb_cic!(particles::Particles, fields::MeshFields)
+    check(ccall((:uapic_interpol_eb_cic, libuapic), Cint,
                 (Ref{CMesh}, Ptr{Cdouble}, Int64, Ptr{Cdouble}, Ptr{Cdouble}, Cint),
                 CMesh(fields.mesh), fields.e, particles.nbpart, particles.x, particles.e, WRAP_JULIA))
     nothing
