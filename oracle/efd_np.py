@@ -23,17 +23,22 @@ def _ifft(a):
     return np.fft.ifft(a, axis=1) * a.shape[1]
 
 
-def efd_run(x, v, ntau=16, eps=1e-3, dt=np.pi / 16, tfinal=np.pi / 2, box=(0.0, 4 * np.pi, 0.0, 2 * np.pi), stages=None):
-    """x, v: (2, np).  Returns (x, v) at tfinal.  `stages`, if a dict, receives ave, xt, yt after the preparation."""
-    x1, x2, v1, v2 = (np.asarray(a, dtype=np.float64)[:, None] for a in (x[0], x[1], v[0], v[1]))
-    nstep = int(round(tfinal / dt))                                                  # efd.f90:102
+def efd_run(x, v, ntau=16, eps=1e-3, dt=np.pi / 16, tfinal=np.pi / 2, box=(0.0, 4 * np.pi, 0.0, 2 * np.pi), stages=None,
+            real=np.float64):
+    """x, v: (2, np).  Returns (x, v) at tfinal.  `stages`, if a dict, receives ave, xt, yt after the preparation.
+    `real=np.longdouble` evaluates the same formulas in x87 extended precision (64-bit mantissa, numpy's FFT included) from the
+    same double inputs: the REFEREE the double implementations are ranked against (tests/test_efd_oracle.py, test_gpu_efd.py)."""
+    x1, x2, v1, v2 = (np.asarray(a, dtype=np.float64).astype(real)[:, None] for a in (x[0], x[1], v[0], v[1]))
+    eps, dt, tfinal = real(eps), real(dt), real(tfinal)
+    pi = real(np.pi) if real is np.float64 else 4 * np.arctan(real(1))
+    nstep = int(round(float(tfinal / dt)))                                           # efd.f90:102
     m = ntau // 2
-    ltau = np.concatenate([np.arange(0, m), np.arange(-m, 0)]).astype(np.float64)[None, :]   # efd.f90:111-112
-    tau = (np.arange(ntau) * (2 * np.pi / ntau))[None, :]
+    ltau = np.concatenate([np.arange(0, m), np.arange(-m, 0)]).astype(real)[None, :]   # efd.f90:111-112
+    tau = (np.arange(ntau).astype(real) * (2 * pi / ntau))[None, :]
     c, s = np.cos(tau), np.sin(tau)
     inv = np.zeros_like(ltau)
     inv[0, 1:] = 1.0 / ltau[0, 1:]
-    time = 0.0
+    time = real(0)
     bx = 1 + 0.5 * np.sin(x1) * np.sin(x2)                                           # efd.f90:139
     ds = dt * bx
 
@@ -122,7 +127,7 @@ def efd_run(x, v, ntau=16, eps=1e-3, dt=np.pi / 16, tfinal=np.pi / 2, box=(0.0, 
     # efd.f90:456-478, 526-544
     ph = np.exp(1j * ltau * tfinal * bx / eps)
     xo = np.stack([(_fft(xt1) * ph).sum(1).real, (_fft(xt2) * ph).sum(1).real])
-    for d, (lo, hi) in enumerate(((box[0], box[1]), (box[2], box[3]))):
+    for d, (lo, hi) in enumerate(((real(box[0]), real(box[1])), (real(box[2]), real(box[3])))):
         span = hi - lo
         for _ in range(64):
             over, under = xo[d] > hi, xo[d] < lo

@@ -68,3 +68,18 @@ def test_two_restatements_agree(ntau):
         xc, vc = oracle.corc().efd_run(x, v, ntau=ntau, eps=eps)
         xn, vn = oracle.efd_np.efd_run(x, v, ntau=ntau, eps=eps)
         assert np.abs(vc - vn).max() < 1e-10 and np.abs(xc - xn).max() < 1e-10
+
+
+@pytest.mark.parametrize("eps", [1e-1, 1e-2, 1e-3, 1e-4])
+def test_extended_precision_referee_ranks_the_restatements(eps):
+    """the same formulas in x87 long double (numpy's FFT included) from the same double inputs: both double restatements sit
+    within the conditioning of the map -- one input ulp moves v by ~1e-12 * 0.1/eps -- of the exact evaluation"""
+    rng = np.random.default_rng(3)
+    n = 1000
+    x = np.asfortranarray(rng.random((2, n)) * [[4 * np.pi], [2 * np.pi]])
+    v = np.asfortranarray(rng.normal(size=(2, n)) * 2)
+    xr, vr = oracle.efd_np.efd_run(x, v, eps=eps, real=np.longdouble)
+    assert xr.dtype == np.longdouble
+    bound = 1e-12 * max(1.0, 0.1 / eps) * float(np.abs(vr).max())
+    for xo, vo in (oracle.corc().efd_run(x, v, eps=eps), oracle.efd_np.efd_run(x, v, eps=eps)):
+        assert float(np.abs(xo - xr).max()) < 1e-12 and float(np.abs(vo - vr).max()) < bound

@@ -58,6 +58,20 @@ def test_vs_numpy_restatement_other_parameters():
     assert np.abs(vg2 - vg).max() > 1e-6
 
 
+@pytest.mark.parametrize("eps", [1e-1, 1e-3, 1e-4])
+def test_vs_extended_precision_referee(corc, eps):
+    """against the formulas evaluated in long double (oracle/efd_np.py, real=np.longdouble): the kernel must be as close to the
+    exact evaluation as the C restatement is (within 10x), and inside the conditioning bound"""
+    x, v = _load(2000, 21)
+    xg, vg = ub.efd_run(x, v, eps=eps)
+    xr, vr = oracle.efd_np.efd_run(x, v, eps=eps, real=np.longdouble)
+    xo, vo = corc.efd_run(x, v, eps=eps)
+    d_gpu, d_orc = float(np.abs(vg - vr).max()), float(np.abs(vo - vr).max())
+    assert d_gpu < 1e-12 * max(1.0, 0.1 / eps) * float(np.abs(vr).max())
+    assert d_gpu < 10 * max(d_orc, 1e-14)
+    assert float(np.abs(xg - xr).max()) < 1e-12
+
+
 def test_reference_program_reproduces_the_printed_constants():
     """the whole program on the reference's own load: the two numbers efd.f90:481 prints must vanish"""
     mesh = ub.Mesh(0, DIMX, 128, 0, DIMY, 64)
