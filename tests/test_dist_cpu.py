@@ -162,3 +162,43 @@ def test_write_data_xdmf_dump(tmp_path):
         assert item.text.strip() == "fields-0001.bin" and np.array_equal(got, want[a.get("Name")])
     with pytest.raises(ValueError):
         ub.write_data(10000, f, str(tmp_path))
+
+
+def test_plasma3d_consumes_the_gfortran_stream_in_the_reference_order():
+    """fortran/particles.F90:107-190 (init_particles_3d): the vectorised loader must hand out exactly the particles a
+    one-deviate-at-a-time loop over the same libgfortran stream produces"""
+    import ctypes as C
+    from importlib import import_module
+    n = 700
+    x, v, src = ub.plasma3d((0, 0, 0), (18, 18, 1), n, use_gfortran=True, return_source=True)
+    if "libgfortran" not in src:
+        pytest.skip("libgfortran not loadable here")
+    u = import_module(ub.plasma.__module__)._Uniforms(None, True)
+    u.gf._gfortran_random_r8.argtypes = [C.POINTER(C.c_double)]
+    tmp = C.c_double()
+
+    def rn():
+        u.gf._gfortran_random_r8(C.byref(tmp))
+        return tmp.value
+
+    xs, vs = np.zeros((3, n), order="F"), np.zeros((3, n), order="F")
+    for m in range(n):
+        for c in range(3):
+            xs[c, m] = rn()
+    m = 0
+    while m < n:
+        xi, yi, zi = 9.0 * rn(), 2.0 * np.pi * rn(), 1.02 * rn()
+        if (1.0 + 0.02 * np.cos(4.0 * yi)) * np.exp(-5.0 * (xi - 4.8) ** 2) >= zi:
+            xs[0, m], xs[1, m] = np.cos(yi) * xi + 9.0, np.sin(yi) * xi + 9.0
+            m += 1
+    m = 0
+    while m < n:
+        xi, yi, wi, zi = (rn() - 0.5) * 8.0, (rn() - 0.5) * 8.0, (rn() - 0.5) * 8.0, rn()
+        if np.exp(-2.0 * (xi ** 2 + yi ** 2 + wi ** 2)) >= zi:
+            vs[:, m] = xi, yi, wi
+            m += 1
+    assert np.array_equal(x, xs) and np.array_equal(v, vs)
+    # densities with a seeded numpy stream: ring of radius ~4.8 around (9, 9), <v_i^2> = 1/4
+    xb, vb = ub.plasma3d((0, 0, 0), (18, 18, 1), 50000, seed=5)
+    r = np.hypot(xb[0] - 9.0, xb[1] - 9.0)
+    assert abs(r.mean() - 4.8) < 0.02 and np.abs((vb ** 2).mean(axis=1) - 0.25).max() < 0.01 and 0 <= xb[2].min() and xb[2].max() < 1

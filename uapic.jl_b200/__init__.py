@@ -9,7 +9,7 @@ from ._lib import (DEPOSIT_FIXED_POINT, DEPOSIT_FP64_ATOMIC, LIB_PATH, SCHEME_CI
 from .api import (UA, Mesh, MeshFields, Particles, Poisson, compute_f, compute_rho_cic, compute_rho_m6, compute_v, errors, fft_tau,  # noqa: F401
                   gnuplot, ifft_tau, integrate, interpol_eb_cic, interpol_eb_m6, preparation, ua_step, ua_step1, ua_step2, update_particles_e,
                   update_particles_x)
-from .loaders import landau_sampling, make_particles_dat, plasma, read_particles, write_particles  # noqa: F401
+from .loaders import landau_sampling, make_particles_dat, plasma, plasma3d, read_particles, write_particles  # noqa: F401
 from .session import Session, run_bupdate  # noqa: F401
 from . import dist  # noqa: F401
 from . import mrc3d  # noqa: F401

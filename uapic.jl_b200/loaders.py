@@ -2,6 +2,7 @@
 
     read_particles / write_particles     src/read_particles.jl:3-35  (one line per particle: ix iy dpx dpy vx vy)
     plasma                               src/plasma.jl:3-52, fortran/particles.F90:21-105 (rejection sampling)
+    plasma3d                             fortran/particles.F90:107-190 (init_particles_3d, the 3D programs' load)
     landau_sampling                      the intent of src/landau.jl:5-47 (that file references undefined names)
 
 `test/particles.dat` is missing from the reference checkout (.MISSING_LARGE_BLOBS), so `make_particles_dat`
@@ -148,6 +149,49 @@ def plasma(mesh: Mesh, nbpart: int, seed=None, alpha=0.05, kx=0.5, use_gfortran=
     if return_source:
         return p, u.source
     return p
+
+
+def plasma3d(xmin, xmax, nbpart: int, seed=None, use_gfortran=False, return_source=False):
+    """init_particles_3d, fortran/particles.F90:107-190 (the load of uapic3d.f90 and test_pic_3d.f90): `random_number` on the
+    whole (3, nbpart) position array first (z keeps it, scaled into the box), then x, y by rejection from the ring density
+    (1 + 0.02 cos 4 theta) exp(-5 (r - 4.8)^2) around (9, 9) -- three deviates per trial -- then v from exp(-2 |v|^2) on
+    [-4, 4]^3 -- four deviates per trial (0.4 % accepted).  Deviates are consumed strictly in the reference's order; with
+    `use_gfortran` the stream is libgfortran's under the seed of particles.F90:142-151, i.e. the Fortran program's own particles.
+    Returns x, v as Fortran-ordered (3, nbpart) arrays."""
+    u = _Uniforms(seed, use_gfortran)
+    x = np.zeros((3, nbpart), order="F")
+    v = np.zeros((3, nbpart), order="F")
+    x[:] = u.take(3 * nbpart).reshape((3, nbpart), order="F")                      # :153
+    x[2] = xmin[2] + (xmax[2] - xmin[2]) * x[2]                                    # :154
+
+    def fill(trial, width, rate, rows, target):
+        k = 0
+        while k < nbpart:
+            n = min(max(1024, int((nbpart - k) * 1.1 / rate)), 1 << 22)
+            d = u.take(width * n).reshape(n, width)
+            vals, ok = trial(d)
+            idx = np.flatnonzero(ok)
+            if idx.size > nbpart - k:           # the loop ends at this trial: the later ones were never drawn
+                idx = idx[:nbpart - k]
+                u.give_back(width * (n - 1 - int(idx[-1])))
+            for r, a in zip(rows, vals):
+                target[r, k:k + idx.size] = a[idx]
+            k += idx.size
+
+    def trial_x(d):                              # :156-170
+        xi, yi, zi = 9.0 * d[:, 0], 2.0 * np.pi * d[:, 1], (1.0 + 0.02) * d[:, 2]
+        temm = (1.0 + 0.02 * np.cos(4.0 * yi)) * np.exp(-5.0 * (xi - 4.8) ** 2)
+        return (np.cos(yi) * xi + 9.0, np.sin(yi) * xi + 9.0), temm >= zi
+
+    def trial_v(d):                              # :172-188
+        xi, yi, wi, zi = (d[:, 0] - 0.5) * 8.0, (d[:, 1] - 0.5) * 8.0, (d[:, 2] - 0.5) * 8.0, d[:, 3]
+        return (xi, yi, wi), np.exp(-2.0 * (xi ** 2 + yi ** 2 + wi ** 2)) >= zi
+
+    fill(trial_x, 3, np.sqrt(np.pi / 5.0) / 9.0 / 1.02, (0, 1), x)
+    fill(trial_v, 4, (np.pi / 2.0) ** 1.5 / 512.0, (0, 1, 2), v)
+    if return_source:
+        return x, v, u.source
+    return x, v
 
 
 def landau_sampling(mesh: Mesh, nbpart: int, seed=20190102, alpha=0.05, kx=0.5):
