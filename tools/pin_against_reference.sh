@@ -36,4 +36,12 @@ python "$HERE/pin/pin_io.py" inputs "$WORK" | while read -r name; do
         julia --project="$REF" "$HERE/pin/pin_julia.jl" "$REF" "$WORK/$name.in" "$WORK/$name.julia.out" > "$WORK/$name.julia.log" 2>&1 || echo "julia run of $name failed (see $WORK/$name.julia.log)"
     fi
 done
+# 6. the external-field program: the reference's efd.f90 with its debug truncation lifted IN A TEMPORARY COPY (particle loop over
+#    all particles, the mid-way `stop` and the per-particle prints dropped) -- it then prints sum(v) + the constants of its
+#    line 481, which must vanish, and so must `python -c "import uapic_b200 as u; print(u.efd(16)[2])"` on a B200.
+sed -e 's/^do m=1,1!nbpart/do m=1,nbpart/' -e '/^    stop$/d' -e '/^    print\*,/d' "$REF/fortran/efd.f90" > "$WORK/efd_all_particles.f90"
+$FC $FFLAGS -c "$REF/fortran/fft.f90" -o "$WORK/fft.o"
+$FC $FFLAGS "$WORK/efd_all_particles.f90" "$WORK"/{fft,meshfields,particles,compute_rho_m6}.o $FFTW_LIB -o "$WORK/efd_all" \
+    && { echo "reference efd.f90 over all particles: sum(v) + printed constants (expect ~1e-10):"; "$WORK/efd_all" | tail -1; } \
+    || echo "efd.f90 did not build here (it needs only fft.f90, meshfields, particles, compute_rho_m6 and FFTW)"
 python "$HERE/pin/pin_io.py" compare "$WORK"
