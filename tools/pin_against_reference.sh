@@ -42,6 +42,6 @@ done
 sed -e 's/^do m=1,1!nbpart/do m=1,nbpart/' -e '/^    stop$/d' -e '/^    print\*,/d' "$REF/fortran/efd.f90" > "$WORK/efd_all_particles.f90"
 $FC $FFLAGS -c "$REF/fortran/fft.f90" -o "$WORK/fft.o"
 $FC $FFLAGS "$WORK/efd_all_particles.f90" "$WORK"/{fft,meshfields,particles,compute_rho_m6}.o $FFTW_LIB -o "$WORK/efd_all" \
-    && { echo "reference efd.f90 over all particles: sum(v) + printed constants (expect ~1e-10):"; "$WORK/efd_all" | tail -1; } \
+    && { echo "reference efd.f90 over all particles: sum(v) + printed constants (expect ~1e-10):"; "$WORK/efd_all" | tail -2; } \
     || echo "efd.f90 did not build here (it needs only fft.f90, meshfields, particles, compute_rho_m6 and FFTW)"
 python "$HERE/pin/pin_io.py" compare "$WORK"
