@@ -18,6 +18,8 @@
 // uapic_generic.cu).  One body serves both through a small policy type.
 //
 // Quantities the program computes and never uses (pl, ql, gx, ave2: efd.f90:143-149,275,283) are left out.
+#include <cstdlib>
+
 #include "uapic_internal.h"
 
 namespace uapic {
@@ -38,6 +40,7 @@ namespace uapic {
 namespace {
 
 constexpr int kEfdBlock = 128;
+constexpr bool kEfdSpl2Default = false;   // two tau samples per lane (LaneTau2) instead of one; UAPIC_EFD_SPL2=0/1 overrides
 
 struct EfdArgs {
     EfdScalars s;
@@ -211,6 +214,61 @@ template <int N> struct LaneTau {
 // ---- one warp per particle, R samples per lane ------------------------------------------------------------------
 #endif
 
+#if !UAPIC_EFD_TW_REGS
+// ---- two tau samples per lane (N >= 4): lane j of the N/2 lanes of a particle holds samples j and j + N/2 -------------------
+// The first butterfly stage of the length-N transform stays inside the thread (its twiddle exp(-2 pi i j / N) is the lane's own
+// (cos tau_j, -sin tau_j)); the two half-length transforms that follow run across the N/2 lanes for both slots at once.  Slot 0
+// then holds the even mode 2 bitrev(j), slot 1 the odd mode 2 bitrev(j) + 1.  Per particle and transform pair this is 12 + 4 L1
+// data-pipe wavefronts (shuffles + twiddle loads) instead of 16 + 6, the unit the kernel is bound by; selected at run time with
+// UAPIC_EFD_SPL2 (uapic_efd.cu, launch_efd).
+template <int N> struct LaneTau2 {
+    static constexpr int SPL = 2;
+    static constexpr int M = N / 2;
+    static constexpr int kLanesPerParticle = M;
+    static constexpr int kMinBlocks = 3;
+    static constexpr int LOG = Log2<M>::v;
+    int j;
+    double c_, s_, l0_, l1_;
+    static size_t smem_bytes(int) { return sizeof(cd) * (size_t)M * (LOG > 1 ? LOG - 1 : 1); }
+    DEVINL void init(int, cd *smem) {
+        TauLane<M> L;                              // lane constants of the half-length transform
+        L.init(threadIdx.x & 31);
+        j = L.j;
+        sincospi(2.0 * (double)j / (double)N, &s_, &c_);
+        const int k0 = 2 * L.k, k1 = 2 * L.k + 1;
+        l0_ = (double)(k0 < N / 2 ? k0 : k0 - N);
+        l1_ = (double)(k1 < N / 2 ? k1 : k1 - N);
+        if (threadIdx.x < M) {
+#pragma unroll
+            for (int s = 0; s < LOG - 1; ++s) smem[s * M + j] = mk(L.twr[s], L.twi[s]);
+        }
+        __syncthreads();
+    }
+    DEVINL bool leader() const { return j == 0; }
+    DEVINL double ct(int q) const { return q ? -c_ : c_; }                // tau_{j + N/2} = tau_j + pi
+    DEVINL double st(int q) const { return q ? -s_ : s_; }
+    DEVINL bool mode_live(int) const { return true; }
+    DEVINL double lmode(int q) const { return q ? l1_ : l0_; }
+    // forward, carrying 1/N: in-thread stage (with 1/2), then the half-length transform (which carries 1/M)
+    DEVINL void split(cd (&a)[2]) const {
+        const cd u = mk(0.5 * (a[0].re + a[1].re), 0.5 * (a[0].im + a[1].im));
+        const cd d = mk(0.5 * (a[0].re - a[1].re), 0.5 * (a[0].im - a[1].im));
+        a[0] = u; a[1] = cmul(d, mk(c_, -s_));
+    }
+    DEVINL void join(cd (&a)[2]) const {
+        const cd t = cmul(a[1], mk(c_, s_));
+        const cd u = a[0];
+        a[0] = mk(u.re + t.re, u.im + t.im); a[1] = mk(u.re - t.re, u.im - t.im);
+    }
+    DEVINL void fwd(cd (&a)[2]) const { split(a); const cd2 r = LaneFft<M>::fwd(a[0], a[1]); a[0] = r.a; a[1] = r.b; }
+    DEVINL void fwd2(cd (&a)[2], cd (&b)[2]) const { fwd(a); fwd(b); }
+    DEVINL void inv1(cd (&a)[2]) const { const cd2 r = LaneFft<M>::inv(a[0], a[1]); a[0] = r.a; a[1] = r.b; join(a); }
+    DEVINL void inv2(cd (&a)[2], cd (&b)[2]) const { inv1(a); inv1(b); }
+    DEVINL cd first(const cd (&a)[2]) const { return group_bcast0<M>(a[0]); }    // tau index 0 and mode 0 are both slot 0 of lane 0
+    DEVINL cd sum(cd v) const { return mk(group_sum<M>(v.re), group_sum<M>(v.im)); }
+};
+#endif
+
 // out of line for the same reason as LaneFft (inlined at ~110 call sites with R unrolled, WarpTau<8> was 2 MB of SASS)
 template <int R> __device__ __noinline__ void warp_dft(cd (&a)[R], cd *buf, const cd *tw, int N, int lane, bool forward) {
     __syncwarp();
@@ -317,6 +375,18 @@ cudaError_t launch_efd(const LaunchCtx &c, int ntau, double eps, double dt, doub
     q.s.xmin = box[0]; q.s.xmax = box[1]; q.s.ymin = box[2]; q.s.ymax = box[3];
     q.x = reinterpret_cast<const double2 *>(x); q.v = reinterpret_cast<const double2 *>(v);
     q.xo = reinterpret_cast<double2 *>(x_out); q.vo = reinterpret_cast<double2 *>(v_out);
+#if !UAPIC_EFD_TW_REGS
+    static const bool spl2 = [] { const char *e = getenv("UAPIC_EFD_SPL2"); return e ? atoi(e) != 0 : kEfdSpl2Default; }();
+    if (spl2) {
+        switch (ntau) {
+            case 4: return launch_one<LaneTau2<4>>(c, q);
+            case 8: return launch_one<LaneTau2<8>>(c, q);
+            case 16: return launch_one<LaneTau2<16>>(c, q);
+            case 32: return launch_one<LaneTau2<32>>(c, q);
+            default: break;
+        }
+    }
+#endif
     switch (ntau) {
         case 2: return launch_one<LaneTau<2>>(c, q);
         case 4: return launch_one<LaneTau<4>>(c, q);
