@@ -11,7 +11,8 @@
 // this is the text behind that `stop` over all particles -- the computation that produced the constants of efd.f90:481,
 // which the oracle reproduces to 13 digits from init_particles_2d's own load (tests/test_efd_oracle.py).
 //
-// Mapping.  Power-of-two ntau <= 32: one tau sample per lane, ntau lanes per particle, the length-ntau transforms as
+// Mapping.  Power-of-two ntau <= 32: one tau sample per lane, ntau lanes per particle (LaneTau) -- or, the default for
+// ntau >= 4, two samples per lane on ntau/2 lanes (LaneTau2, first butterfly stage inside the thread) --, the transforms as
 // shuffle butterflies (TauLane / fft_fwd / fft_bwd of uapic_device.cuh; Fourier slots live bit-reversed, which every
 // spectral operation here -- diagonal multipliers, mode 0, sums over all modes -- is indifferent to).  Any other even
 // ntau <= 256: one warp per particle, samples strided over the lanes, direct DFTs out of shared memory (as
