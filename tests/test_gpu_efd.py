@@ -129,3 +129,33 @@ def test_edge_cases_and_errors():
             ub.efd_run(x, v, **bad)
     with pytest.raises(ValueError):
         ub.efd_run(np.zeros((3, 4)), np.zeros((3, 4)))
+
+
+def test_one_sample_per_lane_policy(corc):
+    """the library picks the tau policy once per process (UAPIC_EFD_SPL2, default: two samples per lane); the other lane policy is
+    held to the same oracle in a child process"""
+    import json
+    import os
+    import subprocess
+    import sys
+    x, v = _load(333, 17)
+    code = ("import sys, json, numpy as np; sys.path.insert(0, %r); import uapic_b200 as ub; "
+            "d = np.load(sys.argv[1]); out = {}\n"
+            "for ntau in (4, 8, 16, 32):\n"
+            "    xg, vg = ub.efd_run(d['x'], d['v'], ntau=ntau)\n"
+            "    out[str(ntau)] = [xg.tolist(), vg.tolist()]\n"
+            "print('RESULT' + json.dumps(out))") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "load.npz")
+        np.savez(path, x=x, v=v)
+        env = dict(os.environ, UAPIC_EFD_SPL2="0")
+        r = subprocess.run([sys.executable, "-c", code, path], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = json.loads([line for line in r.stdout.splitlines() if line.startswith("RESULT")][-1][6:])
+    for ntau in (4, 8, 16, 32):
+        xo, vo = corc.efd_run(x, v, ntau=ntau)
+        xg, vg = (np.array(a) for a in out[str(ntau)])
+        _close(xg, vg, xo, vo)
+        x2, v2 = ub.efd_run(x, v, ntau=ntau)                      # this process: the default policy
+        _close(x2, v2, xo, vo)
