@@ -211,8 +211,6 @@ template <int N> struct LaneTau {
     DEVINL cd first(const cd (&a)[1]) const { return group_bcast0<N>(a[0]); }                     // tau index 0 == Fourier slot 0
     DEVINL cd sum(cd v) const { return mk(group_sum<N>(v.re), group_sum<N>(v.im)); }
 };
-
-// ---- one warp per particle, R samples per lane ------------------------------------------------------------------
 #endif
 
 #if !UAPIC_EFD_TW_REGS
@@ -270,7 +268,8 @@ template <int N> struct LaneTau2 {
 };
 #endif
 
-// out of line for the same reason as LaneFft (inlined at ~110 call sites with R unrolled, WarpTau<8> was 2 MB of SASS)
+// ---- one warp per particle, R samples per lane ------------------------------------------------------------------
+// the DFT is out of line for the same reason as LaneFft (inlined at ~110 call sites with R unrolled, WarpTau<8> was 2 MB of SASS)
 template <int R> __device__ __noinline__ void warp_dft(cd (&a)[R], cd *buf, const cd *tw, int N, int lane, bool forward) {
     __syncwarp();
 #pragma unroll
